@@ -1,0 +1,348 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+
+CPU restatement (torch-CPU + scipy + the C library in this directory) of
+FastPoseCNN's post-network pose-recovery path.  Each function cites the
+reference lines it follows (paths relative to
+``/root/reference/source_code/FastPoseCNN/``).  The op *sequence* is kept the
+same as the reference wherever the float bits depend on it (torch ``norm``,
+``sum``, ``matmul``, ``pinverse``, ``inverse``), so that on one machine this
+port and the imported reference agree bit for bit; that agreement is what
+``tests/test_oracle_vs_reference.py`` and the fixtures under ``tests/golden/``
+pin (the reference ships no golden vectors of its own -- SURVEY.md section 4).
+
+Nothing under ``fastposecnn_b200/`` imports this module.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import scipy.ndimage
+import torch
+
+from . import native
+
+# lib/aggregation_layer.py:43-59 -- centre plane is the 2-D cross, the two outer
+# planes are empty: 4-connectivity inside an image, nothing across images.
+LABEL_STRUCTURE = np.zeros((3, 3, 3), dtype=bool)
+LABEL_STRUCTURE[1] = [[0, 1, 0], [1, 1, 1], [0, 1, 0]]
+
+
+# ----------------------------------------------------------------------------
+# lib/gpu_tensor_funcs.py
+# ----------------------------------------------------------------------------
+
+def normalize(data: torch.Tensor, dim: int) -> torch.Tensor:
+    """gpu_tensor_funcs.py:37-50 -- L2 normalise with a zero-norm -> 1 guard."""
+    n = data.norm(dim=dim, keepdim=True)
+    one = torch.tensor(1.0, device=n.device).float()
+    return data / torch.where(n != 0, n.float(), one)
+
+
+def categorical_mask(mask_logits: torch.Tensor) -> torch.Tensor:
+    """lib/pose_regressor.py:449 -- argmax over classes of the log-softmax."""
+    return torch.argmax(torch.nn.LogSoftmax(dim=1)(mask_logits), dim=1)
+
+
+def class_compress(num_of_classes: int, cat_mask: torch.Tensor, logits: Dict[str, torch.Tensor]):
+    """gpu_tensor_funcs.py:52-99 -- keep, per pixel, the channels of the predicted class."""
+    b, h, w = cat_mask.shape
+    onehot = torch.zeros((b, num_of_classes, h, w), device=cat_mask.device)
+    onehot = onehot.scatter(1, cat_mask.unsqueeze(1), 1)[:, 1:]            # :64-65 (bg dropped)
+    sel = onehot.unsqueeze(2).bool()
+    out = {}
+    for key, head in logits.items():
+        if key == "mask":
+            continue
+        per_class = torch.stack(torch.chunk(head, num_of_classes - 1, dim=1), dim=1)   # :68
+        picked = torch.where(sel, per_class.double(), 0.0).float()                     # :78-82
+        val = picked.sum(dim=1)                                                        # :85
+        if key == "z":
+            val = val.squeeze(1)                                                       # :89-90
+        elif key in ("quaternion", "xy"):
+            val = normalize(val, dim=1)                                                # :93-94
+        out[key] = val
+    return out
+
+
+def class_compression(logits: Dict[str, torch.Tensor], num_of_classes: int):
+    """lib/pose_regressor.py:445-457 (``Model.class_compression``)."""
+    cat_mask = categorical_mask(logits["mask"])
+    cat = class_compress(num_of_classes, cat_mask, logits)
+    cat["mask"] = cat_mask
+    return cat
+
+
+def quats_2_rotation_matrix(q: torch.Tensor) -> torch.Tensor:
+    """gpu_tensor_funcs.py:306-326 (note the final transpose)."""
+    a, b, c, d = q.unbind(dim=-1)
+    aa, bb, cc, dd = torch.pow(a, 2), torch.pow(b, 2), torch.pow(c, 2), torch.pow(d, 2)
+    m = torch.zeros((q.shape[0], 3, 3), device=q.device, dtype=q.dtype)
+    m[:, 0, 0] = aa - bb - cc + dd
+    m[:, 0, 1] = 2 * (a * b + c * d)
+    m[:, 0, 2] = 2 * (a * c - b * d)
+    m[:, 1, 0] = 2 * (a * b - c * d)
+    m[:, 1, 1] = -aa + bb - cc + dd
+    m[:, 1, 2] = 2 * (b * c + a * d)
+    m[:, 2, 0] = 2 * (a * c + b * d)
+    m[:, 2, 1] = 2 * (b * c - a * d)
+    m[:, 2, 2] = -aa - bb + cc + dd
+    return m.transpose(-2, -1)
+
+
+def batchwise_get_RT(q, xys, exp_zs, inv_intrinsics):
+    """gpu_tensor_funcs.py:204-235."""
+    proj = xys * (exp_zs / 1000)
+    homo = torch.vstack([proj.T, exp_zs.T / 1000])
+    T = inv_intrinsics @ homo
+    n = q.norm(dim=1)
+    q = q / torch.where(n > 0, n, torch.ones_like(n)).unsqueeze(1)
+    R = quats_2_rotation_matrix(q)
+    inv_R = torch.inverse(R)
+    bottom = torch.tensor([0, 0, 0, 1], device=q.device, dtype=q.dtype).expand((q.shape[0], 1, 4))
+    inv_RT = torch.cat([torch.cat([inv_R, T.T.unsqueeze(-1)], dim=-1), bottom], dim=1)
+    RT = torch.inverse(inv_RT)
+    return R, T.t(), RT
+
+
+def samplewise_get_RT(agg, inv_intrinsics):
+    """gpu_tensor_funcs.py:237-253."""
+    agg["R"], agg["T"], agg["RT"] = batchwise_get_RT(agg["quaternion"], agg["xy"], agg["z"], inv_intrinsics)
+    return agg
+
+
+# ----------------------------------------------------------------------------
+# lib/aggregation_layer.py
+# ----------------------------------------------------------------------------
+
+def label_instances(fg: torch.Tensor):
+    """aggregation_layer.py:160-183 (CPU branch :174-181): scipy.ndimage.label on
+    the [b,h,w] volume with LABEL_STRUCTURE.  Returns (int32 labels, total)."""
+    lab, total = scipy.ndimage.label(np.asarray(fg), structure=LABEL_STRUCTURE)
+    return torch.from_numpy(lab), int(total)
+
+
+def aggregate(cat: Dict[str, torch.Tensor]):
+    """aggregation_layer.py:61-158 (``AggregationLayer.forward``)."""
+    cat_mask = cat["mask"]
+    labels, total = label_instances(cat_mask != 0)                                      # :76
+    b, h, w = cat_mask.shape
+    class_ids: List[torch.Tensor] = []
+    planes_all: List[torch.Tensor] = []
+    sample_ids: List[torch.Tensor] = []
+    for bi in range(b):                                                                 # :87
+        n_here = (torch.unique(labels[bi]) != 0).sum()                                  # :90
+        sample_ids.append(torch.ones((n_here,), dtype=torch.int64) * bi)                # :91-98
+        planes = torch.zeros((total + 1, h, w))
+        planes = planes.scatter(0, labels[bi].unsqueeze(0).type(torch.int64), 1)[1:]    # :101-102
+        planes = planes[planes.sum(dim=(-2, -1)) != 0]                                  # :105
+        planes_all.append(planes)
+        per_inst = cat_mask[bi].unsqueeze(0) * planes.bool()                            # :111
+        try:
+            cls = torch.stack([torch.unique(x)[1] for x in torch.unbind(per_inst)])     # :113
+        except RuntimeError:
+            cls = torch.empty((0,))                                                     # :115
+        class_ids.append(cls)
+    out = {
+        "class_ids": torch.cat(class_ids, dim=0),
+        "instance_masks": torch.cat(planes_all, dim=0),
+        "sample_ids": torch.cat(sample_ids, dim=0),
+    }
+    masks = out["instance_masks"]
+    for key in ("quaternion", "scales", "xy", "z"):                                     # :125
+        per_inst = cat[key][out["sample_ids"]]                                          # :128
+        if key == "z":
+            per_inst = per_inst.unsqueeze(1)
+        masked = masks.unsqueeze(1) * per_inst                                          # :135
+        if key == "xy":
+            out[key] = masked                                                           # :152-153
+            continue
+        tot = masked.sum(dim=(-2, -1))                                                  # :139
+        size = masks.sum(dim=(-2, -1))
+        val = torch.div(tot, size.unsqueeze(1))                                         # :141 (mask_size.T on 1-D is a no-op)
+        if key == "z":
+            val = torch.exp(val)                                                        # :145
+        elif key == "quaternion":
+            val = normalize(val, dim=1)                                                 # :149
+        out[key] = val
+    return out
+
+
+# ----------------------------------------------------------------------------
+# lib/ransac_voting_gpu_layer/ransac_voting_gpu.py
+# ----------------------------------------------------------------------------
+
+def b_inv(m: torch.Tensor) -> torch.Tensor:
+    """ransac_voting_gpu.py:503-516.  ``torch.solve`` no longer exists (torch>=2),
+    so the reference always lands in its ``except RuntimeError`` arm: pinverse."""
+    return torch.pinverse(m)
+
+
+IdxSource = Callable[[int, int, int, int], torch.Tensor]   # (instance, hn, vn, tn) -> int32 [hn,vn,2]
+
+
+def seeded_idx_source(seed: int = 1234) -> IdxSource:
+    """Fixed pre-sampled pixel pairs: one CPU generator, drawn in instance order,
+    only for instances that reach the sampling line (tn >= min_num), exactly where
+    the reference calls ``random_(0, tn)`` (ransac_voting_gpu.py:552)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def draw(_i, hn, vn, tn):
+        return torch.randint(0, tn, (hn, vn, 2), generator=g, dtype=torch.int32)
+    return draw
+
+
+def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=30000, *, idx_source: Optional[IdxSource] = None,
+                           select_masks: Optional[Dict[int, torch.Tensor]] = None,
+                           details: Optional[list] = None, kernels=None):
+    """ransac_voting_gpu.py:518-607.
+
+    ``idx_source`` replaces the in-place ``random_`` draw; ``select_masks[i]`` replaces the
+    Bernoulli sub-sampling mask of instance ``i`` when it has more than ``max_num`` pixels.
+    ``details`` (a list) receives one dict per instance with hypotheses, counts and winner.
+    """
+    rv = kernels or native.ransac_voting
+    if idx_source is None:
+        idx_source = seeded_idx_source()
+    n, h, w, vn, _ = vertex.shape
+    results = []
+    for i in range(n):
+        cur = mask[i].bool()                                                    # :532
+        fg = torch.sum(cur)
+        if fg < min_num:                                                        # :536-539
+            results.append(torch.zeros([1, vn, 2], dtype=torch.float32))
+            if details is not None:
+                details.append({"tn": int(fg), "skipped": True})
+            continue
+        if fg > max_num:                                                        # :542-545
+            if select_masks is not None and i in select_masks:
+                keep = select_masks[i].bool()
+            else:
+                u = torch.zeros(cur.shape, dtype=torch.float32).uniform_(0, 1)
+                keep = u < (max_num / fg.float())
+            cur = cur * keep
+        coords = torch.nonzero(cur).float()[:, [1, 0]]                          # :547-548  (x=col, y=row)
+        direct = vertex[i].masked_select(cur.unsqueeze(2).unsqueeze(3))         # :549
+        direct = direct.view([coords.shape[0], vn, 2])
+        tn = coords.shape[0]
+        idxs = idx_source(i, round_hyp_num, vn, tn).contiguous()                # :552
+        best_ratio = torch.zeros([vn], dtype=torch.float32)
+        best_pts = torch.zeros([vn, 2], dtype=torch.float32)
+        hyp_num, it = 0, 0
+        while True:                                                             # :557-581
+            hyp = rv.generate_hypothesis(direct, coords, idxs)
+            inl = torch.zeros([round_hyp_num, vn, tn], dtype=torch.uint8)
+            rv.voting_for_hypothesis(direct, coords, hyp, inl, inlier_thresh)
+            counts = torch.sum(inl, 2)
+            win_counts, win_idx = torch.max(counts, 0)
+            win_pts = hyp[win_idx, torch.arange(vn)]
+            ratio = win_counts.float() / tn
+            better = best_ratio < ratio
+            best_pts[better, :] = win_pts[better, :]
+            best_ratio[better] = ratio[better]
+            if details is not None and it == 0:
+                details.append({"tn": tn, "skipped": False, "hyp": hyp.clone(), "counts": counts.clone(),
+                                "win_idx": win_idx.clone(), "win_counts": win_counts.clone(),
+                                "idxs": idxs.clone()})
+            hyp_num += round_hyp_num
+            it += 1
+            lo = torch.min(best_ratio)
+            if (1 - (1 - lo ** 2) ** hyp_num) > confidence or it > max_iter:
+                break
+        normal = torch.zeros_like(direct)                                       # :584-586
+        normal[:, :, 0] = direct[:, :, 1]
+        normal[:, :, 1] = -direct[:, :, 0]
+        final_inl = torch.zeros([1, vn, tn], dtype=torch.uint8)
+        rv.voting_for_hypothesis(direct, coords, best_pts.unsqueeze(0).contiguous(), final_inl, inlier_thresh)
+        wgt = final_inl.float().squeeze(0)                                      # [vn,tn]
+        nrm = normal.permute(1, 0, 2) * wgt.unsqueeze(2)                        # :592-593
+        bb = torch.sum(nrm * coords.unsqueeze(0), 2)                            # :595
+        ata = torch.matmul(nrm.permute(0, 2, 1), nrm)                           # :596
+        atb = torch.sum(nrm * bb.unsqueeze(2), 1)                               # :597
+        refined = torch.matmul(b_inv(ata), atb.unsqueeze(2))                    # :598
+        if details is not None:
+            details[-1].update({"best_pts": best_pts.clone(), "refine_inliers": int(wgt.sum())})
+        results.append(refined[None, :, :, 0])
+    if not results:
+        return torch.empty((0, vn, 2))
+    return torch.cat(results)
+
+
+def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99,
+                        max_iter=20, min_num=5, max_num=30000, *, idx_source: Optional[IdxSource] = None,
+                        kernels=None):
+    """ransac_voting_gpu.py:11-98 (v1: per image, per class id, no refinement)."""
+    rv = kernels or native.ransac_voting
+    if idx_source is None:
+        idx_source = seeded_idx_source()
+    b, h, w, vn, _ = vertex.shape
+    per_image = []
+    problem = 0
+    for bi in range(b):
+        per_class = []
+        hyp_num = 0                                   # :26 -- NOT reset per class in the reference
+        for k in range(class_num - 1):
+            cur = mask[bi] == k + 1
+            fg = torch.sum(cur)
+            if fg < min_num:
+                per_class.append(torch.zeros([1, vn, 2], dtype=torch.float32))
+                problem += 1
+                continue
+            if fg > max_num:
+                u = torch.zeros(cur.shape, dtype=torch.float32).uniform_(0, 1)
+                cur = cur * (u < (max_num / fg.float()))
+            coords = torch.nonzero(cur).float()[:, [1, 0]]
+            direct = vertex[bi].masked_select(cur.unsqueeze(2).unsqueeze(3)).view([coords.shape[0], vn, 2])
+            tn = coords.shape[0]
+            idxs = idx_source(problem, round_hyp_num, vn, tn).contiguous()
+            problem += 1
+            best_ratio = torch.zeros([vn], dtype=torch.float32)
+            best_pts = torch.zeros([vn, 2], dtype=torch.float32)
+            it = 0
+            while True:
+                hyp = rv.generate_hypothesis(direct, coords, idxs)
+                inl = torch.zeros([round_hyp_num, vn, tn], dtype=torch.uint8)
+                rv.voting_for_hypothesis(direct, coords, hyp, inl, inlier_thresh)
+                counts = torch.sum(inl, 2)
+                win_counts, win_idx = torch.max(counts, 0)
+                win_pts = hyp[win_idx, torch.arange(vn)]
+                ratio = win_counts.float() / tn
+                better = best_ratio < ratio
+                best_pts[better, :] = win_pts[better, :]
+                best_ratio[better] = ratio[better]
+                hyp_num += round_hyp_num
+                it += 1
+                lo = torch.min(best_ratio)
+                if (1 - (1 - lo ** 2) ** hyp_num) > confidence or it > max_iter:
+                    break
+            per_class.append(best_pts.unsqueeze(0))
+        per_image.append(torch.cat(per_class, 0).unsqueeze(0))
+    return torch.cat(per_image, 0)
+
+
+# ----------------------------------------------------------------------------
+# lib/hough_voting.py and the Model mixin
+# ----------------------------------------------------------------------------
+
+def hough_voting(agg, round_hyp_num: int, **vote_kwargs):
+    """hough_voting.py:41-63 (``HoughVotingLayer.forward``)."""
+    uv = agg["xy"]
+    vertex = uv.permute(0, 2, 3, 1).unsqueeze(3)                               # :51
+    out = ransac_voting_layer_v3(mask=agg["instance_masks"], vertex=vertex,
+                                 round_hyp_num=round_hyp_num, **vote_kwargs)
+    agg.update({"hypothesis": out, "pruned_hypothesis": out, "xy": out.squeeze(1), "xy_mask": uv})
+    return agg
+
+
+def pose_recover(logits, inv_intrinsics, round_hyp_num: int, num_of_classes: Optional[int] = None,
+                 **vote_kwargs):
+    """lib/pose_regressor.py:445-504, 753-770: class compression -> aggregation ->
+    voting -> RT, i.e. the whole hot path on CPU tensors."""
+    if num_of_classes is None:
+        num_of_classes = logits["mask"].shape[1]
+    cat = class_compression(logits, num_of_classes)
+    agg = aggregate(cat)
+    agg = hough_voting(agg, round_hyp_num, **vote_kwargs)
+    agg = samplewise_get_RT(agg, inv_intrinsics)
+    return cat, agg
