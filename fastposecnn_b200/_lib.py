@@ -1,0 +1,108 @@
+"""ctypes binding of ``libfpc_b200.so`` (C ABI declared in ``include/fpc_b200.h``).
+
+There is no fallback of any kind: if the shared library is missing the first
+call raises, and every entry point refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfpc_b200.so")
+
+FPC_OK, FPC_EINVAL, FPC_ECUDA, FPC_ECAPACITY = 0, -1, -2, -3
+ARITH_IEEE, ARITH_NVCC_FMA = 0, 1
+POSE_ROW = 48
+NUM_COUNTERS = 16
+CNT_INSTANCES, CNT_ROWS, CNT_RECORDS, CNT_WORK, CNT_FLAGS = 0, 1, 2, 3, 4
+FLAG_INSTANCES, FLAG_ROWS, FLAG_RECORDS = 1, 2, 4
+# word offsets inside a pose-table row (include/fpc_b200.h)
+ROW_CLASS, ROW_SAMPLE, ROW_COUNT, ROW_Q, ROW_SCALES, ROW_XY, ROW_Z, ROW_T, ROW_R, ROW_RT = 0, 1, 2, 3, 7, 10, 12, 13, 16, 25
+ROW_HYP, ROW_WIN_IDX, ROW_WIN_COUNT, ROW_TN, ROW_REFINE_INL, ROW_BBOX = 41, 43, 44, 45, 46, 47
+
+EXPORTS = (
+    "fpc_version", "fpc_last_error", "fpc_generate_hypothesis", "fpc_voting_for_hypothesis",
+    "fpc_normalize", "fpc_class_compress", "fpc_get_rt", "fpc_pose_recover_workspace_bytes",
+    "fpc_pose_recover", "fpc_pose_recover_num_launches", "fpc_aggregate_workspace_bytes", "fpc_aggregate",
+    "fpc_vote_dense_workspace_bytes", "fpc_vote_dense", "fpc_materialize_instances",
+)
+
+_vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+
+class RecoverArgs(ctypes.Structure):
+    """``fpc_recover_args`` (include/fpc_b200.h)."""
+    _fields_ = [
+        ("b", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("num_classes", ctypes.c_int32),
+        ("hn", ctypes.c_int32), ("max_instances", ctypes.c_int32),
+        ("max_records", ctypes.c_int64), ("max_rows", ctypes.c_int64),
+        ("inlier_thresh", ctypes.c_float), ("min_num", ctypes.c_int32), ("max_num", ctypes.c_int32),
+        ("arith", ctypes.c_int32), ("seed", ctypes.c_uint64),
+        ("mask_logits", _vp), ("quaternion", _vp), ("scales", _vp), ("xy", _vp), ("z", _vp),
+        ("inv_intrinsics", _vp), ("idxs", _vp), ("select_u", _vp),
+        ("pose_table", _vp), ("counters", _vp), ("cat_mask_u8", _vp), ("labels", _vp),
+        ("hyp_out", _vp), ("vote_counts_out", _vp),
+        ("workspace", _vp), ("workspace_bytes", ctypes.c_size_t), ("stream", _vp),
+    ]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"fastposecnn_b200: {LIB_PATH} is missing -- build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C fastposecnn_b200/csrc`. "
+            "There is no CPU or PyTorch fallback for this path.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.fpc_version.restype = _i
+    L.fpc_last_error.restype = ctypes.c_char_p
+    L.fpc_generate_hypothesis.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+    L.fpc_voting_for_hypothesis.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]
+    L.fpc_normalize.argtypes = [_vp, _vp, _ll, _i, _ll, _vp]
+    L.fpc_class_compress.argtypes = [_vp] * 11 + [_i, _i, _i, _i, _vp]
+    L.fpc_get_rt.argtypes = [_vp] * 7 + [_i, _vp]
+    L.fpc_pose_recover_workspace_bytes.argtypes = [ctypes.POINTER(RecoverArgs)]
+    L.fpc_pose_recover_workspace_bytes.restype = ctypes.c_size_t
+    L.fpc_pose_recover.argtypes = [ctypes.POINTER(RecoverArgs)]
+    L.fpc_pose_recover_num_launches.restype = _i
+    for name in ("fpc_generate_hypothesis", "fpc_voting_for_hypothesis", "fpc_normalize", "fpc_class_compress",
+                 "fpc_get_rt", "fpc_pose_recover"):
+        getattr(L, name).restype = _i
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != FPC_OK:
+        msg = lib().fpc_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libfpc_b200 error {rc}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=None, contiguous: bool = True) -> torch.Tensor:
+    """Mirrors CHECK_INPUT of the reference binding (src/ransac_voting.cpp:7-9): CUDA + contiguous."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (fastposecnn_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t
+
+
+def current_stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,516 @@
+// Aggregation half of the path: mask arg-max, 4-connected instance labelling, per-instance
+// statistics, (instance,row) tables, masked sums and voting records.
+//
+// Reference behaviour being reproduced (paths relative to /root/reference/source_code/FastPoseCNN/):
+//   lib/pose_regressor.py:449            cat_mask = argmax(log_softmax(mask logits))
+//   lib/gpu_tensor_funcs.py:52-99        class_compress (select the predicted class's channels, normalise q / xy)
+//   lib/aggregation_layer.py:43-59,160-183  connected components of cat_mask != 0, 4-connectivity, per image,
+//                                        labels in raster order of each component's first pixel
+//   lib/aggregation_layer.py:87-156      class id = min non-zero class in the component, masked means
+//   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:532-550  per-instance pixel list in raster order
+#include "fpc_internal.cuh"
+
+namespace fpc {
+
+// =============================================================================================
+// A. arg-max over the mask logits + run-aware label initialisation
+// =============================================================================================
+// One thread owns 4 consecutive pixels (one 16-byte load per class plane).  HBM-bound: 4*C bytes
+// read, 5 bytes written per pixel.  label[p] is initialised to the first pixel of p's horizontal
+// foreground run *inside the warp's 128-pixel span* (and inside its image row), -1 for background,
+// so that only span-crossing and vertical adjacencies are left for the union-find merge.
+__global__ void __launch_bounds__(256) k_argmax_init_v4(const float *__restrict__ mask, uint8_t *__restrict__ cls,
+                                                        int *__restrict__ label, int C, int hw, int w, int P4) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int p = t * 4;
+    int nib = 0, x0 = 0;
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (t < P4) {
+        const int bi = p / hw;
+        const int pix = p - bi * hw;
+        x0 = pix % w;
+        const float4 *src = reinterpret_cast<const float4 *>(mask + (size_t)bi * C * hw + pix);
+        const int plane4 = hw >> 2;
+        float4 best = __ldcs(src);
+        for (int c = 1; c < C; ++c) {
+            float4 v = __ldcs(src + (size_t)c * plane4);
+            // strict '>' keeps the first maximum, like torch.argmax
+            if (v.x > best.x) { best.x = v.x; a0 = c; }
+            if (v.y > best.y) { best.y = v.y; a1 = c; }
+            if (v.z > best.z) { best.z = v.z; a2 = c; }
+            if (v.w > best.w) { best.w = v.w; a3 = c; }
+        }
+        nib = (a0 != 0) | ((a1 != 0) << 1) | ((a2 != 0) << 2) | ((a3 != 0) << 3);
+    }
+    // --- run start inside the warp span -----------------------------------------------------
+    int prev_last = __shfl_up_sync(FULL, (nib >> 3) & 1, 1);
+    if (lane == 0) prev_last = 0;
+    const bool cont = (nib & 1) && prev_last && (x0 != 0);   // my first pixel continues the previous lane's run
+    const unsigned transparent = __ballot_sync(FULL, (nib == 0xF) && cont);
+    const unsigned below = ~transparent & ((1u << lane) - 1u);
+    const int s = below ? (31 - __clz(below)) : 0;           // nearest lane below me whose pixels break/start the run
+    const int nib_s = __shfl_sync(FULL, nib, s);
+    const int tail_ones = __clz(~((unsigned)nib_s << 28));   // trailing foreground pixels of lane s (0..4)
+    const int chain_start = p - 4 * (lane - s) + (4 - tail_ones);
+    if (t < P4) {
+        int lab[4];
+        int cur = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((nib >> j) & 1) {
+                if (cur < 0) cur = (j == 0 && cont) ? chain_start : p + j;
+                lab[j] = cur;
+            } else {
+                lab[j] = -1;
+                cur = -1;
+            }
+        }
+        *reinterpret_cast<int4 *>(label + p) = make_int4(lab[0], lab[1], lab[2], lab[3]);
+        *reinterpret_cast<uchar4 *>(cls + p) = make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3);
+    }
+}
+
+// Scalar variant for widths that are not a multiple of 4 (or misaligned inputs): span = 1 pixel.
+__global__ void __launch_bounds__(256) k_argmax_init_v1(const float *__restrict__ mask, uint8_t *__restrict__ cls,
+                                                        int *__restrict__ label, int C, int hw, int P) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int bi = p / hw, pix = p - bi * hw;
+    const float *src = mask + (size_t)bi * C * hw + pix;
+    float best = __ldcs(src);
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {
+        float v = __ldcs(src + (size_t)c * hw);
+        if (v > best) { best = v; arg = c; }
+    }
+    cls[p] = (uint8_t)arg;
+    label[p] = arg ? p : -1;
+}
+
+// Label initialisation from an already categorical mask (AggregationLayer drop-in: cat_mask int64).
+__global__ void __launch_bounds__(256) k_init_from_catmask(const long long *__restrict__ cat, uint8_t *__restrict__ cls,
+                                                           int *__restrict__ label, int P) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const long long c = cat[p];
+    cls[p] = (uint8_t)(c < 0 ? 0 : (c > 255 ? 255 : c));
+    label[p] = c != 0 ? p : -1;
+}
+
+// =============================================================================================
+// B/C. union-find merge and flatten (roots = smallest linear index of the component)
+// =============================================================================================
+__device__ __forceinline__ int uf_find(const int *L, int x) {
+    while (true) {
+        int p = L[x];
+        if (p == x) return x;
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_unite(int *L, int a, int b) {
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }      // link the larger root under the smaller one
+        int old = atomicMin(&L[a], b);
+        if (old == a) return;                         // a was still a root: done
+        a = old;                                      // somebody re-parented a meanwhile: retry from there
+    }
+}
+
+// `span`: width of the pixel spans inside which k_argmax_init_* already linked horizontal runs
+// (128 for the v4 kernel, 1 otherwise).  Spans start at multiples of `span` in linear index.
+__global__ void __launch_bounds__(256) k_ccl_merge(const uint8_t *__restrict__ cls, int *label, int w, int hw, int P,
+                                                   int span) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    if (!cls[p]) return;
+    const int pix = p % hw;
+    const int y = pix / w, x = pix - y * w;
+    const bool left = x > 0 && cls[p - 1];
+    if (left && (p % span) == 0) uf_unite(label, p, p - 1);
+    if (y > 0 && cls[p - w]) {
+        // if left and up-left are both foreground, the left pixel already carries this adjacency
+        if (!(left && cls[p - w - 1])) uf_unite(label, p, p - w);
+    }
+}
+
+constexpr int TILE = 1024;  // pixels per block in the flatten / id-assignment kernels (256 threads x 4)
+
+__global__ void __launch_bounds__(256) k_ccl_flatten(int *label, int *__restrict__ tile_roots, int P) {
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = blockIdx.x * TILE + j * 256 + threadIdx.x;
+        if (p < P) {
+            const int l = label[p];
+            if (l >= 0) {
+                const int r = uf_find(label, l);
+                if (r != l) label[p] = r;
+                n += (r == p);
+            }
+        }
+    }
+    n = __reduce_add_sync(FULL, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_roots[blockIdx.x] = s_n;
+}
+
+// D. exclusive scan of the per-tile root counts (single block) -> N
+__global__ void __launch_bounds__(1024) k_scan_tiles(int *tile_roots, int ntiles, int *counters, int max_instances) {
+    const int total = block_exclusive_scan_inplace(tile_roots, ntiles);
+    if (threadIdx.x == 0) {
+        counters[FPC_CNT_INSTANCES] = total;
+        counters[FPC_CNT_FLAGS] = total > max_instances ? FPC_FLAG_INSTANCES : 0;
+        counters[FPC_CNT_TICKET] = 0;
+    }
+}
+
+// E. instance id = rank of the root pixel in raster order over the whole batch volume
+//    (== scipy.ndimage.label's numbering, aggregation_layer.py:178)
+__global__ void __launch_bounds__(256) k_assign_ids(const int *__restrict__ label, const int *__restrict__ tile_base,
+                                                    int *__restrict__ idmap, InstTables T, int P, int max_instances) {
+    __shared__ int s_w[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int base = tile_base[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = blockIdx.x * TILE + j * 256 + threadIdx.x;
+        const bool root = (p < P) && (label[p] == p);
+        const unsigned bal = __ballot_sync(FULL, root);
+        if (lane == 0) s_w[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = s_w[k];
+            woff += (k < wid) ? c : 0;
+            tot += c;
+        }
+        if (root) {
+            const int id = base + woff + __popc(bal & ((1u << lane) - 1u));
+            idmap[p] = id;
+            if (id < max_instances) {
+                T.root[id] = p;
+                T.count[id] = 0;
+                T.ymin[id] = INT_MAX;
+                T.ymax[id] = -1;
+                T.xmin[id] = INT_MAX;
+                T.xmax[id] = -1;
+                T.mincls[id] = INT_MAX;
+            }
+        }
+        base += tot;
+        __syncthreads();
+    }
+}
+
+// F. per-instance pixel count, bounding box and minimum class id; rewrites label[p] from
+//    "root pixel index" to "instance id + 1" (0 = background), i.e. the scipy label volume.
+__global__ void __launch_bounds__(256) k_instance_stats(int *label, const int *__restrict__ idmap,
+                                                        const uint8_t *__restrict__ cls, InstTables T, int w, int hw, int P,
+                                                        int max_instances) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int p = gw * 128 + it * 32 + lane;
+        int id = -1, x = 0, y = 0, c = 0;
+        if (p < P) {
+            const int l = label[p];
+            if (l >= 0) {
+                id = idmap[l];
+                const int pix = p % hw;
+                y = pix / w;
+                x = pix - y * w;
+                c = cls[p];
+            }
+            label[p] = id + 1;
+        }
+        unsigned rem = __ballot_sync(FULL, id >= 0);
+        while (rem) {
+            const int cur = __shfl_sync(FULL, id, __ffs(rem) - 1);
+            const bool mine = (id == cur);
+            const unsigned gm = __ballot_sync(FULL, mine);
+            rem &= ~gm;
+            const int xmn = __reduce_min_sync(FULL, mine ? x : INT_MAX);
+            const int xmx = __reduce_max_sync(FULL, mine ? x : -1);
+            const int ymn = __reduce_min_sync(FULL, mine ? y : INT_MAX);
+            const int ymx = __reduce_max_sync(FULL, mine ? y : -1);
+            const int cmn = __reduce_min_sync(FULL, mine ? c : INT_MAX);
+            if (lane == 0 && cur < max_instances) {
+                atomicAdd(&T.count[cur], __popc(gm));
+                atomicMin(&T.xmin[cur], xmn);
+                atomicMax(&T.xmax[cur], xmx);
+                atomicMin(&T.ymin[cur], ymn);
+                atomicMax(&T.ymax[cur], ymx);
+                atomicMin(&T.mincls[cur], cmn);
+            }
+        }
+    }
+}
+
+// G. rows of every instance's bounding box -> rowoff (exclusive scan over instances, single block)
+__global__ void __launch_bounds__(1024) k_scan_rows_per_instance(InstTables T, int *counters, int max_instances,
+                                                                  long long max_rows) {
+    const int N = min(counters[FPC_CNT_INSTANCES], max_instances);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) T.rowoff[i] = T.ymax[i] - T.ymin[i] + 1;
+    __syncthreads();
+    const int total = block_exclusive_scan_inplace(T.rowoff, N);
+    if (threadIdx.x == 0) {
+        T.rowoff[N] = total;
+        counters[FPC_CNT_ROWS] = total;
+        if ((long long)total > max_rows) atomicOr(&counters[FPC_CNT_FLAGS], FPC_FLAG_ROWS);
+    }
+}
+
+struct RowItem {
+    int i, y, img, x0, x1, cnt;
+    bool valid;
+};
+__device__ __forceinline__ RowItem decode_row(const InstTables &T, int N, int r, int hw) {
+    RowItem it;
+    it.i = upper_index(T.rowoff, N, r);
+    it.y = T.ymin[it.i] + (r - T.rowoff[it.i]);
+    it.img = T.root[it.i] / hw;
+    it.x0 = T.xmin[it.i];
+    it.x1 = T.xmax[it.i];
+    it.cnt = T.count[it.i];
+    it.valid = true;
+    return it;
+}
+
+__device__ __forceinline__ float select_uniform(const PathParams &pp, int p) {
+    if (pp.select_u) return pp.select_u[p];
+    return (float)(hash3(pp.seed, (uint32_t)p, 0x5e1ec7u, 0u) >> 8) * (1.0f / 16777216.0f);
+}
+
+// H. pixels that will vote, per (instance,row).  Also zeroes the vote counters of the live instances.
+//    ransac_voting_gpu.py:536-545: fewer than min_num pixels -> the instance does not vote;
+//    more than max_num -> Bernoulli(max_num / count) sub-sampling.
+__global__ void __launch_bounds__(256) k_row_count(const int *__restrict__ label, InstTables T, RowTables R,
+                                                   const int *__restrict__ counters, PathParams pp, int *votes) {
+    if (counters[FPC_CNT_FLAGS]) return;
+    const int N = counters[FPC_CNT_INSTANCES];
+    const int rows = counters[FPC_CNT_ROWS];
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const long long nvotes = (long long)N * pp.hn;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nvotes; k += (long long)gridDim.x * blockDim.x)
+        votes[k] = 0;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
+        const RowItem it = decode_row(T, N, r, pp.hw);
+        int n = 0;
+        if (it.cnt >= pp.min_num) {
+            const bool sub = it.cnt > pp.max_num;
+            const float thr = (float)pp.max_num / (float)it.cnt;
+            const int rowbase = it.img * pp.hw + it.y * pp.w;
+            for (int xb = it.x0; xb <= it.x1; xb += 32) {
+                const int x = xb + lane;
+                bool m = (x <= it.x1) && (label[rowbase + x] == it.i + 1);
+                if (m && sub) m = select_uniform(pp, rowbase + x) < thr;
+                n += __popc(__ballot_sync(FULL, m));
+            }
+        }
+        if (lane == 0) R.base[r] = n;
+    }
+}
+
+// I1. exclusive prefix of the row counts inside each instance (one warp per instance) -> tn
+__global__ void __launch_bounds__(256) k_row_prefix(InstTables T, RowTables R, const int *__restrict__ counters) {
+    if (counters[FPC_CNT_FLAGS]) return;
+    const int N = counters[FPC_CNT_INSTANCES];
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += nwarps) {
+        const int r0 = T.rowoff[i], r1 = T.rowoff[i + 1];
+        int running = 0;
+        for (int rb = r0; rb < r1; rb += 32) {
+            const int r = rb + lane;
+            const int v = (r < r1) ? R.base[r] : 0;
+            const int inc = warp_incl_scan(v, lane);
+            if (r < r1) R.base[r] = running + inc - v;
+            running += __shfl_sync(FULL, inc, 31);
+        }
+        if (lane == 0) T.tn[i] = running;
+    }
+}
+
+// I2. record offsets and vote work items per instance (single block)
+__global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counters, long long max_records, int chunk) {
+    if (counters[FPC_CNT_FLAGS]) return;
+    const int N = counters[FPC_CNT_INSTANCES];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int tn = T.tn[i];
+        T.pxoff[i] = tn;
+        T.workoff[i] = (tn + chunk - 1) / chunk;
+    }
+    __syncthreads();
+    const int total = block_exclusive_scan_inplace(T.pxoff, N);
+    __syncthreads();
+    const int work = block_exclusive_scan_inplace(T.workoff, N);
+    if (threadIdx.x == 0) {
+        T.pxoff[N] = total;
+        T.workoff[N] = work;
+        counters[FPC_CNT_RECORDS] = total;
+        counters[FPC_CNT_WORK] = work;
+        if ((long long)total > max_records) atomicOr(&counters[FPC_CNT_FLAGS], FPC_FLAG_RECORDS);
+    }
+}
+
+// J. one warp per (instance,row): masked sums of the predicted class's quaternion / scales / z
+//    (aggregation_layer.py:125-149, on the class-compressed + per-pixel-normalised fields of
+//    gpu_tensor_funcs.py:78-94) and the raster-ordered voting records (x, y, dir_x, dir_y)
+//    (ransac_voting_gpu.py:547-550).  Head maps are read exactly once, foreground pixels only.
+template <bool FUSED_HEADS>
+__global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, const uint8_t *__restrict__ cls,
+                                                InstTables T, RowTables R, const int *__restrict__ counters,
+                                                PathParams pp, FieldSrc F, float4 *__restrict__ rec) {
+    if (counters[FPC_CNT_FLAGS]) return;
+    const int N = counters[FPC_CNT_INSTANCES];
+    const int rows = counters[FPC_CNT_ROWS];
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int K = pp.num_classes - 1;
+    const size_t hw = (size_t)pp.hw;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
+        const RowItem it = decode_row(T, N, r, pp.hw);
+        const int tn = T.tn[it.i];
+        const bool sub = it.cnt > pp.max_num;
+        const float thr = (float)pp.max_num / (float)it.cnt;
+        const int rowbase = it.img * pp.hw + it.y * pp.w;
+        const int rec0 = T.pxoff[it.i] + R.base[r];
+        int running = 0;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int xb = it.x0; xb <= it.x1; xb += 32) {
+            const int x = xb + lane;
+            const int p = rowbase + x;
+            const bool mem = (x <= it.x1) && (label[p] == it.i + 1);
+            float vx = 0.f, vy = 0.f;
+            if (mem) {
+                const size_t pix = (size_t)(it.y * pp.w + x);
+                float q0, q1, q2, q3, s0, s1, s2, zz;
+                if (FUSED_HEADS) {
+                    const int k = (int)cls[p] - 1;  // predicted class of THIS pixel (class_compress is per pixel)
+                    const float *q = F.quaternion + ((size_t)it.img * 4 * K + 4 * k) * hw + pix;
+                    const float *s = F.scales + ((size_t)it.img * 3 * K + 3 * k) * hw + pix;
+                    const float *v = F.xy + ((size_t)it.img * 2 * K + 2 * k) * hw + pix;
+                    q0 = __ldcs(q); q1 = __ldcs(q + hw); q2 = __ldcs(q + 2 * hw); q3 = __ldcs(q + 3 * hw);
+                    s0 = __ldcs(s); s1 = __ldcs(s + hw); s2 = __ldcs(s + 2 * hw);
+                    zz = __ldcs(F.z + ((size_t)it.img * K + k) * hw + pix);
+                    vx = __ldcs(v); vy = __ldcs(v + hw);
+                    const float qn = __fsqrt_rn(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+                    if (qn != 0.f) { q0 = __fdiv_rn(q0, qn); q1 = __fdiv_rn(q1, qn); q2 = __fdiv_rn(q2, qn); q3 = __fdiv_rn(q3, qn); }
+                    const float vn = __fsqrt_rn(vx * vx + vy * vy);
+                    if (vn != 0.f) { vx = __fdiv_rn(vx, vn); vy = __fdiv_rn(vy, vn); }
+                } else {
+                    // already class-compressed CategoricalData (lib/type_hinting.py:12-17): [b,4|3|2,h,w], z [b,h,w]
+                    const float *q = F.quaternion + ((size_t)it.img * 4) * hw + pix;
+                    const float *s = F.scales + ((size_t)it.img * 3) * hw + pix;
+                    const float *v = F.xy + ((size_t)it.img * 2) * hw + pix;
+                    q0 = q[0]; q1 = q[hw]; q2 = q[2 * hw]; q3 = q[3 * hw];
+                    s0 = s[0]; s1 = s[hw]; s2 = s[2 * hw];
+                    zz = F.z[(size_t)it.img * hw + pix];
+                    vx = v[0]; vy = v[hw];
+                }
+                acc[0] += q0; acc[1] += q1; acc[2] += q2; acc[3] += q3;
+                acc[4] += s0; acc[5] += s1; acc[6] += s2; acc[7] += zz;
+            }
+            bool sel = mem && tn > 0;
+            if (sel && sub) sel = select_uniform(pp, p) < thr;
+            const unsigned bal = __ballot_sync(FULL, sel);
+            if (sel && rec) {
+                const int idx = rec0 + running + __popc(bal & ((1u << lane) - 1u));
+                rec[idx] = make_float4((float)x, (float)it.y, vx, vy);
+            }
+            running += __popc(bal);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = acc[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+            acc[k] = v;
+        }
+        if (lane < 8) {
+            float v = acc[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) v = (lane == k) ? acc[k] : v;
+            R.sum[(size_t)r * 8 + lane] = v;
+        }
+    }
+}
+
+template __global__ void k_gather<true>(const int *, const uint8_t *, InstTables, RowTables, const int *, PathParams,
+                                        FieldSrc, float4 *);
+template __global__ void k_gather<false>(const int *, const uint8_t *, InstTables, RowTables, const int *, PathParams,
+                                         FieldSrc, float4 *);
+
+// =============================================================================================
+// host-side launch sequence of the aggregation half
+// =============================================================================================
+int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,
+                            const long long *cat_mask_i64, cudaStream_t st) {
+    const int P = pp.P;
+    const int ntiles = ceil_div(P, TILE);
+    int span = 1;
+    if (mask_logits) {
+        const bool vec_ok = (pp.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mask_logits) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(ws.label) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(ws.cls) & 3) == 0);
+        if (vec_ok) {
+            const int P4 = P / 4;
+            k_argmax_init_v4<<<ceil_div(P4, 256), 256, 0, st>>>(mask_logits, ws.cls, ws.label, pp.num_classes, pp.hw,
+                                                                pp.w, P4);
+            span = 128;
+        } else {
+            k_argmax_init_v1<<<ceil_div(P, 256), 256, 0, st>>>(mask_logits, ws.cls, ws.label, pp.num_classes, pp.hw, P);
+        }
+        FPC_LAUNCH_CHECK("k_argmax_init");
+    } else {
+        k_init_from_catmask<<<ceil_div(P, 256), 256, 0, st>>>(cat_mask_i64, ws.cls, ws.label, P);
+        FPC_LAUNCH_CHECK("k_init_from_catmask");
+    }
+    k_ccl_merge<<<ceil_div(P, 256), 256, 0, st>>>(ws.cls, ws.label, pp.w, pp.hw, P, span);
+    FPC_LAUNCH_CHECK("k_ccl_merge");
+    k_ccl_flatten<<<ntiles, 256, 0, st>>>(ws.label, ws.tile_roots, P);
+    FPC_LAUNCH_CHECK("k_ccl_flatten");
+    k_scan_tiles<<<1, 1024, 0, st>>>(ws.tile_roots, ntiles, ws.counters, pp.max_instances);
+    FPC_LAUNCH_CHECK("k_scan_tiles");
+    k_assign_ids<<<ntiles, 256, 0, st>>>(ws.label, ws.tile_roots, ws.idmap, ws.T, P, pp.max_instances);
+    FPC_LAUNCH_CHECK("k_assign_ids");
+    k_instance_stats<<<ceil_div(P, 128 * 8), 256, 0, st>>>(ws.label, ws.idmap, ws.cls, ws.T, pp.w, pp.hw, P,
+                                                           pp.max_instances);
+    FPC_LAUNCH_CHECK("k_instance_stats");
+    k_scan_rows_per_instance<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_instances, pp.max_rows);
+    FPC_LAUNCH_CHECK("k_scan_rows_per_instance");
+    return FPC_OK;
+}
+
+int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, bool fused_heads,
+                            bool want_records, int vote_chunk, cudaStream_t st) {
+    const int grid = sm_count() * 8;
+    k_row_count<<<grid, 256, 0, st>>>(ws.label, ws.T, ws.R, ws.counters, pp, ws.votes);
+    FPC_LAUNCH_CHECK("k_row_count");
+    k_row_prefix<<<grid, 256, 0, st>>>(ws.T, ws.R, ws.counters);
+    FPC_LAUNCH_CHECK("k_row_prefix");
+    k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk);
+    FPC_LAUNCH_CHECK("k_scan_records");
+    float4 *rec = want_records ? ws.rec : nullptr;
+    if (fused_heads)
+        k_gather<true><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+    else
+        k_gather<false><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+    FPC_LAUNCH_CHECK("k_gather");
+    return FPC_OK;
+}
+
+}  // namespace fpc

@@ -1,0 +1,281 @@
+// extern "C" surface of libfpc_b200.so (declared in include/fpc_b200.h) + the element-wise kernels
+// behind gpu_tensor_funcs.normalize / class_compress.
+#include "fpc_internal.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace fpc {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+char *err_buf() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gpu_tensor_funcs.normalize (lib/gpu_tensor_funcs.py:37-50) over the middle axis of [outer,c,inner]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_normalize(const float *__restrict__ in, float *__restrict__ out, long long outer,
+                                                   int c, long long inner) {
+    const long long n = outer * inner;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long o = t / inner, i = t - o * inner;
+        const float *src = in + o * c * inner + i;
+        float *dst = out + o * c * inner + i;
+        float ss = 0.f;
+        for (int k = 0; k < c; ++k) {
+            const float v = src[k * inner];
+            ss = fmaf(v, v, ss);
+        }
+        const float nrm = __fsqrt_rn(ss);
+        const float d = nrm != 0.f ? nrm : 1.f;
+        for (int k = 0; k < c; ++k) dst[k * inner] = __fdiv_rn(src[k * inner], d);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model.class_compression / gpu_tensor_funcs.class_compress with dense outputs (drop-in mode)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_class_compress(const float *__restrict__ mask, const long long *__restrict__ cat_in,
+                                                        const float *__restrict__ quat, const float *__restrict__ scales,
+                                                        const float *__restrict__ xy, const float *__restrict__ z,
+                                                        long long *__restrict__ cat_out, float *__restrict__ q_out,
+                                                        float *__restrict__ s_out, float *__restrict__ xy_out,
+                                                        float *__restrict__ z_out, int C, int hw, int P) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int bi = p / hw;
+    const size_t pix = (size_t)(p - bi * hw);
+    const size_t HW = (size_t)hw;
+    const int K = C - 1;
+    int cls;
+    if (cat_in) {
+        const long long c = cat_in[p];
+        cls = (c >= 0 && c < C) ? (int)c : 0;
+    } else {
+        const float *src = mask + (size_t)bi * C * HW + pix;
+        float best = __ldcs(src);
+        cls = 0;
+        for (int c = 1; c < C; ++c) {
+            const float v = __ldcs(src + c * HW);
+            if (v > best) { best = v; cls = c; }
+        }
+    }
+    if (cat_out) cat_out[p] = cls;
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, vx = 0.f, vy = 0.f, zz = 0.f;
+    if (cls > 0) {
+        const int k = cls - 1;
+        const float *q = quat + ((size_t)bi * 4 * K + 4 * k) * HW + pix;
+        const float *s = scales + ((size_t)bi * 3 * K + 3 * k) * HW + pix;
+        const float *v = xy + ((size_t)bi * 2 * K + 2 * k) * HW + pix;
+        q0 = __ldcs(q); q1 = __ldcs(q + HW); q2 = __ldcs(q + 2 * HW); q3 = __ldcs(q + 3 * HW);
+        s0 = __ldcs(s); s1 = __ldcs(s + HW); s2 = __ldcs(s + 2 * HW);
+        vx = __ldcs(v); vy = __ldcs(v + HW);
+        zz = __ldcs(z + ((size_t)bi * K + k) * HW + pix);
+        const float qn = __fsqrt_rn(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        if (qn != 0.f) { q0 = __fdiv_rn(q0, qn); q1 = __fdiv_rn(q1, qn); q2 = __fdiv_rn(q2, qn); q3 = __fdiv_rn(q3, qn); }
+        const float vn = __fsqrt_rn(vx * vx + vy * vy);
+        if (vn != 0.f) { vx = __fdiv_rn(vx, vn); vy = __fdiv_rn(vy, vn); }
+    }
+    float *qo = q_out + (size_t)bi * 4 * HW + pix;
+    qo[0] = q0; qo[HW] = q1; qo[2 * HW] = q2; qo[3 * HW] = q3;
+    float *so = s_out + (size_t)bi * 3 * HW + pix;
+    so[0] = s0; so[HW] = s1; so[2 * HW] = s2;
+    float *vo = xy_out + (size_t)bi * 2 * HW + pix;
+    vo[0] = vx; vo[HW] = vy;
+    z_out[(size_t)bi * HW + pix] = zz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------------
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base(static_cast<char *>(b)) {}
+    template <typename T>
+    T *take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+static size_t carve(Workspace &ws, void *base, long long P, int max_instances, int hn, long long max_records,
+                    long long max_rows, bool own_cls, bool own_label, bool own_votes, bool own_hyp) {
+    Carver c(base);
+    const size_t ni = (size_t)max_instances + 1;
+    ws.counters = nullptr;
+    if (own_cls) ws.cls = c.take<uint8_t>((size_t)P);
+    if (own_label) ws.label = c.take<int>((size_t)P);
+    ws.idmap = c.take<int>((size_t)P);
+    ws.tile_roots = c.take<int>((size_t)(P / 1024 + 2));
+    ws.T.root = c.take<int>(ni);
+    ws.T.count = c.take<int>(ni);
+    ws.T.ymin = c.take<int>(ni);
+    ws.T.ymax = c.take<int>(ni);
+    ws.T.xmin = c.take<int>(ni);
+    ws.T.xmax = c.take<int>(ni);
+    ws.T.mincls = c.take<int>(ni);
+    ws.T.rowoff = c.take<int>(ni);
+    ws.T.tn = c.take<int>(ni);
+    ws.T.pxoff = c.take<int>(ni);
+    ws.T.workoff = c.take<int>(ni);
+    ws.R.base = c.take<int>((size_t)max_rows);
+    ws.R.sum = c.take<float>((size_t)max_rows * 8);
+    ws.rec = c.take<float4>((size_t)max_records);
+    if (own_hyp) ws.hyp = c.take<float2>((size_t)max_instances * hn);
+    if (own_votes) ws.votes = c.take<int>((size_t)max_instances * hn);
+    return (c.off + 255) & ~size_t(255);
+}
+
+static int check_sizes(const fpc_recover_args *a) {
+    if (!a) return fail(FPC_EINVAL, "args is NULL");
+    if (a->b <= 0 || a->h <= 0 || a->w <= 0) return fail(FPC_EINVAL, "b, h, w must be positive (got %d, %d, %d)", a->b, a->h, a->w);
+    if (a->num_classes < 2 || a->num_classes > 255) return fail(FPC_EINVAL, "num_classes must be in [2,255] (got %d)", a->num_classes);
+    if ((long long)a->b * a->h * a->w >= (1ll << 31)) return fail(FPC_EINVAL, "b*h*w must be < 2^31");
+    if (a->h >= 65536 || a->w >= 65536) return fail(FPC_EINVAL, "h and w must be < 65536");
+    if (a->hn <= 0) return fail(FPC_EINVAL, "hn must be positive (got %d)", a->hn);
+    if (a->max_instances <= 0) return fail(FPC_EINVAL, "max_instances must be positive");
+    if (a->max_records <= 0 || a->max_rows <= 0) return fail(FPC_EINVAL, "max_records and max_rows must be positive");
+    if ((long long)a->max_instances * a->hn >= (1ll << 31)) return fail(FPC_EINVAL, "max_instances*hn must be < 2^31");
+    if (a->max_records >= (1ll << 31) || a->max_rows >= (1ll << 31)) return fail(FPC_EINVAL, "max_records/max_rows must be < 2^31");
+    return FPC_OK;
+}
+
+}  // namespace fpc
+
+using namespace fpc;
+
+extern "C" {
+
+int fpc_version(void) { return FPC_VERSION; }
+const char *fpc_last_error(void) { return err_buf(); }
+
+int fpc_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hypo_pts, int tn, int vn,
+                            int hn, int arith, void *stream) {
+    if (tn < 0 || vn < 0 || hn < 0) return fail(FPC_EINVAL, "negative size");
+    if (hn * vn == 0) return FPC_OK;
+    if (!direct || !coords || !idxs || !hypo_pts) return fail(FPC_EINVAL, "NULL pointer");
+    if (arith != FPC_ARITH_IEEE && arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", arith);
+    return launch_generate_hypothesis(direct, coords, idxs, hypo_pts, tn, vn, hn, arith, (cudaStream_t)stream);
+}
+
+int fpc_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo_pts, uint8_t *inliers, int tn,
+                              int vn, int hn, float inlier_thresh, int arith, void *stream) {
+    if (tn < 0 || vn < 0 || hn < 0) return fail(FPC_EINVAL, "negative size");
+    if ((long long)tn * vn * hn == 0) return FPC_OK;
+    if (!direct || !coords || !hypo_pts || !inliers) return fail(FPC_EINVAL, "NULL pointer");
+    if (vn > 65535) return fail(FPC_EINVAL, "vn too large");
+    if (arith != FPC_ARITH_IEEE && arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", arith);
+    return launch_voting_for_hypothesis(direct, coords, hypo_pts, inliers, tn, vn, hn, inlier_thresh, arith,
+                                        (cudaStream_t)stream);
+}
+
+int fpc_normalize(const float *in, float *out, long long outer, int c, long long inner, void *stream) {
+    if (outer < 0 || c < 0 || inner < 0) return fail(FPC_EINVAL, "negative size");
+    if (outer * inner == 0 || c == 0) return FPC_OK;
+    if (!in || !out) return fail(FPC_EINVAL, "NULL pointer");
+    const long long n = outer * inner;
+    const int grid = (int)std::min<long long>(ceil_div_ll(n, 256), (long long)sm_count() * 32);
+    k_normalize<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, outer, c, inner);
+    FPC_LAUNCH_CHECK("k_normalize");
+    return FPC_OK;
+}
+
+int fpc_class_compress(const float *mask_logits, const int64_t *cat_mask_in, const float *quaternion, const float *scales,
+                       const float *xy, const float *z, int64_t *cat_mask_out, float *q_out, float *s_out, float *xy_out,
+                       float *z_out, int b, int num_classes, int h, int w, void *stream) {
+    if (b < 0 || h < 0 || w < 0) return fail(FPC_EINVAL, "negative size");
+    if (num_classes < 2 || num_classes > 255) return fail(FPC_EINVAL, "num_classes must be in [2,255]");
+    const long long P = (long long)b * h * w;
+    if (P == 0) return FPC_OK;
+    if (P >= (1ll << 31)) return fail(FPC_EINVAL, "b*h*w must be < 2^31");
+    if (!mask_logits && !cat_mask_in) return fail(FPC_EINVAL, "need mask_logits or cat_mask_in");
+    if (!quaternion || !scales || !xy || !z || !q_out || !s_out || !xy_out || !z_out) return fail(FPC_EINVAL, "NULL pointer");
+    k_class_compress<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
+        mask_logits, reinterpret_cast<const long long *>(cat_mask_in), quaternion, scales, xy, z,
+        reinterpret_cast<long long *>(cat_mask_out), q_out, s_out, xy_out, z_out, num_classes, h * w, (int)P);
+    FPC_LAUNCH_CHECK("k_class_compress");
+    return FPC_OK;
+}
+
+int fpc_get_rt(const float *q, const float *xy, const float *z, const float *inv_k, float *R, float *T, float *RT, int n,
+               void *stream) {
+    if (n < 0) return fail(FPC_EINVAL, "negative size");
+    if (n == 0) return FPC_OK;
+    if (!q || !xy || !z || !inv_k || !R || !T || !RT) return fail(FPC_EINVAL, "NULL pointer");
+    return launch_get_rt(q, xy, z, inv_k, R, T, RT, n, (cudaStream_t)stream);
+}
+
+size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *a) {
+    if (check_sizes(a) != FPC_OK) return 0;
+    Workspace ws;
+    const long long P = (long long)a->b * a->h * a->w;
+    return carve(ws, nullptr, P, a->max_instances, a->hn, a->max_records, a->max_rows, true, true, true, true) + 256;
+}
+
+int fpc_pose_recover_num_launches(void) { return 13; }
+
+int fpc_pose_recover(const fpc_recover_args *a) {
+    int rc = check_sizes(a);
+    if (rc != FPC_OK) return rc;
+    if (!a->mask_logits || !a->quaternion || !a->scales || !a->xy || !a->z || !a->inv_intrinsics)
+        return fail(FPC_EINVAL, "NULL input pointer");
+    if (!a->pose_table || !a->counters || !a->workspace) return fail(FPC_EINVAL, "NULL output/workspace pointer");
+    if (a->arith != FPC_ARITH_IEEE && a->arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", a->arith);
+    if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return fail(FPC_EINVAL, "workspace must be 256-byte aligned");
+    const long long P = (long long)a->b * a->h * a->w;
+    Workspace ws;
+    ws.cls = a->cat_mask_u8;
+    ws.label = a->labels;
+    ws.votes = a->vote_counts_out;
+    ws.hyp = reinterpret_cast<float2 *>(a->hyp_out);
+    const size_t need = carve(ws, a->workspace, P, a->max_instances, a->hn, a->max_records, a->max_rows,
+                              a->cat_mask_u8 == nullptr, a->labels == nullptr, a->vote_counts_out == nullptr,
+                              a->hyp_out == nullptr);
+    if (need > a->workspace_bytes)
+        return fail(FPC_ECAPACITY, "workspace too small: need %zu bytes, got %zu", need, a->workspace_bytes);
+    ws.counters = a->counters;
+
+    PathParams pp;
+    pp.b = a->b; pp.h = a->h; pp.w = a->w; pp.hw = a->h * a->w; pp.P = (int)P;
+    pp.num_classes = a->num_classes; pp.hn = a->hn;
+    pp.max_instances = a->max_instances; pp.max_records = a->max_records; pp.max_rows = a->max_rows;
+    pp.inlier_thresh = a->inlier_thresh; pp.min_num = a->min_num; pp.max_num = a->max_num;
+    pp.arith = a->arith; pp.seed = a->seed; pp.idxs = a->idxs; pp.select_u = a->select_u;
+
+    cudaStream_t st = (cudaStream_t)a->stream;
+    rc = launch_label_and_tables(ws, pp, a->mask_logits, nullptr, st);
+    if (rc != FPC_OK) return rc;
+    FieldSrc F{a->quaternion, a->scales, a->xy, a->z};
+    rc = launch_rows_and_records(ws, pp, F, /*fused_heads=*/true, /*want_records=*/true, VOTE_CHUNK, st);
+    if (rc != FPC_OK) return rc;
+    rc = launch_vote(ws, pp, ws.hyp, ws.votes, st);
+    if (rc != FPC_OK) return rc;
+    return launch_finalize(ws, pp, ws.hyp, ws.votes, a->inv_intrinsics, a->pose_table, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Shared device/host helpers of libfpc_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "fpc_b200.h"
+
+namespace fpc {
+
+// ---- error plumbing (thread-local message, negative return codes; never exit) ----------
+char *err_buf();
+int fail(int code, const char *fmt, ...);
+
+#define FPC_CUDA_TRY(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess) return ::fpc::fail(FPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define FPC_LAUNCH_CHECK(name)                                                               \
+    do {                                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                 \
+        if (e_ != cudaSuccess) return ::fpc::fail(FPC_ECUDA, "launch of %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Number of SMs of the current device (cached); grids of persistent kernels are multiples of it.
+int sm_count();
+
+// ---- reference arithmetic (lib/ransac_voting_gpu_layer/src/ransac_voting_kernel.cu) -----
+// a*b + c*d in the two arithmetic modes of fpc_b200.h.
+template <int ARITH>
+__device__ __forceinline__ float sum_prod(float a, float b, float c, float d) {
+    if (ARITH == FPC_ARITH_IEEE) return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+    return __fmaf_rn(a, b, __fmul_rn(c, d));
+}
+
+// The reference compares float magnitudes against the DOUBLE literal 1e-6 (.cu:42-43,119).
+// (float)1e-6 = 0x358637BD lies just below 1e-6, so for any float x:
+//   (double)x < 1e-6   <=>   x <= 1e-6f
+__device__ __forceinline__ bool below_1e6(float x) { return x <= 1e-6f; }
+
+// ransac_voting_kernel.cu:112-125 -- the cosine test of one (hypothesis, pixel) pair.
+template <int ARITH>
+__device__ __forceinline__ bool vote_exact(float cx, float cy, float nx, float ny, float hx, float hy, float thresh) {
+    float dx = __fsub_rn(hx, cx);
+    float dy = __fsub_rn(hy, cy);
+    float norm1 = __fsqrt_rn(sum_prod<ARITH>(nx, nx, ny, ny));
+    float norm2 = __fsqrt_rn(sum_prod<ARITH>(dx, dx, dy, dy));
+    if (below_1e6(norm1) || below_1e6(norm2)) return false;
+    float ang = __fdiv_rn(sum_prod<ARITH>(dx, nx, dy, ny), __fmul_rn(norm1, norm2));
+    return ang > thresh;
+}
+
+// ransac_voting_kernel.cu:30-48 -- intersection of the two lines through (c0, dir d0) and
+// (c1, dir d1).  Returns false (hypothesis stays (0,0)) for a degenerate pair.
+template <int ARITH>
+__device__ __forceinline__ bool hypothesis_exact(float d0x, float d0y, float c0x, float c0y, float d1x, float d1y,
+                                                 float c1x, float c1y, float &x, float &y) {
+    float nx0 = d0y, ny0 = -d0x, nx1 = d1y, ny1 = -d1x;
+    float det_y = __fsub_rn(__fmul_rn(nx1, ny0), __fmul_rn(nx0, ny1));
+    float det_x = __fsub_rn(__fmul_rn(ny1, nx0), __fmul_rn(ny0, nx1));
+    if (below_1e6(fabsf(det_y)) || below_1e6(fabsf(det_x))) return false;
+    float p0 = sum_prod<ARITH>(nx0, c0x, ny0, c0y);
+    float p1 = sum_prod<ARITH>(nx1, c1x, ny1, c1y);
+    float num_y, num_x;
+    if (ARITH == FPC_ARITH_IEEE) {
+        num_y = __fsub_rn(__fmul_rn(nx1, p0), __fmul_rn(nx0, p1));
+        num_x = __fsub_rn(__fmul_rn(ny1, p0), __fmul_rn(ny0, p1));
+    } else {
+        // contraction pattern of nvcc 12.9 / sm_100a for the same source (see oracle/ransac_voting_ref.c)
+        num_y = __fmaf_rn(nx1, p0, -__fmul_rn(nx0, p1));
+        num_x = __fmaf_rn(-ny0, p1, __fmul_rn(ny1, p0));
+    }
+    y = __fdiv_rn(num_y, det_y);
+    x = __fdiv_rn(num_x, det_x);
+    return true;
+}
+
+// ---- small device utilities --------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t hash3(uint64_t seed, uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t h = mix32((uint32_t)seed ^ 0x9e3779b9u);
+    h = mix32(h ^ (uint32_t)(seed >> 32));
+    h = mix32(h ^ a);
+    h = mix32(h + 0x7f4a7c15u + b);
+    h = mix32(h ^ (c * 0x27d4eb2fu));
+    return h;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// Exclusive scan of data[0..n) in place by ONE thread block (any blockDim multiple of 32, <= 1024).
+// Returns the total in every thread.
+__device__ inline int block_exclusive_scan_inplace(int *data, int n) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = (i < n) ? data[i] : 0;
+        int inc = warp_incl_scan(v, lane);
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = (lane < nw) ? s_warp[lane] : 0;
+            int winc = warp_incl_scan(w, lane);
+            s_warp[lane] = winc - w;  // exclusive offset of each warp
+        }
+        __syncthreads();
+        int carry = s_carry;
+        int woff = s_warp[wid];
+        if (i < n) data[i] = carry + woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + inc;  // last thread holds the chunk total
+        __syncthreads();
+    }
+    return s_carry;
+}
+
+}  // namespace fpc

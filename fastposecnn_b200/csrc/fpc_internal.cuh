@@ -1,0 +1,120 @@
+// Internal structures shared by the translation units of libfpc_b200.so.
+#pragma once
+
+#include "fpc_common.cuh"
+
+namespace fpc {
+
+// Per-instance tables (capacity = max_instances [+1 for the offset arrays]).
+struct InstTables {
+    int *root;     // linear index (over the [b,h,w] volume) of the component's first pixel
+    int *count;    // pixels in the instance mask
+    int *ymin, *ymax, *xmin, *xmax;
+    int *mincls;   // min non-zero class id inside the component (aggregation_layer.py:113)
+    int *rowoff;   // [N+1] first (instance,row) item of the instance
+    int *tn;       // pixels that vote (0 if count < min_num; ~max_num if sub-sampled)
+    int *pxoff;    // [N+1] first voting record of the instance
+    int *workoff;  // [N+1] first vote work item (chunk of pixels) of the instance
+};
+
+// Per-(instance,row) tables.
+struct RowTables {
+    int *base;     // voting pixels in the row, then their exclusive prefix inside the instance
+    float *sum;    // [rows,8] partial sums: q0..q3, s0..s2, z
+};
+
+// Where the per-pixel regression fields come from.
+struct FieldSrc {
+    const float *quaternion, *scales, *xy, *z;
+};
+
+struct PathParams {
+    int b, h, w, hw, P;          // P = b*h*w  (< 2^31)
+    int num_classes, hn;
+    int max_instances;
+    long long max_records, max_rows;
+    float inlier_thresh;
+    int min_num, max_num;
+    int arith;
+    unsigned long long seed;
+    const int *idxs;             // [max_instances,hn,2] or nullptr
+    const float *select_u;       // [b,h,w] or nullptr
+};
+
+struct Workspace {
+    uint8_t *cls;      // [P]
+    int *label;        // [P]
+    int *idmap;        // [P] root pixel -> instance id (written at root positions only)
+    int *tile_roots;   // [ntiles+1]
+    int *counters;     // [FPC_NUM_COUNTERS]
+    InstTables T;
+    RowTables R;
+    float4 *rec;       // [max_records] (x, y, dir_x, dir_y)
+    float2 *hyp;       // [max_instances, hn]
+    int *votes;        // [max_instances, hn]
+};
+
+constexpr int VOTE_CHUNK = 2048;  // pixels per vote work item
+
+// fpc_aggregate.cu
+int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,
+                            const long long *cat_mask_i64, cudaStream_t st);
+int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, bool fused_heads,
+                            bool want_records, int vote_chunk, cudaStream_t st);
+
+// fpc_voting.cu
+int launch_generate_hypothesis(const float *direct, const float *coords, const int *idxs, float *hypo, int tn, int vn,
+                               int hn, int arith, cudaStream_t st);
+int launch_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo, uint8_t *inliers, int tn,
+                                 int vn, int hn, float thresh, int arith, cudaStream_t st);
+int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st);
+int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp, const int *votes, const float *inv_k,
+                    float *pose_table, cudaStream_t st);
+int launch_get_rt(const float *q, const float *xy, const float *z, const float *inv_k, float *R, float *T, float *RT,
+                  int n, cudaStream_t st);
+
+// Largest i in [0,n) with a[i] <= v  (a ascending, a[0] == 0 <= v).
+__device__ __forceinline__ int upper_index(const int *__restrict__ a, int n, int v) {
+    int lo = 0, hi = n;  // invariant: a[lo] <= v, (hi == n or a[hi] > v)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// gpu_tensor_funcs.batchwise_get_RT (lib/gpu_tensor_funcs.py:204-235) for one instance, with
+// quats_2_rotation_matrix (:306-326, including its final transpose).  The reference builds
+// inv_RT = [[R^-1, T],[0,0,0,1]] and inverts it; in closed form that is RT = [[R, -R T],[0,0,0,1]].
+__device__ inline void pose_from_qxyz(const float *q, float x, float y, float z, const float *__restrict__ inv_k,
+                                      float *R, float *T, float *RT) {
+    const float zz = z / 1000.f;
+    const float hx = x * zz, hy = y * zz;
+    float t[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) t[r] = inv_k[3 * r] * hx + inv_k[3 * r + 1] * hy + inv_k[3 * r + 2] * zz;
+    const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float sn = n > 0.f ? n : 1.f;
+    const float a = q[0] / sn, b = q[1] / sn, c = q[2] / sn, d = q[3] / sn;
+    const float aa = a * a, bb = b * b, cc = c * c, dd = d * d;
+    float m[3][3];
+    m[0][0] = aa - bb - cc + dd;  m[0][1] = 2.f * (a * b + c * d); m[0][2] = 2.f * (a * c - b * d);
+    m[1][0] = 2.f * (a * b - c * d); m[1][1] = -aa + bb - cc + dd; m[1][2] = 2.f * (b * c + a * d);
+    m[2][0] = 2.f * (a * c + b * d); m[2][1] = 2.f * (b * c - a * d); m[2][2] = -aa - bb + cc + dd;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float rt = 0.f;
+#pragma unroll
+        for (int cidx = 0; cidx < 3; ++cidx) {
+            const float v = m[cidx][r];   // transpose
+            R[3 * r + cidx] = v;
+            RT[4 * r + cidx] = v;
+            rt += v * t[cidx];
+        }
+        RT[4 * r + 3] = -rt;
+        T[r] = t[r];
+    }
+    RT[12] = 0.f; RT[13] = 0.f; RT[14] = 0.f; RT[15] = 1.f;
+}
+
+}  // namespace fpc

@@ -1,0 +1,187 @@
+"""Fused entry of the path: per-pixel head outputs -> per-instance pose table.
+
+Replaces, in one stream of 13 kernel launches with no host synchronisation,
+``Model.class_compression`` -> ``aggregate`` -> ``hough_voting`` ->
+``perform_RT_calculation`` (lib/pose_regressor.py:445-504 of the reference).
+The dense intermediates of the reference (``instance_masks [N,h,w]``,
+``xy_mask [N,2,h,w]``, the ``hn x tn`` inlier matrix) are never materialised
+unless asked for.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import RecoverArgs
+
+
+class PoseRecoveryEngine:
+    """Owns every device buffer one shape of the path needs (workspace, pose table, counters)
+    so that repeated calls allocate nothing and the launch sequence can be CUDA-graphed."""
+
+    def __init__(self, b: int, h: int, w: int, num_classes: int, hn: int, device, *, max_instances: Optional[int] = None,
+                 max_records: Optional[int] = None, max_rows: Optional[int] = None, inlier_thresh: float = 0.999,
+                 min_num: int = 5, max_num: int = 30000, arith: int = _lib.ARITH_IEEE, seed: int = 1234):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PoseRecoveryEngine needs a CUDA device (no CPU path)")
+        self.b, self.h, self.w, self.num_classes, self.hn = b, h, w, num_classes, hn
+        P = b * h * w
+        self.max_instances = int(max_instances if max_instances is not None else max(1024, 128 * b))
+        self.max_records = int(max_records if max_records is not None else P)
+        self.max_rows = int(max_rows if max_rows is not None else min(P, self.max_instances * h))
+        self.inlier_thresh, self.min_num, self.max_num = float(inlier_thresh), int(min_num), int(max_num)
+        self.arith, self.seed = int(arith), int(seed)
+        L = _lib.lib()
+        a = self._base_args()
+        nbytes = L.fpc_pose_recover_workspace_bytes(ctypes.byref(a))
+        if nbytes == 0:
+            raise RuntimeError("libfpc_b200: " + L.fpc_last_error().decode())
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.pose_table = torch.zeros((self.max_instances, _lib.POSE_ROW), dtype=torch.float32, device=self.device)
+        self.counters = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int32, device=self.device)
+        self.counters_host = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int32).pin_memory()
+        self.cat_mask_u8 = torch.empty((b, h, w), dtype=torch.uint8, device=self.device)
+        self.labels = torch.empty((b, h, w), dtype=torch.int32, device=self.device)
+        self.hyp = torch.empty((self.max_instances, hn, 2), dtype=torch.float32, device=self.device)
+        self.votes = torch.empty((self.max_instances, hn), dtype=torch.int32, device=self.device)
+        self.num_launches = int(L.fpc_pose_recover_num_launches())
+
+    def _base_args(self) -> RecoverArgs:
+        a = RecoverArgs()
+        a.b, a.h, a.w, a.num_classes, a.hn = self.b, self.h, self.w, self.num_classes, self.hn
+        a.max_instances, a.max_records, a.max_rows = self.max_instances, self.max_records, self.max_rows
+        a.inlier_thresh, a.min_num, a.max_num = self.inlier_thresh, self.min_num, self.max_num
+        a.arith, a.seed = self.arith, self.seed
+        return a
+
+    def launch(self, logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, idxs: Optional[torch.Tensor] = None,
+               select_u: Optional[torch.Tensor] = None) -> None:
+        """Enqueues the 13 kernels on the current stream.  No synchronisation."""
+        b, h, w, C, K = self.b, self.h, self.w, self.num_classes, self.num_classes - 1
+        f32 = torch.float32
+        mask = _lib.require_cuda(logits["mask"], "logits['mask']", f32)
+        quat = _lib.require_cuda(logits["quaternion"], "logits['quaternion']", f32)
+        scales = _lib.require_cuda(logits["scales"], "logits['scales']", f32)
+        xy = _lib.require_cuda(logits["xy"], "logits['xy']", f32)
+        z = _lib.require_cuda(logits["z"], "logits['z']", f32)
+        # torch.inverse returns a column-major tensor; a 3x3 copy is free
+        inv_k = _lib.require_cuda(inv_intrinsics, "inv_intrinsics", f32, contiguous=False).contiguous()
+        self._invk_keepalive = inv_k
+        for t, c, name in ((mask, C, "mask"), (quat, 4 * K, "quaternion"), (scales, 3 * K, "scales"),
+                           (xy, 2 * K, "xy"), (z, K, "z")):
+            if tuple(t.shape) != (b, c, h, w):
+                raise RuntimeError(f"logits['{name}'] must be [{b},{c},{h},{w}], got {tuple(t.shape)}")
+        if tuple(inv_k.shape) != (3, 3):
+            raise RuntimeError("inv_intrinsics must be [3,3]")
+        a = self._base_args()
+        a.mask_logits, a.quaternion, a.scales, a.xy, a.z = mask.data_ptr(), quat.data_ptr(), scales.data_ptr(), xy.data_ptr(), z.data_ptr()
+        a.inv_intrinsics = inv_k.data_ptr()
+        if idxs is not None:
+            idxs = _lib.require_cuda(idxs, "idxs", torch.int32)
+            if idxs.numel() != 0 and idxs.numel() != idxs.shape[0] * self.hn * 2:
+                raise RuntimeError(f"idxs must be [N,{self.hn},(1,)2] int32, got {tuple(idxs.shape)}")
+            if idxs.shape[0] > self.max_instances:
+                idxs = idxs[: self.max_instances].contiguous()   # the capacity flag reports the overflow
+            if idxs.shape[0] < self.max_instances:
+                # the kernel indexes idxs[instance] for every live instance; pad to capacity once
+                pad = torch.zeros((self.max_instances, self.hn, 2), dtype=torch.int32, device=self.device)
+                pad[: idxs.shape[0]] = idxs.reshape(idxs.shape[0], self.hn, 2)
+                idxs = pad
+            self._idxs_keepalive = idxs
+            a.idxs = idxs.data_ptr()
+        if select_u is not None:
+            select_u = _lib.require_cuda(select_u, "select_u", f32)
+            if tuple(select_u.shape) != (b, h, w):
+                raise RuntimeError("select_u must be [b,h,w]")
+            a.select_u = select_u.data_ptr()
+        a.pose_table, a.counters = self.pose_table.data_ptr(), self.counters.data_ptr()
+        a.cat_mask_u8, a.labels = self.cat_mask_u8.data_ptr(), self.labels.data_ptr()
+        a.hyp_out, a.vote_counts_out = self.hyp.data_ptr(), self.votes.data_ptr()
+        a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
+        a.stream = _lib.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fpc_pose_recover(ctypes.byref(a)))
+
+    def fetch_count(self) -> int:
+        """The path's single device->host read: N (and the capacity flags)."""
+        self.counters_host.copy_(self.counters, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        c = self.counters_host
+        flags = int(c[_lib.CNT_FLAGS])
+        if flags:
+            what = [n for bit, n in ((_lib.FLAG_INSTANCES, f"instances ({int(c[_lib.CNT_INSTANCES])} > max_instances={self.max_instances})"),
+                                     (_lib.FLAG_ROWS, f"rows ({int(c[_lib.CNT_ROWS])} > max_rows={self.max_rows})"),
+                                     (_lib.FLAG_RECORDS, f"records ({int(c[_lib.CNT_RECORDS])} > max_records={self.max_records})"))
+                    if flags & bit]
+            raise RuntimeError("libfpc_b200 error -3 (FPC_ECAPACITY): capacity exceeded for " + ", ".join(what))
+        return int(c[_lib.CNT_INSTANCES])
+
+    def table_to_agg(self, n: int, table: Optional[torch.Tensor] = None, sample_offset: int = 0) -> Dict[str, torch.Tensor]:
+        """Slices the first ``n`` pose-table rows into the reference's AggData keys (lib/type_hinting.py:19-32)."""
+        return table_to_agg(self.pose_table if table is None else table, n, sample_offset)
+
+
+def table_to_agg(table: torch.Tensor, n: int, sample_offset: int = 0) -> Dict[str, torch.Tensor]:
+    t = table[:n]
+    ti = t.view(torch.int32)
+    L = _lib
+    xy = t[:, L.ROW_XY:L.ROW_XY + 2].contiguous()
+    agg = {
+        "class_ids": ti[:, L.ROW_CLASS].to(torch.int64),
+        "sample_ids": ti[:, L.ROW_SAMPLE].to(torch.int64) + sample_offset,
+        "quaternion": t[:, L.ROW_Q:L.ROW_Q + 4].contiguous(),
+        "scales": t[:, L.ROW_SCALES:L.ROW_SCALES + 3].contiguous(),
+        "xy": xy,
+        "z": t[:, L.ROW_Z:L.ROW_Z + 1].contiguous(),
+        "R": t[:, L.ROW_R:L.ROW_R + 9].reshape(n, 3, 3),
+        "T": t[:, L.ROW_T:L.ROW_T + 3].contiguous(),
+        "RT": t[:, L.ROW_RT:L.ROW_RT + 16].reshape(n, 4, 4),
+        "hypothesis": xy.unsqueeze(1),
+        "pruned_hypothesis": xy.unsqueeze(1),
+        # extras (not in the reference's AggData)
+        "mask_sizes": ti[:, L.ROW_COUNT].to(torch.int64),
+        "win_hypothesis": t[:, L.ROW_HYP:L.ROW_HYP + 2].contiguous(),
+        "win_idx": ti[:, L.ROW_WIN_IDX].to(torch.int64),
+        "win_counts": ti[:, L.ROW_WIN_COUNT].to(torch.int64),
+        "tn": ti[:, L.ROW_TN].to(torch.int64),
+        "refine_inliers": ti[:, L.ROW_REFINE_INL].to(torch.int64),
+    }
+    return agg
+
+
+_engines: Dict[tuple, PoseRecoveryEngine] = {}
+
+
+def get_engine(b, h, w, num_classes, hn, device, **kw) -> PoseRecoveryEngine:
+    key = (b, h, w, num_classes, hn, str(torch.device(device)), tuple(sorted(kw.items())))
+    eng = _engines.get(key)
+    if eng is None:
+        eng = PoseRecoveryEngine(b, h, w, num_classes, hn, device, **kw)
+        _engines[key] = eng
+    return eng
+
+
+def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, hn: int, idxs: Optional[torch.Tensor] = None,
+                 *, select_u: Optional[torch.Tensor] = None, materialize_dense: bool = False, **engine_kw) -> Dict[str, torch.Tensor]:
+    """logits (LogitData, lib/type_hinting.py:5-10) -> AggData with the reference's keys.
+
+    ``idxs``: fixed pre-sampled hypothesis pixel pairs ``[N,hn,2]`` (or ``[N,hn,1,2]``) int32, instance
+    order; ``None`` samples on the device.  ``materialize_dense=True`` additionally returns the
+    reference's dense ``instance_masks [N,h,w]`` and ``xy_mask [N,2,h,w]``."""
+    mask = logits["mask"]
+    b, C, h, w = mask.shape
+    eng = get_engine(b, h, w, C, hn, mask.device, **engine_kw)
+    eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
+    n = eng.fetch_count()
+    agg = eng.table_to_agg(n)
+    agg["cat_mask"] = eng.cat_mask_u8
+    agg["labels"] = eng.labels
+    if materialize_dense:
+        from .aggregation_layer import materialize_instance_masks, materialize_xy_mask
+        agg["instance_masks"] = materialize_instance_masks(eng.labels, agg["sample_ids"], n)
+        agg["xy_mask"] = materialize_xy_mask(eng.labels, eng.cat_mask_u8, logits["xy"], agg["sample_ids"], n)
+    return agg

@@ -1,0 +1,185 @@
+/*
+ * fpc_b200.h -- C ABI of libfpc_b200.so: FastPoseCNN's post-network pose-recovery
+ * path as hand-written sm_100a CUDA kernels.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - the library allocates nothing, keeps nothing: the caller owns inputs, outputs
+ *     and the workspace (query its size with the matching *_workspace_bytes call);
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*);
+ *     no call synchronises, so every call can be captured in a CUDA graph;
+ *   - every function returns FPC_OK or a negative FPC_E* code and never exits or
+ *     throws (the reference's gpuErrchk calls exit(), src/cuda_common.h:19-26);
+ *     fpc_last_error() returns the message of the calling thread's last failure;
+ *   - there is no CPU fallback.
+ *
+ * File:line citations below are relative to
+ * /root/reference/source_code/FastPoseCNN/ and name the reference interface each
+ * entry point replaces.
+ */
+#ifndef FPC_B200_H_
+#define FPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPC_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define FPC_API __attribute__((visibility("default")))
+#else
+#define FPC_API
+#endif
+
+enum {
+    FPC_OK = 0,
+    FPC_EINVAL = -1,    /* bad argument (null pointer, non-positive size, misalignment) */
+    FPC_ECUDA = -2,     /* a CUDA runtime call or launch failed                        */
+    FPC_ECAPACITY = -3, /* workspace / table capacity too small for this call          */
+};
+
+/* Arithmetic of the hypothesis and voting kernels.  Both are IEEE binary32.
+ *   FPC_ARITH_IEEE      every product and sum rounded separately, in source order
+ *                       (what a CPU build of ransac_voting_kernel.cu computes; the oracle)
+ *   FPC_ARITH_NVCC_FMA  the contraction pattern nvcc applies to the same source for
+ *                       sm_100a (a*b + c*d -> fma(a, b, c*d)); matches a GPU build of the
+ *                       reference kernels */
+enum { FPC_ARITH_IEEE = 0, FPC_ARITH_NVCC_FMA = 1 };
+
+FPC_API int fpc_version(void);
+FPC_API const char *fpc_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * 1:1 mirrors of the reference's native module `ransac_voting`
+ * ---------------------------------------------------------------------------------- */
+
+/* lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:20-31 (kernel: ransac_voting_kernel.cu:11-49).
+ * direct [tn,vn,2] f32, coords [tn,2] f32, idxs [hn,vn,2] i32 -> hypo_pts [hn,vn,2] f32.
+ * Degenerate pairs (|det| < 1e-6) yield (0,0), as the reference's at::zeros output does. */
+FPC_API int fpc_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs,
+                            float *hypo_pts, int tn, int vn, int hn, int arith, void *stream);
+
+/* lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:41-55 (kernel: ransac_voting_kernel.cu:88-126).
+ * Sets inliers[hi,vi,ti] = 1 where the cosine test passes; like the reference it never
+ * writes zeros (the caller pre-zeroes, ransac_voting_gpu.py:562). */
+FPC_API int fpc_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo_pts,
+                              uint8_t *inliers, int tn, int vn, int hn, float inlier_thresh,
+                              int arith, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Stage entry points behind the reference's Python operators
+ * ---------------------------------------------------------------------------------- */
+
+/* gpu_tensor_funcs.normalize (lib/gpu_tensor_funcs.py:37-50) for a contiguous
+ * [outer, c, inner] view normalised over the middle axis. */
+FPC_API int fpc_normalize(const float *in, float *out, long long outer, int c, long long inner, void *stream);
+
+/* Model.class_compression (lib/pose_regressor.py:445-457) = arg-max over the mask logits
+ * + gpu_tensor_funcs.class_compress (lib/gpu_tensor_funcs.py:52-99).
+ *   mask_logits [b,C,h,w] (may be NULL when cat_mask_in is given)
+ *   cat_mask_in [b,h,w] i64 or NULL (NULL: computed from mask_logits and written to cat_mask_out)
+ *   heads: quaternion [b,4(C-1),h,w], scales [b,3(C-1),h,w], xy [b,2(C-1),h,w], z [b,C-1,h,w]
+ *   outputs: cat_mask_out [b,h,w] i64 (may be NULL), q_out [b,4,h,w], s_out [b,3,h,w],
+ *            xy_out [b,2,h,w], z_out [b,h,w]; q and xy are L2-normalised per pixel. */
+FPC_API int fpc_class_compress(const float *mask_logits, const int64_t *cat_mask_in,
+                       const float *quaternion, const float *scales, const float *xy, const float *z,
+                       int64_t *cat_mask_out, float *q_out, float *s_out, float *xy_out, float *z_out,
+                       int b, int num_classes, int h, int w, void *stream);
+
+/* gpu_tensor_funcs.batchwise_get_RT / samplewise_get_RT (lib/gpu_tensor_funcs.py:204-253)
+ * with quats_2_rotation_matrix (:306-326).  q [n,4], xy [n,2], z [n,1], inv_k [3,3]
+ * -> R [n,3,3], T [n,3], RT [n,4,4]. */
+FPC_API int fpc_get_rt(const float *q, const float *xy, const float *z, const float *inv_k,
+               float *R, float *T, float *RT, int n, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * The fused path: head maps -> per-instance pose table
+ * (Model.class_compression + aggregate + hough_voting + perform_RT_calculation,
+ *  lib/pose_regressor.py:445-504)
+ * ---------------------------------------------------------------------------------- */
+
+#define FPC_POSE_ROW 48 /* 32-bit words per pose-table row */
+/* word offsets inside a pose-table row (ints are stored as int32 bit patterns) */
+enum {
+    FPC_ROW_CLASS = 0,   /* i32  class id = min non-zero class in the component (aggregation_layer.py:113) */
+    FPC_ROW_SAMPLE = 1,  /* i32  frame index (sample_ids, :91-98)                                           */
+    FPC_ROW_COUNT = 2,   /* i32  pixels in the instance mask                                                */
+    FPC_ROW_Q = 3,       /* f32x4 normalised mean quaternion                                               */
+    FPC_ROW_SCALES = 7,  /* f32x3 mean scales                                                              */
+    FPC_ROW_XY = 10,     /* f32x2 refined centre (x = column, y = row)                                     */
+    FPC_ROW_Z = 12,      /* f32   exp(mean z)                                                              */
+    FPC_ROW_T = 13,      /* f32x3                                                                          */
+    FPC_ROW_R = 16,      /* f32x9 row-major                                                                */
+    FPC_ROW_RT = 25,     /* f32x16 row-major                                                               */
+    FPC_ROW_HYP = 41,    /* f32x2 winning (unrefined) hypothesis                                           */
+    FPC_ROW_WIN_IDX = 43,   /* i32 index of the winning hypothesis (first max)                             */
+    FPC_ROW_WIN_COUNT = 44, /* i32 its inlier count                                                        */
+    FPC_ROW_TN = 45,        /* i32 pixels that voted (after the max_num sub-sampling)                      */
+    FPC_ROW_REFINE_INL = 46,/* i32 inliers of the refinement vote                                          */
+    FPC_ROW_BBOX = 47,      /* i32 (ymin << 16) | xmin                                                     */
+};
+
+/* counters[] words the host reads back (one D2H copy of FPC_NUM_COUNTERS int32) */
+enum {
+    FPC_CNT_INSTANCES = 0, /* N found (may exceed max_instances -> FPC_FLAG_INSTANCES)  */
+    FPC_CNT_ROWS = 1,
+    FPC_CNT_RECORDS = 2,
+    FPC_CNT_WORK = 3,
+    FPC_CNT_FLAGS = 4,
+    FPC_CNT_TICKET = 5,
+    FPC_NUM_COUNTERS = 16,
+};
+enum { FPC_FLAG_INSTANCES = 1, FPC_FLAG_ROWS = 2, FPC_FLAG_RECORDS = 4 };
+
+typedef struct fpc_recover_args {
+    /* sizes */
+    int32_t b, h, w, num_classes; /* num_classes includes background */
+    int32_t hn;                   /* hypotheses per instance (HPARAM.HV_NUM_OF_HYPOTHESES) */
+    int32_t max_instances;        /* capacity of every per-instance table                  */
+    int64_t max_records;          /* capacity of the voting-record array (<= b*h*w)        */
+    int64_t max_rows;             /* capacity of the (instance,row) table (<= b*h*w)       */
+    /* voting parameters (ransac_voting_gpu.py:518-519) */
+    float inlier_thresh;
+    int32_t min_num, max_num;
+    int32_t arith;                /* FPC_ARITH_*                                           */
+    uint64_t seed;                /* device-side sampling when idxs / select_u are NULL    */
+    /* inputs */
+    const float *mask_logits;     /* [b,C,h,w]          */
+    const float *quaternion;      /* [b,4(C-1),h,w]     */
+    const float *scales;          /* [b,3(C-1),h,w]     */
+    const float *xy;              /* [b,2(C-1),h,w]     */
+    const float *z;               /* [b,C-1,h,w]        */
+    const float *inv_intrinsics;  /* [3,3]              */
+    const int32_t *idxs;          /* [max_instances,hn,2] fixed pre-sampled pixel pairs, or NULL */
+    const float *select_u;        /* [b,h,w] uniforms for the max_num sub-sampling, or NULL      */
+    /* outputs */
+    float *pose_table;            /* [max_instances, FPC_POSE_ROW]                         */
+    int32_t *counters;            /* [FPC_NUM_COUNTERS]                                    */
+    uint8_t *cat_mask_u8;         /* [b,h,w] predicted class per pixel (may be NULL -> in workspace) */
+    int32_t *labels;              /* [b,h,w] instance id + 1, 0 = background (may be NULL -> workspace) */
+    float *hyp_out;               /* [max_instances,hn,2] or NULL                          */
+    int32_t *vote_counts_out;     /* [max_instances,hn]  or NULL (then kept in workspace)  */
+    /* scratch */
+    void *workspace;
+    size_t workspace_bytes;
+    void *stream;
+} fpc_recover_args;
+
+/* Workspace size for fpc_pose_recover with these sizes (only the size fields are read). */
+FPC_API size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *args);
+
+/* Runs the whole path.  Launches only; read `counters` (and the first
+ * counters[FPC_CNT_INSTANCES] rows of pose_table) after synchronising the stream. */
+FPC_API int fpc_pose_recover(const fpc_recover_args *args);
+
+/* Number of kernels fpc_pose_recover launches per call (for launch accounting). */
+FPC_API int fpc_pose_recover_num_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPC_B200_H_ */
