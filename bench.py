@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the pose-recovery hot path (BASELINE.json metric: aggregation+voting frames/s @640x480 b32).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (head maps -> per-instance pose table) over one batch of
+synthetic NOCS-shaped head outputs: BASELINE.json configs[1] (b=32 frames of 640x480, 6 classes x 3
+instances, 128 fixed pre-sampled hypotheses per instance) PER GPU (weak scaling: frames are sharded by
+image, the only collective is the all-gather of the per-instance pose tables).
+
+Prints ONE JSON line on rank 0 (see the task contract); `value` = frames/s with inputs resident in HBM,
+`e2e` = frames/s through the public API with HOST (pinned) head maps, H2D/D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "aggregation+voting frames/s @640x480 b32"
+UNIT = "frames/s"
+
+
+# --------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_frames_per_s(wl, frames_per_step: int, steps: int, warmup: int):
+    """The oracle port (reference algorithm on CPU tensors: torch-CPU aggregation + scipy CCL + the C
+    restatement of the voting kernels) on a bounded sample of the workload, all host threads."""
+    from fastposecnn_b200 import synthetic as syn
+    from oracle import native, port
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    logits = syn.render_workload(wl, batch=frames_per_step, seed=0, device="cpu")
+    inv_k = torch.inverse(syn.camera_intrinsics())
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        port.pose_recover(logits, inv_k, wl.hyps, idx_source=port.seeded_idx_source(1234))
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return frames_per_step * len(times) / total, total / len(times), ncores, native.num_threads()
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fastposecnn_b200 import synthetic as syn
+    wl = syn.WORKLOADS[args.workload]
+    frames_per_step = args.ref_frames
+    fps, s_per_step, ncores, omp = cpu_reference_frames_per_s(wl, frames_per_step, args.steps, args.warmup)
+    sample = (f"{frames_per_step} frames of {wl.name} per step ({args.steps} timed steps after {args.warmup} warm-up), "
+              f"oracle/port.py on CPU tensors, torch threads={ncores}, OpenMP threads={omp}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "frames_per_step": frames_per_step, "hypotheses": wl.hyps,
+                   "instances_per_frame": wl.instances_per_frame},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from fastposecnn_b200 import _lib
+    from fastposecnn_b200 import synthetic as syn
+    from fastposecnn_b200.pose_recovery import PoseRecoveryEngine
+    from fastposecnn_b200.sharding import gather_pose_tables
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device: the path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = syn.WORKLOADS[args.workload]
+    bpg = args.batch_per_gpu or wl.batch
+    hn = wl.hyps
+    hbm_peak, peak_src = load_peaks()
+
+    # ---- synthetic inputs, resident in HBM (2.6 GB per 32 frames: far larger than the 126 MB L2) ----
+    logits = syn.render_workload(wl, batch=bpg, seed=1000 + rank, device=dev)
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(dev).contiguous()
+    discs = wl.discs()
+    tn_disc = [syn.disc_pixel_count(cx, cy, r, wl.h, wl.w) for (cx, cy, r, _c) in discs]
+    n_expected = bpg * len(discs)
+    eng = PoseRecoveryEngine(bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected))
+    idxs = torch.zeros((eng.max_instances, hn, 2), dtype=torch.int32)
+    idxs[:n_expected] = syn.presampled_idxs(tn_disc * bpg, hn, seed=1234).reshape(n_expected, hn, 2)
+    idxs = idxs.to(dev)
+    gathered = torch.empty((world, eng.max_instances + 1, _lib.POSE_ROW), dtype=torch.float32, device=dev) if world > 1 else None
+
+    nk = eng.num_launches
+    kernel_names = [_lib.lib().fpc_pose_recover_kernel_name(k).decode() for k in range(nk)]
+
+    def make_events(n):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        for e in evs:
+            e.record()           # instantiates the cudaEvent_t
+        return evs
+
+    def step(stage_events=None):
+        eng.launch(logits, inv_k, idxs=idxs, stage_events=stage_events)
+        if world > 1:
+            gather_pose_tables(eng, gathered)
+        return eng.fetch_count()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        n = step()
+    if n != n_expected:
+        raise RuntimeError(f"synthetic workload produced {n} instances, expected {n_expected}")
+    step_events = [make_events(nk + 1) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+
+    # ---- FP32 peak of this chip (pure FFMA loop), denominator of the voting roofline ----
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fma_blocks, fma_iters = sms * 16, 1 << 14
+    best_ms = None
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().fpc_bench_fp32_fma(sink.data_ptr(), fma_blocks, fma_iters, _lib.current_stream(dev)))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best_ms = ms if best_ms is None else min(best_ms, ms)
+    fp32_peak_tflops = fma_blocks * 256 * fma_iters * 16 * 2 / (best_ms * 1e-3) / 1e12
+
+    # ---- timed region: K steps, device-timed, barrier + synchronize on both sides ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        step(step_events[k])
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * bpg / (ms_per_step * 1e-3)
+
+    # per-kernel durations inside the timed region (events recorded by the library between launches)
+    kernel_ms = [0.0] * nk
+    for evs in step_events:
+        for k in range(nk):
+            kernel_ms[k] += evs[k].elapsed_time(evs[k + 1])
+    kernel_ms = [v / args.steps for v in kernel_ms]
+
+    # ---- algorithmic work ----
+    hw = wl.h * wl.w
+    fg = sum(tn_disc)
+    bytes_argmax = 4 * wl.num_classes * hw * bpg                      # 28 B per pixel: the 7 mask logits
+    bytes_gather = 40 * fg * bpg                                      # predicted class's 4+3+2+1 floats, fg pixels only
+    bytes_agg = (4 * wl.num_classes * hw + 40 * fg + 184 * len(discs)) * bpg
+    flop_vote = sum(12.0 * tn * (hn + 1) + 4.0 * tn for tn in tn_disc) * bpg
+    i_arg, i_gather, i_vote = kernel_names.index("k_argmax_init"), kernel_names.index("k_gather"), kernel_names.index("k_vote")
+    agg_ms = sum(kernel_ms[k] for k in range(nk) if k not in (i_vote,))
+    def hbm(bytes_, ms):
+        a = bytes_ / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": None}
+    roof_argmax = dict(hbm(bytes_argmax, kernel_ms[i_arg]), kernel="k_argmax_init", ms=kernel_ms[i_arg],
+                       algorithmic_bytes=bytes_argmax, peak_source=peak_src)
+    roof_gather = dict(hbm(bytes_gather, kernel_ms[i_gather]), kernel="k_gather", ms=kernel_ms[i_gather],
+                       algorithmic_bytes=bytes_gather, peak_source=peak_src)
+    roof_agg = dict(hbm(bytes_agg, agg_ms), kernel="all aggregation kernels (everything but k_vote)", ms=agg_ms,
+                    algorithmic_bytes=bytes_agg, peak_source=peak_src)
+    a_v = flop_vote / (kernel_ms[i_vote] * 1e-3) / 1e12
+    roof_vote = {"bound": "fp32", "achieved": a_v, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": a_v / fp32_peak_tflops,
+                 "traffic": None, "kernel": "k_vote", "ms": kernel_ms[i_vote], "algorithmic_flop": flop_vote,
+                 "votes_per_s": flop_vote / 12.0 / (kernel_ms[i_vote] * 1e-3),
+                 "peak_source": "measured in this run: fpc_bench_fp32_fma (pure FFMA loop), 2 flop per FMA"}
+    dominant = max(range(nk), key=lambda k: kernel_ms[k])
+
+    # ---- end to end through the public API with HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in logits.items()}
+        for k, v in logits.items():
+            host[k].copy_(v)
+        dev_in = {k: torch.empty_like(v) for k, v in logits.items()}
+        table_host = torch.empty((eng.max_instances, _lib.POSE_ROW), dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+        def e2e_step():
+            for k in host:
+                dev_in[k].copy_(host[k], non_blocking=True)
+            eng.launch(dev_in, inv_k, idxs=idxs)
+            if world > 1:
+                gather_pose_tables(eng, gathered)
+            n_ = eng.fetch_count()
+            table_host[:n_].copy_(eng.pose_table[:n_], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return n_
+        for _ in range(2):
+            n_ = e2e_step()
+        d2h = n_ * _lib.POSE_ROW * 4 + _lib.NUM_COUNTERS * 4
+        ksteps = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(ksteps):
+            e2e_step()
+        s1.record()
+        torch.cuda.synchronize()
+        ems = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": world * bpg / (ems / ksteps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ems / ksteps, "steps": ksteps,
+               "note": "pinned host head maps -> H2D -> fpc_pose_recover -> D2H of N and the pose table, every step; PCIe-bound"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        fps, s_per, ncores, omp = cpu_reference_frames_per_s(wl, args.ref_frames, 3, 1)
+        cpu = {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port",
+               "sample": f"{args.ref_frames} frames of {wl.name}, 1 warm-up + 3 timed passes of oracle/port.py "
+                         f"(torch-CPU aggregation + scipy CCL + C voting kernels, OpenMP threads={omp})"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "frames_per_gpu": bpg, "global_batch": world * bpg, "hypotheses": hn,
+                       "instances_per_frame": len(discs), "parallelism": f"image-sharded x{world}",
+                       "l2": "inputs (2.6 GB of head maps per GPU) are larger than the 126 MB L2; no flush needed",
+                       "arith": "IEEE (un-contracted) voting arithmetic", "timed": "13 kernels + D2H read of N"
+                                + (" + NCCL all-gather of pose tables" if world > 1 else "")},
+            "roofline": roof_argmax if kernel_names[dominant] != "k_gather" else roof_gather,
+            "roofline_fp32_voting": roof_vote,
+            "roofline_gather": roof_gather,
+            "roofline_aggregation_total": roof_agg,
+            "dominant_kernel": kernel_names[dominant],
+            "kernel_ms": {kernel_names[k]: round(kernel_ms[k], 5) for k in range(nk)},
+            "fp32_peak_tflops_measured": fp32_peak_tflops,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": nk * args.steps,
+            "clocks": clocks,
+            "instances": n,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--batch-per-gpu", type=int, default=0, help="frames per GPU (default: the workload's batch, 32 for cfg2)")
+    ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference pass (bounded sample)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "b200" and world != args.gpus:
+        if args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,8 @@ ROW_HYP, ROW_WIN_IDX, ROW_WIN_COUNT, ROW_TN, ROW_REFINE_INL, ROW_BBOX = 41, 43, 
 EXPORTS = (
     "fpc_version", "fpc_last_error", "fpc_generate_hypothesis", "fpc_voting_for_hypothesis",
     "fpc_normalize", "fpc_class_compress", "fpc_get_rt", "fpc_pose_recover_workspace_bytes",
-    "fpc_pose_recover", "fpc_pose_recover_num_launches", "fpc_aggregate_workspace_bytes", "fpc_aggregate",
+    "fpc_pose_recover", "fpc_pose_recover_num_launches", "fpc_pose_recover_kernel_name", "fpc_bench_fp32_fma",
+    "fpc_aggregate_workspace_bytes", "fpc_aggregate",
     "fpc_vote_dense_workspace_bytes", "fpc_vote_dense", "fpc_materialize_instances",
 )
 
@@ -47,6 +48,7 @@ class RecoverArgs(ctypes.Structure):
         ("pose_table", _vp), ("counters", _vp), ("cat_mask_u8", _vp), ("labels", _vp),
         ("hyp_out", _vp), ("vote_counts_out", _vp),
         ("workspace", _vp), ("workspace_bytes", ctypes.c_size_t), ("stream", _vp),
+        ("stage_events", ctypes.POINTER(_vp)), ("num_stage_events", ctypes.c_int32),
     ]
 
 
@@ -74,6 +76,10 @@ def lib() -> ctypes.CDLL:
     L.fpc_pose_recover_workspace_bytes.restype = ctypes.c_size_t
     L.fpc_pose_recover.argtypes = [ctypes.POINTER(RecoverArgs)]
     L.fpc_pose_recover_num_launches.restype = _i
+    L.fpc_pose_recover_kernel_name.argtypes = [_i]
+    L.fpc_pose_recover_kernel_name.restype = ctypes.c_char_p
+    L.fpc_bench_fp32_fma.argtypes = [_vp, _i, _i, _vp]
+    L.fpc_bench_fp32_fma.restype = _i
     for name in ("fpc_generate_hypothesis", "fpc_voting_for_hypothesis", "fpc_normalize", "fpc_class_compress",
                  "fpc_get_rt", "fpc_pose_recover"):
         getattr(L, name).restype = _i

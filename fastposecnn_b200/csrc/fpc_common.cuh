@@ -21,10 +21,17 @@ int fail(int code, const char *fmt, ...);
         if (e_ != cudaSuccess) return ::fpc::fail(FPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+// Optional per-kernel timing: the caller may hand fpc_pose_recover an array of cudaEvent_t; event 0 is
+// recorded before the first kernel and event k after the k-th launch (thread-local cursor).
+void stage_begin(void **events, int n, cudaStream_t st);
+void stage_mark();
+void stage_end();
+
 #define FPC_LAUNCH_CHECK(name)                                                               \
     do {                                                                                     \
         cudaError_t e_ = cudaGetLastError();                                                 \
         if (e_ != cudaSuccess) return ::fpc::fail(FPC_ECUDA, "launch of %s: %s", name, cudaGetErrorString(e_)); \
+        ::fpc::stage_mark();                                                                 \
     } while (0)
 
 constexpr unsigned FULL = 0xffffffffu;

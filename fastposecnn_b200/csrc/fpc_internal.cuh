@@ -54,7 +54,7 @@ struct Workspace {
     int *votes;        // [max_instances, hn]
 };
 
-constexpr int VOTE_CHUNK = 2048;  // pixels per vote work item
+constexpr int VOTE_CHUNK = 1024;  // pixels per vote work item
 
 // fpc_aggregate.cu
 int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,
@@ -67,6 +67,7 @@ int launch_generate_hypothesis(const float *direct, const float *coords, const i
                                int hn, int arith, cudaStream_t st);
 int launch_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo, uint8_t *inliers, int tn,
                                  int vn, int hn, float thresh, int arith, cudaStream_t st);
+void set_vote_packed(int v);
 int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st);
 int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp, const int *votes, const float *inv_k,
                     float *pose_table, cudaStream_t st);

@@ -8,6 +8,8 @@
 //   lib/gpu_tensor_funcs.py:204-253, 306-326                         translation / rotation / RT
 #include "fpc_internal.cuh"
 
+#include <cstdlib>
+
 namespace fpc {
 
 // =============================================================================================
@@ -57,33 +59,101 @@ __global__ void __launch_bounds__(256) k_voting_for_hypothesis(const float *__re
 // =============================================================================================
 // Fused hypothesis generation + vote counting
 // =============================================================================================
-// Work item = (instance, chunk of <= VOTE_CHUNK voting records).  The chunk's pixels are staged in
-// shared memory once, as (x, y, a_x, a_y) with a = dir / (|dir| * thresh); every lane keeps Q
-// hypotheses in registers and walks the pixels with broadcast LDS.128 loads.  No inlier matrix is
-// ever written (the reference materialises hn*tn bytes and re-reads them, ransac_voting_gpu.py:562-566).
+// Work item = (instance, chunk of <= VOTE_CHUNK voting records), handed out through an atomic ticket
+// so every resident block stays busy until the work runs out.  The chunk's pixels are staged in
+// shared memory once as six SoA planes (-x, -y, dir_x, dir_y, k_hi, k_lo); every lane keeps VQ
+// hypotheses in registers and walks the pixels with broadcast LDS.128 loads (4 pixels per load).
+// No inlier matrix is ever written (the reference materialises hn*tn bytes and re-reads them,
+// ransac_voting_gpu.py:562-566).
 //
 // Exactness.  The reference decides   dot(d,n) / (|n| |d|) > thresh   in rounded binary32 ops.
-// The fast test evaluates  s = (d.a)|d.a|  against  |d|^2 (1 +- 2^-16): outside that band the two
-// decisions provably agree (accumulated rounding of either side is < 2e-6 relative); inside it, and
-// for hypotheses within 1e-3 of a pixel lattice point (where |d| can fall under the reference's
-// 1e-6 guard), the reference expression itself is evaluated with explicitly rounded intrinsics.
-constexpr int VT = 256;        // threads per block
-constexpr int VQ = 4;          // hypotheses per lane
-constexpr int VHB = 1024;      // hypotheses per shared-memory batch
-constexpr float BAND_HI = -(1.0f + 1.52587890625e-05f);
-constexpr float BAND_LO = -(1.0f - 1.52587890625e-05f);
+// The fast test compares  s = (d.n)|d.n|  with  |d|^2 * (|n| thresh)^2 * (1 +- e),  e = 2^-18 = 64 u:
+//   hi = s - k_hi |d|^2 >= 0  -> certainly an inlier,   lo = s - k_lo |d|^2 < 0 -> certainly not.
+// Worst-case relative rounding error of the fast ratio is 12 u and of the reference's squared cosine
+// 16 u, so the two decisions can only differ inside the band (28 u < e; derivation in DESIGN.md).
+// Votes that land inside the band (a few per 10^4) are queued in shared memory and settled afterwards
+// by all lanes in parallel with the reference expression itself (explicitly rounded intrinsics), as
+// are all votes of hypotheses within 1e-3 of a pixel-lattice point (where |d| may fall under the
+// reference's 1e-6 guard).  Both sign bits of every vote are collected with funnel shifts, so the hot
+// loop has no branch.
+constexpr int VT = 256;            // threads per block
+constexpr int VQ = 4;              // hypotheses per lane
+constexpr int VHB = 1024;          // hypotheses per shared-memory batch (8 groups of 32 lanes x VQ)
+constexpr int VROUND = 16;         // pixels per sign-collection round (2 bits per vote in a 32-bit word)
+constexpr int VQCAP = 2048;        // deferred exact-vote queue entries
+constexpr float BAND_E = 3.814697265625e-06f;  // 2^-18
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 __device__ __forceinline__ bool near_lattice(float x, float y) {
     return fabsf(x - rintf(x)) < 1e-3f && fabsf(y - rintf(y)) < 1e-3f;
 }
 
-template <int ARITH>
-__global__ void __launch_bounds__(VT) k_vote(InstTables T, const int *__restrict__ counters, PathParams pp,
-                                             const float4 *__restrict__ rec, float2 *__restrict__ hyp_g,
-                                             int *__restrict__ votes) {
-    __shared__ float4 s_px[VOTE_CHUNK];
-    __shared__ float2 s_hyp[VHB];
-    __shared__ int s_cnt[VHB];
+struct VoteSmem {
+    float ncx[VOTE_CHUNK], ncy[VOTE_CHUNK], nx[VOTE_CHUNK], ny[VOTE_CHUNK], khi[VOTE_CHUNK], klo[VOTE_CHUNK];
+    float2 hyp[VHB];
+    unsigned queue[VQCAP];
+    unsigned short exlist[VHB];
+    int qn, nex, wi;
+};
+
+// one vote on the fast path: appends sign(hi), sign(lo) to acc
+__device__ __forceinline__ void vote_fast(float hx, float hy, float ncx, float ncy, float nx, float ny, float khi,
+                                          float klo, unsigned &acc) {
+    const float dx = hx + ncx, dy = hy + ncy;
+    const float d2 = fmaf(dy, dy, dx * dx);
+    const float dt = fmaf(dy, ny, dx * nx);
+    const float s = dt * fabsf(dt);
+    const float hi = fmaf(d2, khi, s);
+    const float lo = fmaf(d2, klo, s);
+    acc = __funnelshift_l(__float_as_uint(hi), acc, 1);
+    acc = __funnelshift_l(__float_as_uint(lo), acc, 1);
+}
+// two pixels (a, b) against one hypothesis, packed f32x2 arithmetic
+__device__ __forceinline__ void vote_fast2(u64 hx2, u64 hy2, u64 ncx2, u64 ncy2, u64 nx2, u64 ny2, u64 khi2, u64 klo2,
+                                           unsigned &acc) {
+    const u64 dx = add2(hx2, ncx2), dy = add2(hy2, ncy2);
+    const u64 d2 = fma2(dy, dy, mul2(dx, dx));
+    const u64 dt = fma2(dy, ny2, mul2(dx, nx2));
+    float dta, dtb;
+    unpk2(dt, dta, dtb);
+    const u64 s = pk2(dta * fabsf(dta), dtb * fabsf(dtb));
+    const u64 hi = fma2(d2, khi2, s), lo = fma2(d2, klo2, s);
+    float hia, hib, loa, lob;
+    unpk2(hi, hia, hib);
+    unpk2(lo, loa, lob);
+    acc = __funnelshift_l(__float_as_uint(hia), acc, 1);
+    acc = __funnelshift_l(__float_as_uint(loa), acc, 1);
+    acc = __funnelshift_l(__float_as_uint(hib), acc, 1);
+    acc = __funnelshift_l(__float_as_uint(lob), acc, 1);
+}
+
+template <int ARITH, bool PACKED>
+__global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ counters, PathParams pp,
+                                                const float4 *__restrict__ rec, float2 *__restrict__ hyp_g,
+                                                int *__restrict__ votes) {
+    __shared__ __align__(16) VoteSmem sm;
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
     const int W = counters[FPC_CNT_WORK];
@@ -91,36 +161,47 @@ __global__ void __launch_bounds__(VT) k_vote(InstTables T, const int *__restrict
     const int hn = pp.hn;
     const float thresh = pp.inlier_thresh;
     const bool all_exact = !(thresh > 0.f);
-    const float inv_t = all_exact ? 0.f : __fdiv_rn(1.0f, thresh);
+    const float t2 = thresh * thresh;
 
-    for (int wi = blockIdx.x; wi < W; wi += gridDim.x) {
+    while (true) {
+        __syncthreads();  // previous work item is done with shared memory
+        if (tid == 0) {
+            sm.wi = atomicAdd(&counters[FPC_CNT_TICKET], 1);
+            sm.qn = 0;
+            sm.nex = 0;
+        }
+        __syncthreads();
+        const int wi = sm.wi;
+        if (wi >= W) break;
         const int i = upper_index(T.workoff, N, wi);
         const int chunk = wi - T.workoff[i];
         const int tn = T.tn[i];
         const int px0 = chunk * VOTE_CHUNK;
         const int npx = min(VOTE_CHUNK, tn - px0);
-        const int nblk = (npx + 31) >> 5;
+        const int nrounds = (npx + VROUND - 1) / VROUND;
         const float4 *rec_i = rec + T.pxoff[i];
-        __syncthreads();  // previous work item is done with shared memory
-        for (int k = tid; k < nblk * 32; k += VT) {
-            float4 v = make_float4(1e18f, 1e18f, 0.f, 0.f);  // padding: can never be an inlier
+        // ---- stage the chunk's pixels ----
+        for (int k = tid; k < nrounds * VROUND; k += VT) {
+            float ncx = -1e18f, ncy = -1e18f, nx = 0.f, ny = 0.f, khi = -1.f, klo = -1.f;  // padding: never an inlier
             if (k < npx) {
                 const float4 r = rec_i[px0 + k];
-                const float n1 = __fsqrt_rn(sum_prod<ARITH>(r.z, r.z, r.w, r.w));
-                v = make_float4(r.x, r.y, 0.f, 0.f);
-                if (!below_1e6(n1)) {
-                    const float sc = inv_t / n1;
-                    v.z = r.z * sc;
-                    v.w = r.w * sc;
+                ncx = -r.x; ncy = -r.y; nx = r.z; ny = r.w;
+                const float n1sq = sum_prod<ARITH>(nx, nx, ny, ny);
+                if (below_1e6(__fsqrt_rn(n1sq))) {
+                    khi = -1e30f; klo = -1e30f;      // the reference skips pixels with |n| < 1e-6 (.cu:119)
+                } else {
+                    const float m = n1sq * t2;
+                    khi = -(m * (1.0f + BAND_E));
+                    klo = -(m * (1.0f - BAND_E));
                 }
             }
-            s_px[k] = v;
+            sm.ncx[k] = ncx; sm.ncy[k] = ncy; sm.nx[k] = nx; sm.ny[k] = ny; sm.khi[k] = khi; sm.klo[k] = klo;
         }
         for (int hb = 0; hb < hn; hb += VHB) {
             const int nh = min(VHB, hn - hb);
             const int G = (nh + 127) >> 7;  // groups of 128 hypotheses (32 lanes x VQ)
+            // ---- hypotheses of this batch (ransac_voting_kernel.cu:11-49) ----
             for (int k = tid; k < G * 128; k += VT) {
-                s_cnt[k] = 0;
                 float2 hp = make_float2(0.f, 0.f);
                 if (k < nh) {
                     const int h = hb + k;
@@ -138,10 +219,12 @@ __global__ void __launch_bounds__(VT) k_vote(InstTables T, const int *__restrict
                     float x, y;
                     if (hypothesis_exact<ARITH>(r0.z, r0.w, r0.x, r0.y, r1.z, r1.w, r1.x, r1.y, x, y)) hp = make_float2(x, y);
                     if (chunk == 0) hyp_g[(size_t)i * hn + h] = hp;
+                    if (all_exact || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex, 1)] = (unsigned short)k;
                 }
-                s_hyp[k] = hp;
+                sm.hyp[k] = hp;
             }
             __syncthreads();
+            // ---- fast voting: warp -> (hypothesis group g, every parts-th round) ----
             const int parts = 8 / G;  // G <= 8 because VHB = 8 * 128
             if (wv < G * parts) {
                 const int g = wv % G, part = wv / G;
@@ -151,51 +234,66 @@ __global__ void __launch_bounds__(VT) k_vote(InstTables T, const int *__restrict
 #pragma unroll
                 for (int q = 0; q < VQ; ++q) {
                     const int idx = g * 128 + q * 32 + lane;
-                    const float2 hp = s_hyp[idx];
-                    hx[q] = hp.x;
-                    hy[q] = hp.y;
+                    const float2 hp = sm.hyp[idx];
+                    hx[q] = hp.x; hy[q] = hp.y;
                     cnt[q] = 0;
-                    ex[q] = (idx < nh) && (all_exact || near_lattice(hp.x, hp.y));
+                    ex[q] = (idx >= nh) || all_exact || near_lattice(hp.x, hp.y);   // not counted on the fast path
                 }
-                for (int blk = part; blk < nblk; blk += parts) {
+                for (int rd = part; rd < nrounds; rd += parts) {
                     unsigned acc[VQ];
 #pragma unroll
                     for (int q = 0; q < VQ; ++q) acc[q] = 0u;
-                    unsigned band = 0u;
-                    const float4 *px = s_px + blk * 32;
-#pragma unroll 8
-                    for (int k = 0; k < 32; ++k) {
-                        const float4 c = px[k];
+                    const int kb = rd * VROUND;
 #pragma unroll
-                        for (int q = 0; q < VQ; ++q) {
-                            const float dx = hx[q] - c.x, dy = hy[q] - c.y;
-                            const float d2 = fmaf(dy, dy, dx * dx);
-                            const float dt = fmaf(dy, c.w, dx * c.z);
-                            const float s = dt * fabsf(dt);
-                            const float hi = fmaf(d2, BAND_HI, s);  // >= 0: certainly an inlier
-                            const float lo = fmaf(d2, BAND_LO, s);  // <  0: certainly not
-                            acc[q] = __funnelshift_l(__float_as_uint(hi), acc[q], 1);  // collect sign(hi)
-                            band |= __float_as_uint(lo) ^ __float_as_uint(hi);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < VQ; ++q) cnt[q] += __popc(~acc[q]);
-                    if ((int)band < 0) {
-                        // some (pixel, hypothesis) pair of this block fell inside the band: settle those exactly
-                        for (int k = 0; k < 32; ++k) {
-                            const float4 c = px[k];
-                            const int kk = blk * 32 + k;
+                    for (int j4 = 0; j4 < VROUND; j4 += 4) {
+                        const float4 ncx = *reinterpret_cast<const float4 *>(&sm.ncx[kb + j4]);
+                        const float4 ncy = *reinterpret_cast<const float4 *>(&sm.ncy[kb + j4]);
+                        const float4 nx = *reinterpret_cast<const float4 *>(&sm.nx[kb + j4]);
+                        const float4 ny = *reinterpret_cast<const float4 *>(&sm.ny[kb + j4]);
+                        const float4 khi = *reinterpret_cast<const float4 *>(&sm.khi[kb + j4]);
+                        const float4 klo = *reinterpret_cast<const float4 *>(&sm.klo[kb + j4]);
+                        if (PACKED) {
+                            const u64 ncxa = pk2(ncx.x, ncx.y), ncxb = pk2(ncx.z, ncx.w);
+                            const u64 ncya = pk2(ncy.x, ncy.y), ncyb = pk2(ncy.z, ncy.w);
+                            const u64 nxa = pk2(nx.x, nx.y), nxb = pk2(nx.z, nx.w);
+                            const u64 nya = pk2(ny.x, ny.y), nyb = pk2(ny.z, ny.w);
+                            const u64 kha = pk2(khi.x, khi.y), khb = pk2(khi.z, khi.w);
+                            const u64 kla = pk2(klo.x, klo.y), klb = pk2(klo.z, klo.w);
 #pragma unroll
                             for (int q = 0; q < VQ; ++q) {
-                                const float dx = hx[q] - c.x, dy = hy[q] - c.y;
-                                const float d2 = fmaf(dy, dy, dx * dx);
-                                const float dt = fmaf(dy, c.w, dx * c.z);
-                                const float s = dt * fabsf(dt);
-                                const float hi = fmaf(d2, BAND_HI, s);
-                                const float lo = fmaf(d2, BAND_LO, s);
-                                if (((__float_as_uint(lo) ^ __float_as_uint(hi)) >> 31) && kk < npx) {
-                                    const float4 r = rec_i[px0 + kk];
-                                    cnt[q] += vote_exact<ARITH>(r.x, r.y, r.z, r.w, hx[q], hy[q], thresh) ? 1 : 0;
+                                const u64 hx2 = pk2(hx[q], hx[q]), hy2 = pk2(hy[q], hy[q]);
+                                vote_fast2(hx2, hy2, ncxa, ncya, nxa, nya, kha, kla, acc[q]);
+                                vote_fast2(hx2, hy2, ncxb, ncyb, nxb, nyb, khb, klb, acc[q]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < VQ; ++q) {
+                                vote_fast(hx[q], hy[q], ncx.x, ncy.x, nx.x, ny.x, khi.x, klo.x, acc[q]);
+                                vote_fast(hx[q], hy[q], ncx.y, ncy.y, nx.y, ny.y, khi.y, klo.y, acc[q]);
+                                vote_fast(hx[q], hy[q], ncx.z, ncy.z, nx.z, ny.z, khi.z, klo.z, acc[q]);
+                                vote_fast(hx[q], hy[q], ncx.w, ncy.w, nx.w, ny.w, khi.w, klo.w, acc[q]);
+                            }
+                        }
+                    }
+                    // pixel j of the round sits at bits (2*(15-j)+1: sign(hi), 2*(15-j): sign(lo))
+#pragma unroll
+                    for (int q = 0; q < VQ; ++q) {
+                        const unsigned a = acc[q];
+                        cnt[q] += __popc(~a & 0xAAAAAAAAu);                 // hi >= 0
+                        unsigned b = (a >> 1) & ~a & 0x55555555u;          // hi < 0 and lo >= 0: inside the band
+                        if (b && !ex[q]) {
+                            const unsigned hidx = (unsigned)(g * 128 + q * 32 + lane);
+                            while (b) {
+                                const int pos = __ffs(b) - 1;
+                                b &= b - 1;
+                                const int k = kb + 15 - (pos >> 1);
+                                if (k < npx) {
+                                    const int slot = atomicAdd(&sm.qn, 1);
+                                    if (slot < VQCAP) {
+                                        sm.queue[slot] = ((unsigned)k << 16) | hidx;
+                                    } else if (vote_exact<ARITH>(-sm.ncx[k], -sm.ncy[k], sm.nx[k], sm.ny[k], hx[q], hy[q], thresh)) {
+                                        atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);   // queue full: settle it right here
+                                    }
                                 }
                             }
                         }
@@ -203,27 +301,33 @@ __global__ void __launch_bounds__(VT) k_vote(InstTables T, const int *__restrict
                 }
 #pragma unroll
                 for (int q = 0; q < VQ; ++q) {
-                    if (ex[q]) {  // hypothesis on (or within 1e-3 of) the pixel lattice: count it with the reference expression
-                        int c = 0;
-                        for (int blk = part; blk < nblk; blk += parts)
-                            for (int k = 0; k < 32; ++k) {
-                                const int kk = blk * 32 + k;
-                                if (kk < npx) {
-                                    const float4 r = rec_i[px0 + kk];
-                                    c += vote_exact<ARITH>(r.x, r.y, r.z, r.w, hx[q], hy[q], thresh) ? 1 : 0;
-                                }
-                            }
-                        cnt[q] = c;
-                    }
                     const int idx = g * 128 + q * 32 + lane;
-                    if (idx < nh && cnt[q]) atomicAdd(&s_cnt[idx], cnt[q]);
+                    if (!ex[q] && cnt[q]) atomicAdd(&votes[(size_t)i * hn + hb + idx], cnt[q]);
                 }
             }
             __syncthreads();
-            for (int k = tid; k < nh; k += VT) {
-                const int c = s_cnt[k];
-                if (c) atomicAdd(&votes[(size_t)i * hn + hb + k], c);
+            // ---- band votes: the reference expression, one queued vote per thread ----
+            const int nq = min(sm.qn, VQCAP);
+            for (int e = tid; e < nq; e += VT) {
+                const unsigned ent = sm.queue[e];
+                const int k = (int)(ent >> 16), hidx = (int)(ent & 0xffffu);
+                const float2 hp = sm.hyp[hidx];
+                if (vote_exact<ARITH>(-sm.ncx[k], -sm.ncy[k], sm.nx[k], sm.ny[k], hp.x, hp.y, thresh))
+                    atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);
             }
+            // ---- hypotheses on (or within 1e-3 of) the pixel lattice: every vote with the reference expression ----
+            const int nex = sm.nex;
+            for (int e = 0; e < nex; ++e) {
+                const int hidx = sm.exlist[e];
+                const float2 hp = sm.hyp[hidx];
+                int c = 0;
+                for (int k = tid; k < npx; k += VT)
+                    c += vote_exact<ARITH>(-sm.ncx[k], -sm.ncy[k], sm.nx[k], sm.ny[k], hp.x, hp.y, thresh) ? 1 : 0;
+                c = __reduce_add_sync(FULL, c);
+                if (lane == 0 && c) atomicAdd(&votes[(size_t)i * hn + hb + hidx], c);
+            }
+            __syncthreads();
+            if (tid == 0) { sm.qn = 0; sm.nex = 0; }
             __syncthreads();
         }
     }
@@ -416,14 +520,37 @@ int launch_voting_for_hypothesis(const float *direct, const float *coords, const
     return FPC_OK;
 }
 
-int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st) {
-    const int grid = sm_count() * 4;
-    if (pp.arith == FPC_ARITH_IEEE)
-        k_vote<FPC_ARITH_IEEE><<<grid, VT, 0, st>>>(ws.T, ws.counters, pp, ws.rec, hyp_out, votes);
-    else
-        k_vote<FPC_ARITH_NVCC_FMA><<<grid, VT, 0, st>>>(ws.T, ws.counters, pp, ws.rec, hyp_out, votes);
+// Inner-loop variant: 1 = packed f32x2 arithmetic (FFMA2/FMUL2/FADD2, Blackwell only), 0 = scalar.
+// FPC_VOTE_PACKED=0 in the environment selects the scalar loop (kept for A/B measurements).
+static int g_vote_packed = -1;
+void set_vote_packed(int v) { g_vote_packed = v; }
+static int vote_packed() {
+    if (g_vote_packed < 0) {
+        const char *e = getenv("FPC_VOTE_PACKED");
+        g_vote_packed = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_vote_packed;
+}
+
+template <int ARITH, bool PACKED>
+static int launch_vote_t(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st) {
+    static thread_local int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vote<ARITH, PACKED>, VT, 0) != cudaSuccess || n < 1) n = 2;
+        blocks_per_sm = n;
+    }
+    k_vote<ARITH, PACKED><<<sm_count() * blocks_per_sm, VT, 0, st>>>(ws.T, ws.counters, pp, ws.rec, hyp_out, votes);
     FPC_LAUNCH_CHECK("k_vote");
     return FPC_OK;
+}
+
+int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st) {
+    if (pp.arith == FPC_ARITH_IEEE)
+        return vote_packed() ? launch_vote_t<FPC_ARITH_IEEE, true>(ws, pp, hyp_out, votes, st)
+                             : launch_vote_t<FPC_ARITH_IEEE, false>(ws, pp, hyp_out, votes, st);
+    return vote_packed() ? launch_vote_t<FPC_ARITH_NVCC_FMA, true>(ws, pp, hyp_out, votes, st)
+                         : launch_vote_t<FPC_ARITH_NVCC_FMA, false>(ws, pp, hyp_out, votes, st);
 }
 
 int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp, const int *votes, const float *inv_k,

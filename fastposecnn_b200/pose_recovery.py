@@ -41,8 +41,10 @@ class PoseRecoveryEngine:
         if nbytes == 0:
             raise RuntimeError("libfpc_b200: " + L.fpc_last_error().decode())
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        self.pose_table = torch.zeros((self.max_instances, _lib.POSE_ROW), dtype=torch.float32, device=self.device)
-        self.counters = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int32, device=self.device)
+        # one buffer = header row (the counters) + pose rows: it is also the all-gather send buffer (sharding.py)
+        self.table_full = torch.zeros((self.max_instances + 1, _lib.POSE_ROW), dtype=torch.float32, device=self.device)
+        self.pose_table = self.table_full[1:]
+        self.counters = self.table_full[0, :_lib.NUM_COUNTERS].view(torch.int32)
         self.counters_host = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int32).pin_memory()
         self.cat_mask_u8 = torch.empty((b, h, w), dtype=torch.uint8, device=self.device)
         self.labels = torch.empty((b, h, w), dtype=torch.int32, device=self.device)
@@ -59,7 +61,7 @@ class PoseRecoveryEngine:
         return a
 
     def launch(self, logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, idxs: Optional[torch.Tensor] = None,
-               select_u: Optional[torch.Tensor] = None) -> None:
+               select_u: Optional[torch.Tensor] = None, stage_events=None) -> None:
         """Enqueues the 13 kernels on the current stream.  No synchronisation."""
         b, h, w, C, K = self.b, self.h, self.w, self.num_classes, self.num_classes - 1
         f32 = torch.float32
@@ -103,6 +105,12 @@ class PoseRecoveryEngine:
         a.hyp_out, a.vote_counts_out = self.hyp.data_ptr(), self.votes.data_ptr()
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
         a.stream = _lib.current_stream(self.device)
+        if stage_events is not None:
+            # torch creates the cudaEvent_t lazily on the first record(); callers pass recorded events
+            arr = (ctypes.c_void_p * len(stage_events))(*[int(e.cuda_event) for e in stage_events])
+            self._events_keepalive = arr
+            a.stage_events = ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+            a.num_stage_events = len(stage_events)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().fpc_pose_recover(ctypes.byref(a)))
 

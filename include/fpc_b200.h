@@ -167,6 +167,10 @@ typedef struct fpc_recover_args {
     void *workspace;
     size_t workspace_bytes;
     void *stream;
+    /* optional per-kernel timing: cudaEvent_t handles, event 0 recorded before the first kernel and
+     * event k after the k-th launch (k = 1..fpc_pose_recover_num_launches()); NULL entries are skipped */
+    void **stage_events;
+    int32_t num_stage_events;
 } fpc_recover_args;
 
 /* Workspace size for fpc_pose_recover with these sizes (only the size fields are read). */
@@ -178,6 +182,15 @@ FPC_API int fpc_pose_recover(const fpc_recover_args *args);
 
 /* Number of kernels fpc_pose_recover launches per call (for launch accounting). */
 FPC_API int fpc_pose_recover_num_launches(void);
+
+/* Name of the k-th kernel (0-based) fpc_pose_recover launches, for profiles and bench output. */
+FPC_API const char *fpc_pose_recover_kernel_name(int k);
+
+/* Measurement helper (not on the path): a pure FFMA loop, `blocks` x 256 threads, 16 independent
+ * accumulators x `iters` iterations per thread = blocks*256*iters*16 FMAs (x2 flop).  bench.py
+ * times it with CUDA events to get this chip's FP32 peak, the voting kernel's roofline denominator
+ * (MEASURED_PEAKS.json carries none). */
+FPC_API int fpc_bench_fp32_fma(float *sink, int blocks, int iters, void *stream);
 
 #ifdef __cplusplus
 }
