@@ -1,1 +1,23 @@
-"""fastposecnn_b200 -- B200-native pose-recovery path of FastPoseCNN (placeholder, filled below)."""
+"""fastposecnn_b200 -- B200-native (sm_100a) implementation of FastPoseCNN's post-network pose-recovery
+path: per-pixel head outputs -> per-instance 6D pose and size.
+
+Drop-in names (same call signatures and tensor layouts as the reference):
+    AggregationLayer, HoughVotingLayer, ransac_voting_layer_v3, ransac_voting_layer,
+    class_compress, class_compression, normalize, samplewise_get_RT, batchwise_get_RT, Model
+Fused fast entry:
+    pose_recover(logits, inv_intrinsics, hn, idxs=None) / PoseRecoveryEngine
+
+Every operator calls hand-written CUDA kernels in ``libfpc_b200.so`` through a C ABI
+(``include/fpc_b200.h``).  There is no CPU path and no PyTorch fallback: a missing library or a
+non-CUDA tensor raises.
+"""
+from . import synthetic  # noqa: F401  (pure torch, importable without the native library)
+from .aggregation_layer import AggregationLayer  # noqa: F401
+from .gpu_tensor_funcs import (batchwise_get_RT, class_compress, class_compression, normalize,  # noqa: F401
+                               quats_2_rotation_matrix, samplewise_get_RT)
+from .hough_voting import HoughVotingLayer  # noqa: F401
+from .model import Model, PoseRecovery  # noqa: F401
+from .pose_recovery import PoseRecoveryEngine, pose_recover  # noqa: F401
+from .ransac_voting_gpu_layer.ransac_voting_gpu import b_inv, ransac_voting_layer, ransac_voting_layer_v3  # noqa: F401
+
+__version__ = "0.1.0"

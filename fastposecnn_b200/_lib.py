@@ -28,8 +28,7 @@ EXPORTS = (
     "fpc_version", "fpc_last_error", "fpc_generate_hypothesis", "fpc_voting_for_hypothesis",
     "fpc_normalize", "fpc_class_compress", "fpc_get_rt", "fpc_pose_recover_workspace_bytes",
     "fpc_pose_recover", "fpc_pose_recover_num_launches", "fpc_pose_recover_kernel_name", "fpc_bench_fp32_fma",
-    "fpc_aggregate_workspace_bytes", "fpc_aggregate",
-    "fpc_vote_dense_workspace_bytes", "fpc_vote_dense", "fpc_materialize_instances",
+    "fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances",
 )
 
 _vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
@@ -80,6 +79,11 @@ def lib() -> ctypes.CDLL:
     L.fpc_pose_recover_kernel_name.restype = ctypes.c_char_p
     L.fpc_bench_fp32_fma.argtypes = [_vp, _i, _i, _vp]
     L.fpc_bench_fp32_fma.restype = _i
+    L.fpc_aggregate.argtypes = [ctypes.POINTER(RecoverArgs), _vp]
+    L.fpc_vote_dense.argtypes = [ctypes.POINTER(RecoverArgs), _vp, _vp, _i, _i, _vp, _ll, _ll, _ll, _ll, _i]
+    L.fpc_materialize_instances.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]
+    for name in ("fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances"):
+        getattr(L, name).restype = _i
     for name in ("fpc_generate_hypothesis", "fpc_voting_for_hypothesis", "fpc_normalize", "fpc_class_compress",
                  "fpc_get_rt", "fpc_pose_recover"):
         getattr(L, name).restype = _i

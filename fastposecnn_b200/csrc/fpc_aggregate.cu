@@ -10,6 +10,8 @@
 //   lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:532-550  per-instance pixel list in raster order
 #include "fpc_internal.cuh"
 
+#include <algorithm>
+
 namespace fpc {
 
 // =============================================================================================
@@ -368,7 +370,10 @@ __global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counte
 //    (aggregation_layer.py:125-149, on the class-compressed + per-pixel-normalised fields of
 //    gpu_tensor_funcs.py:78-94) and the raster-ordered voting records (x, y, dir_x, dir_y)
 //    (ransac_voting_gpu.py:547-550).  Head maps are read exactly once, foreground pixels only.
-template <bool FUSED_HEADS>
+// MODE 0: raw head maps, class selected per pixel, q/xy normalised here (fused path)
+// MODE 1: class-compressed CategoricalData [b,4|3|2,h,w] (AggregationLayer drop-in)
+// MODE 2: voting records only, directions from a strided `vertex[N,h,w,vn,2]` view (ransac_voting_layer* drop-in)
+template <int MODE>
 __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, const uint8_t *__restrict__ cls,
                                                 InstTables T, RowTables R, const int *__restrict__ counters,
                                                 PathParams pp, FieldSrc F, float4 *__restrict__ rec) {
@@ -397,8 +402,12 @@ __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, c
             float vx = 0.f, vy = 0.f;
             if (mem) {
                 const size_t pix = (size_t)(it.y * pp.w + x);
-                float q0, q1, q2, q3, s0, s1, s2, zz;
-                if (FUSED_HEADS) {
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, zz = 0.f;
+                if (MODE == 2) {
+                    const float *v = F.xy + (long long)(it.img / F.div) * F.sN + (long long)it.y * F.sH + (long long)x * F.sW;
+                    vx = v[0];
+                    vy = v[F.s2];
+                } else if (MODE == 0) {
                     const int k = (int)cls[p] - 1;  // predicted class of THIS pixel (class_compress is per pixel)
                     const float *q = F.quaternion + ((size_t)it.img * 4 * K + 4 * k) * hw + pix;
                     const float *s = F.scales + ((size_t)it.img * 3 * K + 3 * k) * hw + pix;
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, c
             for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
             acc[k] = v;
         }
-        if (lane < 8) {
+        if (MODE != 2 && lane < 8) {
             float v = acc[0];
 #pragma unroll
             for (int k = 1; k < 8; ++k) v = (lane == k) ? acc[k] : v;
@@ -449,10 +458,123 @@ __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, c
     }
 }
 
-template __global__ void k_gather<true>(const int *, const uint8_t *, InstTables, RowTables, const int *, PathParams,
-                                        FieldSrc, float4 *);
-template __global__ void k_gather<false>(const int *, const uint8_t *, InstTables, RowTables, const int *, PathParams,
-                                         FieldSrc, float4 *);
+
+// =============================================================================================
+// Dense "problems" (drop-in voting entry points): one plane per problem
+// =============================================================================================
+// problem j votes with the pixels of plane src_plane[j] where  fmask != 0  (ransac_voting_layer_v3:
+// mask[N,h,w], any float)  or  imask == match[j]  (ransac_voting_layer v1: class-id mask [b,h,w]).
+// Writes the same label volume / tables the connected-component path produces (label = j+1 inside the
+// problem's plane j), so every later kernel is shared.
+__global__ void __launch_bounds__(256) k_dense_problems(const float *__restrict__ fmask, const int *__restrict__ imask,
+                                                        int nplanes_per_src, int match_base, int *__restrict__ label,
+                                                        InstTables T, int w, int hw, int nprob) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long warps_per_plane = (hw + 127) / 128;
+    const int j = (int)(gw / warps_per_plane);
+    if (j >= nprob) return;
+    const int base = (int)(gw - (long long)j * warps_per_plane) * 128;
+    int cnt = 0, xmn = INT_MAX, xmx = -1, ymn = INT_MAX, ymx = -1;
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int pix = base + it * 32 + lane;
+        if (pix < hw) {
+            bool m;
+            if (fmask) {
+                m = fmask[(size_t)j * hw + pix] != 0.f;
+            } else {
+                const int src = j / nplanes_per_src, k = j - src * nplanes_per_src;
+                m = imask[(size_t)src * hw + pix] == match_base + k;
+            }
+            label[(size_t)j * hw + pix] = m ? j + 1 : 0;
+            if (m) {
+                const int y = pix / w, x = pix - y * w;
+                ++cnt;
+                xmn = min(xmn, x); xmx = max(xmx, x); ymn = min(ymn, y); ymx = max(ymx, y);
+            }
+        }
+    }
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (cnt) {
+        xmn = __reduce_min_sync(FULL, xmn); xmx = __reduce_max_sync(FULL, xmx);
+        ymn = __reduce_min_sync(FULL, ymn); ymx = __reduce_max_sync(FULL, ymx);
+        if (lane == 0) {
+            atomicAdd(&T.count[j], cnt);
+            atomicMin(&T.xmin[j], xmn); atomicMax(&T.xmax[j], xmx);
+            atomicMin(&T.ymin[j], ymn); atomicMax(&T.ymax[j], ymx);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dense_init(InstTables T, int *counters, int hw, int nprob) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) {
+        counters[FPC_CNT_INSTANCES] = nprob;
+        counters[FPC_CNT_FLAGS] = 0;
+        counters[FPC_CNT_TICKET] = 0;
+    }
+    if (j >= nprob) return;
+    T.root[j] = j * hw;   // plane index = root / hw
+    T.count[j] = 0;
+    T.xmin[j] = INT_MAX; T.xmax[j] = -1; T.ymin[j] = INT_MAX; T.ymax[j] = -1;
+    T.mincls[j] = 0;
+}
+
+// empty problems get a one-row, zero-width box so that the row tables stay well formed
+__global__ void __launch_bounds__(256) k_dense_fix_empty(InstTables T, int nprob) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nprob) return;
+    if (T.count[j] == 0) { T.xmin[j] = 0; T.xmax[j] = -1; T.ymin[j] = 0; T.ymax[j] = 0; }
+}
+
+int launch_dense_problems(const Workspace &ws, const PathParams &pp, const float *fmask, const int *imask,
+                          int nplanes_per_src, int match_base, int nprob, cudaStream_t st) {
+    k_dense_init<<<ceil_div(std::max(nprob, 1), 256), 256, 0, st>>>(ws.T, ws.counters, pp.hw, nprob);
+    FPC_LAUNCH_CHECK("k_dense_init");
+    if (nprob > 0) {
+        const long long warps = (long long)nprob * ((pp.hw + 127) / 128);
+        k_dense_problems<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, st>>>(fmask, imask, nplanes_per_src, match_base, ws.label,
+                                                                          ws.T, pp.w, pp.hw, nprob);
+        FPC_LAUNCH_CHECK("k_dense_problems");
+        k_dense_fix_empty<<<ceil_div(nprob, 256), 256, 0, st>>>(ws.T, nprob);
+        FPC_LAUNCH_CHECK("k_dense_fix_empty");
+    }
+    k_scan_rows_per_instance<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_instances, pp.max_rows);
+    FPC_LAUNCH_CHECK("k_scan_rows_per_instance");
+    return FPC_OK;
+}
+
+// Dense reference-layout outputs of AggregationLayer.forward (aggregation_layer.py:101-105,152-153):
+// instance_masks [N,h,w] f32 0/1 and the masked direction field xy [N,2,h,w].
+__global__ void __launch_bounds__(256) k_materialize(const int *__restrict__ label, const float *__restrict__ table,
+                                                     const float *__restrict__ xy_cat, float *__restrict__ masks,
+                                                     float *__restrict__ xy_mask, int hw, long long total) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / hw);
+        const int pix = (int)(t - (long long)i * hw);
+        const int img = __float_as_int(table[(size_t)i * FPC_POSE_ROW + FPC_ROW_SAMPLE]);
+        const bool m = label[(size_t)img * hw + pix] == i + 1;
+        if (masks) masks[t] = m ? 1.f : 0.f;
+        if (xy_mask) {
+            // the reference multiplies: mask * value (so a masked-out NaN stays NaN; we write 0 * v as well)
+            const float vx = xy_cat[((size_t)img * 2) * hw + pix], vy = xy_cat[((size_t)img * 2 + 1) * hw + pix];
+            const float mm = m ? 1.f : 0.f;
+            xy_mask[((size_t)i * 2) * hw + pix] = mm * vx;
+            xy_mask[((size_t)i * 2 + 1) * hw + pix] = mm * vy;
+        }
+    }
+}
+
+int launch_materialize(const int *label, const float *table, const float *xy_cat, float *masks, float *xy_mask, int n,
+                       int hw, cudaStream_t st) {
+    const long long total = (long long)n * hw;
+    if (total == 0) return FPC_OK;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)sm_count() * 32);
+    k_materialize<<<grid, 256, 0, st>>>(label, table, xy_cat, masks, xy_mask, hw, total);
+    FPC_LAUNCH_CHECK("k_materialize");
+    return FPC_OK;
+}
 
 // =============================================================================================
 // host-side launch sequence of the aggregation half
@@ -495,7 +617,7 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
     return FPC_OK;
 }
 
-int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, bool fused_heads,
+int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, int gather_mode,
                             bool want_records, int vote_chunk, cudaStream_t st) {
     const int grid = sm_count() * 8;
     k_row_count<<<grid, 256, 0, st>>>(ws.label, ws.T, ws.R, ws.counters, pp, ws.votes);
@@ -505,10 +627,12 @@ int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const Fie
     k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk);
     FPC_LAUNCH_CHECK("k_scan_records");
     float4 *rec = want_records ? ws.rec : nullptr;
-    if (fused_heads)
-        k_gather<true><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+    if (gather_mode == 0)
+        k_gather<0><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+    else if (gather_mode == 1)
+        k_gather<1><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
     else
-        k_gather<false><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+        k_gather<2><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
     FPC_LAUNCH_CHECK("k_gather");
     return FPC_OK;
 }

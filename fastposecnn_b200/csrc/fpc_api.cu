@@ -291,16 +291,14 @@ int fpc_bench_fp32_fma(float *sink, int blocks, int iters, void *stream) {
     return FPC_OK;
 }
 
-int fpc_pose_recover(const fpc_recover_args *a) {
+// Common argument checks + workspace carving + parameter block of the three pipeline entry points.
+static int setup(const fpc_recover_args *a, Workspace &ws, PathParams &pp) {
     int rc = check_sizes(a);
     if (rc != FPC_OK) return rc;
-    if (!a->mask_logits || !a->quaternion || !a->scales || !a->xy || !a->z || !a->inv_intrinsics)
-        return fail(FPC_EINVAL, "NULL input pointer");
     if (!a->pose_table || !a->counters || !a->workspace) return fail(FPC_EINVAL, "NULL output/workspace pointer");
     if (a->arith != FPC_ARITH_IEEE && a->arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", a->arith);
     if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return fail(FPC_EINVAL, "workspace must be 256-byte aligned");
     const long long P = (long long)a->b * a->h * a->w;
-    Workspace ws;
     ws.cls = a->cat_mask_u8;
     ws.label = a->labels;
     ws.votes = a->vote_counts_out;
@@ -311,19 +309,70 @@ int fpc_pose_recover(const fpc_recover_args *a) {
     if (need > a->workspace_bytes)
         return fail(FPC_ECAPACITY, "workspace too small: need %zu bytes, got %zu", need, a->workspace_bytes);
     ws.counters = a->counters;
-
-    PathParams pp;
     pp.b = a->b; pp.h = a->h; pp.w = a->w; pp.hw = a->h * a->w; pp.P = (int)P;
     pp.num_classes = a->num_classes; pp.hn = a->hn;
     pp.max_instances = a->max_instances; pp.max_records = a->max_records; pp.max_rows = a->max_rows;
     pp.inlier_thresh = a->inlier_thresh; pp.min_num = a->min_num; pp.max_num = a->max_num;
     pp.arith = a->arith; pp.seed = a->seed; pp.idxs = a->idxs; pp.select_u = a->select_u;
+    pp.refine = 1;
+    return FPC_OK;
+}
+
+int fpc_aggregate(const fpc_recover_args *a, const int64_t *cat_mask) {
+    Workspace ws;
+    PathParams pp;
+    int rc = setup(a, ws, pp);
+    if (rc != FPC_OK) return rc;
+    if (!cat_mask || !a->quaternion || !a->scales || !a->xy || !a->z) return fail(FPC_EINVAL, "NULL input pointer");
+    pp.min_num = INT_MAX;   // nobody votes: rows of the table carry class / sample / count / q / scales / z only
+    cudaStream_t st = (cudaStream_t)a->stream;
+    rc = launch_label_and_tables(ws, pp, nullptr, reinterpret_cast<const long long *>(cat_mask), st);
+    FieldSrc F{a->quaternion, a->scales, a->xy, a->z, 0, 0, 0, 0, 1};
+    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/1, /*want_records=*/false, VOTE_CHUNK, st);
+    if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, nullptr, a->pose_table, st);
+    return rc;
+}
+
+int fpc_vote_dense(const fpc_recover_args *a, const float *fmask, const int32_t *imask, int nplanes_per_src,
+                   int match_base, const float *vertex, long long sN, long long sH, long long sW, long long s2, int refine) {
+    Workspace ws;
+    PathParams pp;
+    int rc = setup(a, ws, pp);
+    if (rc != FPC_OK) return rc;
+    if ((!fmask && !imask) || !vertex) return fail(FPC_EINVAL, "NULL input pointer");
+    if (a->b > a->max_instances) return fail(FPC_ECAPACITY, "max_instances (%d) < number of problems (%d)", a->max_instances, a->b);
+    if (nplanes_per_src < 1) return fail(FPC_EINVAL, "nplanes_per_src must be >= 1");
+    pp.refine = refine;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    rc = launch_dense_problems(ws, pp, fmask, imask, nplanes_per_src, match_base, a->b, st);
+    FieldSrc F{nullptr, nullptr, vertex, nullptr, sN, sH, sW, s2, nplanes_per_src};
+    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/2, /*want_records=*/true, VOTE_CHUNK, st);
+    if (rc == FPC_OK) rc = launch_vote(ws, pp, ws.hyp, ws.votes, st);
+    if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, nullptr, a->pose_table, st);
+    return rc;
+}
+
+int fpc_materialize_instances(const int32_t *labels, const float *pose_table, const float *xy_cat, float *instance_masks,
+                              float *xy_mask, int n, int h, int w, void *stream) {
+    if (n < 0 || h <= 0 || w <= 0) return fail(FPC_EINVAL, "bad size");
+    if (n == 0) return FPC_OK;
+    if (!labels || !pose_table || (xy_mask && !xy_cat)) return fail(FPC_EINVAL, "NULL pointer");
+    return launch_materialize(labels, pose_table, xy_cat, instance_masks, xy_mask, n, h * w, (cudaStream_t)stream);
+}
+
+int fpc_pose_recover(const fpc_recover_args *a) {
+    Workspace ws;
+    PathParams pp;
+    int rc = setup(a, ws, pp);
+    if (rc != FPC_OK) return rc;
+    if (!a->mask_logits || !a->quaternion || !a->scales || !a->xy || !a->z || !a->inv_intrinsics)
+        return fail(FPC_EINVAL, "NULL input pointer");
 
     cudaStream_t st = (cudaStream_t)a->stream;
     stage_begin(a->stage_events, a->num_stage_events, st);
     rc = launch_label_and_tables(ws, pp, a->mask_logits, nullptr, st);
-    FieldSrc F{a->quaternion, a->scales, a->xy, a->z};
-    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*fused_heads=*/true, /*want_records=*/true, VOTE_CHUNK, st);
+    FieldSrc F{a->quaternion, a->scales, a->xy, a->z, 0, 0, 0, 0, 1};
+    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/0, /*want_records=*/true, VOTE_CHUNK, st);
     if (rc == FPC_OK) rc = launch_vote(ws, pp, ws.hyp, ws.votes, st);
     if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, a->inv_intrinsics, a->pose_table, st);
     stage_end();

@@ -26,6 +26,9 @@ struct RowTables {
 // Where the per-pixel regression fields come from.
 struct FieldSrc {
     const float *quaternion, *scales, *xy, *z;
+    // gather mode 2: `xy` is a strided vertex view; element strides of (problem, row, column, component)
+    long long sN, sH, sW, s2;
+    int div;   // problems per source plane (v1: classes per image); vertex plane = problem / div
 };
 
 struct PathParams {
@@ -39,6 +42,7 @@ struct PathParams {
     unsigned long long seed;
     const int *idxs;             // [max_instances,hn,2] or nullptr
     const float *select_u;       // [b,h,w] or nullptr
+    int refine;                  // 1: inlier refinement (v3); 0: winning hypothesis as is (v1)
 };
 
 struct Workspace {
@@ -59,8 +63,12 @@ constexpr int VOTE_CHUNK = 1024;  // pixels per vote work item
 // fpc_aggregate.cu
 int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,
                             const long long *cat_mask_i64, cudaStream_t st);
-int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, bool fused_heads,
+int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, int gather_mode,
                             bool want_records, int vote_chunk, cudaStream_t st);
+int launch_dense_problems(const Workspace &ws, const PathParams &pp, const float *fmask, const int *imask,
+                          int nplanes_per_src, int match_base, int nprob, cudaStream_t st);
+int launch_materialize(const int *label, const float *table, const float *xy_cat, float *masks, float *xy_mask, int n,
+                       int hw, cudaStream_t st);
 
 // fpc_voting.cu
 int launch_generate_hypothesis(const float *direct, const float *coords, const int *idxs, float *hypo, int tn, int vn,

@@ -450,8 +450,11 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
             double t[13];
             for (int k = 0; k < 13; ++k) t[k] = s_d[0][k] + s_d[1][k] + s_d[2][k] + s_d[3][k];
             const int inl = s_i[0][2] + s_i[1][2] + s_i[2][2] + s_i[3][2];
-            double rx = 0.0, ry = 0.0;
-            if (tn > 0) solve_sym2_pinv(t[0], t[1], t[2], t[3], t[4], rx, ry);
+            double rx = wx, ry = wy;   // v1 (ransac_voting_gpu.py:11-98) returns the winning hypothesis itself
+            if (pp.refine) {
+                rx = 0.0; ry = 0.0;
+                if (tn > 0) solve_sym2_pinv(t[0], t[1], t[2], t[3], t[4], rx, ry);
+            }
             const float x = (float)rx, y = (float)ry;
             // means (aggregation_layer.py:138-149)
             const double inv_cnt = 1.0 / (double)cnt;
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
             row[FPC_ROW_XY] = x;
             row[FPC_ROW_XY + 1] = y;
             row[FPC_ROW_Z] = z;
-            pose_from_qxyz(q, x, y, z, inv_k, row + FPC_ROW_R, row + FPC_ROW_T, row + FPC_ROW_RT);
+            if (inv_k) pose_from_qxyz(q, x, y, z, inv_k, row + FPC_ROW_R, row + FPC_ROW_T, row + FPC_ROW_RT);
             row[FPC_ROW_HYP] = wx;
             row[FPC_ROW_HYP + 1] = wy;
             row[FPC_ROW_WIN_IDX] = __int_as_float(tn > 0 ? win_idx : -1);

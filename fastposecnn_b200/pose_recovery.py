@@ -189,7 +189,9 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
     agg["cat_mask"] = eng.cat_mask_u8
     agg["labels"] = eng.labels
     if materialize_dense:
+        # optional reference-layout dense outputs (one extra class-compression pass for the xy field)
         from .aggregation_layer import materialize_instance_masks, materialize_xy_mask
-        agg["instance_masks"] = materialize_instance_masks(eng.labels, agg["sample_ids"], n)
-        agg["xy_mask"] = materialize_xy_mask(eng.labels, eng.cat_mask_u8, logits["xy"], agg["sample_ids"], n)
+        from .gpu_tensor_funcs import class_compression
+        agg["instance_masks"] = materialize_instance_masks(eng.labels, eng.pose_table, n)
+        agg["xy_mask"] = materialize_xy_mask(eng.labels, eng.pose_table, class_compression(logits, C)["xy"], n)
     return agg

@@ -180,6 +180,32 @@ FPC_API size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *args);
  * counters[FPC_CNT_INSTANCES] rows of pose_table) after synchronising the stream. */
 FPC_API int fpc_pose_recover(const fpc_recover_args *args);
 
+/* AggregationLayer.forward (lib/aggregation_layer.py:61-158) on already class-compressed
+ * CategoricalData: cat_mask [b,h,w] i64, and in `args` quaternion [b,4,h,w], scales [b,3,h,w],
+ * xy [b,2,h,w], z [b,h,w] (mask_logits / inv_intrinsics / idxs are ignored).  Fills class, sample,
+ * count, quaternion, scales and z of every pose-table row and the label volume (args->labels or the
+ * workspace); nothing votes.  Same workspace size as fpc_pose_recover. */
+FPC_API int fpc_aggregate(const fpc_recover_args *args, const int64_t *cat_mask);
+
+/* ransac_voting_layer_v3 / ransac_voting_layer (lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:518-607,
+ * :11-98) on dense masks.  args->b is the number of voting problems (v3: instances; v1: images x
+ * (class_num-1)), args->h/w the plane size.  Problem j votes with the pixels of
+ *   fmask[j] != 0                                   (v3: mask [N,h,w] f32), or
+ *   imask[j / nplanes_per_src] == match_base + j % nplanes_per_src   (v1: class-id mask [b,h,w] i32),
+ * with directions vertex[(j / nplanes_per_src)*sN + y*sH + x*sW + {0, s2}] (element strides, so a
+ * non-contiguous [.,h,w,vn,2] view of one keypoint works).  refine=1: inlier refinement (v3);
+ * refine=0: the winning hypothesis (v1).  Results: FPC_ROW_XY / HYP / WIN_* / TN of each table row.
+ * args->select_u, if given, is [nproblems,h,w].  Same workspace size as fpc_pose_recover. */
+FPC_API int fpc_vote_dense(const fpc_recover_args *args, const float *fmask, const int32_t *imask, int nplanes_per_src,
+                           int match_base, const float *vertex, long long sN, long long sH, long long sW, long long s2,
+                           int refine);
+
+/* Dense reference-layout outputs of AggregationLayer.forward (lib/aggregation_layer.py:101-105,152-153):
+ * instance_masks [n,h,w] f32 0/1 and xy_mask [n,2,h,w] = mask * xy_cat[sample]; either may be NULL.
+ * labels [b,h,w] = instance id + 1; pose_table rows supply each instance's frame. */
+FPC_API int fpc_materialize_instances(const int32_t *labels, const float *pose_table, const float *xy_cat,
+                                      float *instance_masks, float *xy_mask, int n, int h, int w, void *stream);
+
 /* Number of kernels fpc_pose_recover launches per call (for launch accounting). */
 FPC_API int fpc_pose_recover_num_launches(void);
 
