@@ -114,5 +114,20 @@ def require_cuda(t: torch.Tensor, name: str, dtype=None, contiguous: bool = True
     return t
 
 
+def require_device_readable(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    """CUDA tensor, or a PINNED host tensor: under unified virtual addressing a page-locked host allocation is
+    addressable from the device with the same pointer, so the kernels can read it in place over PCIe (zero-copy
+    ingestion of host-resident head maps: only the bytes the path needs ever cross the bus)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda and not t.is_pinned():
+        raise RuntimeError(f"{name} must be a CUDA tensor or a pinned host tensor (fastposecnn_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t
+
+
 def current_stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream

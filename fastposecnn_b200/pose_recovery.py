@@ -65,11 +65,11 @@ class PoseRecoveryEngine:
         """Enqueues the 13 kernels on the current stream.  No synchronisation."""
         b, h, w, C, K = self.b, self.h, self.w, self.num_classes, self.num_classes - 1
         f32 = torch.float32
-        mask = _lib.require_cuda(logits["mask"], "logits['mask']", f32)
-        quat = _lib.require_cuda(logits["quaternion"], "logits['quaternion']", f32)
-        scales = _lib.require_cuda(logits["scales"], "logits['scales']", f32)
-        xy = _lib.require_cuda(logits["xy"], "logits['xy']", f32)
-        z = _lib.require_cuda(logits["z"], "logits['z']", f32)
+        mask = _lib.require_device_readable(logits["mask"], "logits['mask']", f32)
+        quat = _lib.require_device_readable(logits["quaternion"], "logits['quaternion']", f32)
+        scales = _lib.require_device_readable(logits["scales"], "logits['scales']", f32)
+        xy = _lib.require_device_readable(logits["xy"], "logits['xy']", f32)
+        z = _lib.require_device_readable(logits["z"], "logits['z']", f32)
         # torch.inverse returns a column-major tensor; a 3x3 copy is free
         inv_k = _lib.require_cuda(inv_intrinsics, "inv_intrinsics", f32, contiguous=False).contiguous()
         self._invk_keepalive = inv_k
@@ -182,7 +182,9 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
     reference's dense ``instance_masks [N,h,w]`` and ``xy_mask [N,2,h,w]``."""
     mask = logits["mask"]
     b, C, h, w = mask.shape
-    eng = get_engine(b, h, w, C, hn, mask.device, **engine_kw)
+    # head maps may also be PINNED HOST tensors (read in place over PCIe); the device then comes from inv_intrinsics
+    device = mask.device if mask.is_cuda else inv_intrinsics.device
+    eng = get_engine(b, h, w, C, hn, device, **engine_kw)
     eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
     n = eng.fetch_count()
     agg = eng.table_to_agg(n)

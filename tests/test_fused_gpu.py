@@ -83,3 +83,19 @@ def test_cfg1_full_size():
     # known answer: every refined centre is the disc centre
     cent = torch.tensor([[d[0], d[1]] for d in wl.discs()])
     assert (out["xy"].cpu() - cent).abs().max() < 0.1
+
+
+def test_zero_copy_pinned_host_inputs_match_device_inputs():
+    """Head maps left in pinned host memory are read in place by the kernels; results are bit-identical."""
+    from fastposecnn_b200.pose_recovery import pose_recover
+    frames, h, w = helpers.scenes()["wide"]
+    logits = syn.render_heads(frames, h, w, seed=3)
+    dev = torch.device("cuda:0")
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(dev)
+    a = pose_recover({k: v.to(dev) for k, v in logits.items()}, inv_k, HN)
+    ta = {k: v.clone() for k, v in a.items() if k in ("xy", "quaternion", "RT", "class_ids", "win_counts")}
+    b = pose_recover({k: v.pin_memory() for k, v in logits.items()}, inv_k, HN)
+    for k, v in ta.items():
+        assert torch.equal(v, b[k]), k
+    with pytest.raises(RuntimeError, match="pinned"):
+        pose_recover(logits, inv_k, HN)          # pageable host memory is refused
