@@ -145,7 +145,7 @@ def run_b200(args):
     import torch.distributed as dist
     from fastposecnn_b200 import _lib
     from fastposecnn_b200 import synthetic as syn
-    from fastposecnn_b200.pose_recovery import PoseRecoveryEngine
+    from fastposecnn_b200.pose_recovery import PoseRecoveryEngine, PoseRecoveryPipeline
     from fastposecnn_b200.sharding import gather_pose_tables
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,11 +168,15 @@ def run_b200(args):
     discs = wl.discs()
     tn_disc = [syn.disc_pixel_count(cx, cy, r, wl.h, wl.w) for (cx, cy, r, _c) in discs]
     n_expected = bpg * len(discs)
-    eng = PoseRecoveryEngine(bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected))
+    depth = max(1, args.pipeline_depth)
+    pipe = PoseRecoveryPipeline(depth, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected))
+    eng = pipe.engines[0]
     idxs = torch.zeros((eng.max_instances, hn, 2), dtype=torch.int32)
     idxs[:n_expected] = syn.presampled_idxs(tn_disc * bpg, hn, seed=1234).reshape(n_expected, hn, 2)
     idxs = idxs.to(dev)
-    gathered = torch.empty((world, eng.max_instances + 1, _lib.POSE_ROW), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = [torch.empty((world, eng.max_instances + 1, _lib.POSE_ROW), dtype=torch.float32, device=dev)
+                for _ in range(depth)] if world > 1 else None
+    gather_slot = {id(e): i for i, e in enumerate(pipe.engines)}
 
     nk = eng.num_launches
     kernel_names = [_lib.lib().fpc_pose_recover_kernel_name(k).decode() for k in range(nk)]
@@ -183,17 +187,24 @@ def run_b200(args):
             e.record()           # instantiates the cudaEvent_t
         return evs
 
-    def step(stage_events=None):
-        eng.launch(logits, inv_k, idxs=idxs, stage_events=stage_events)
+    def after_launch(e):
         if world > 1:
-            gather_pose_tables(eng, gathered)
-        return eng.fetch_count()
+            gather_pose_tables(e, gathered[gather_slot[id(e)]])
+
+    def check(res):
+        if res is not None and res[1] != n_expected:
+            raise RuntimeError(f"synthetic workload produced {res[1]} instances, expected {n_expected}")
+
+    def step(stage_events=None):
+        # one pass of the path over one batch; the host waits for the count of the batch `depth-1` steps back
+        check(pipe.submit(logits, inv_k, idxs=idxs, stage_events=stage_events, after_launch=after_launch))
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
-        n = step()
-    if n != n_expected:
-        raise RuntimeError(f"synthetic workload produced {n} instances, expected {n_expected}")
+        step()
+    for res in pipe.drain():
+        check(res)
+    n = n_expected
     step_events = [make_events(nk + 1) for _ in range(args.steps)]
     torch.cuda.synchronize()
 
@@ -224,6 +235,8 @@ def run_b200(args):
     t_start.record()
     for k in range(args.steps):
         step(step_events[k])
+    for res in pipe.drain():
+        check(res)
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -292,7 +305,7 @@ def run_b200(args):
                     dev_in[k].copy_(host[k], non_blocking=True)
             eng.launch(dev_in, inv_k, idxs=idxs)
             if world > 1:
-                gather_pose_tables(eng, gathered)
+                gather_pose_tables(eng, gathered[0])
             n_ = eng.fetch_count()
             table_host[:n_].copy_(eng.pose_table[:n_], non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -338,7 +351,7 @@ def run_b200(args):
             "config": {"workload": wl.name, "frames_per_gpu": bpg, "global_batch": world * bpg, "hypotheses": hn,
                        "instances_per_frame": len(discs), "parallelism": f"image-sharded x{world}",
                        "l2": "inputs (2.6 GB of head maps per GPU) are larger than the 126 MB L2; no flush needed",
-                       "arith": "IEEE (un-contracted) voting arithmetic", "timed": "13 kernels + D2H read of N"
+                       "arith": "IEEE (un-contracted) voting arithmetic", "timed": f"{nk} kernels + D2H read of N per step, {depth} steps in flight"
                                 + (" + NCCL all-gather of pose tables" if world > 1 else "")},
             "roofline": roof_argmax if kernel_names[dominant] != "k_gather" else roof_gather,
             "roofline_fp32_voting": roof_vote,
@@ -367,6 +380,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="frames per GPU (default: the workload's batch, 32 for cfg2)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference pass (bounded sample)")
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="batches in flight (1 = wait for N after every step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-mode", default="zerocopy", choices=["zerocopy", "copy"])
     ap.add_argument("--no-cpu", action="store_true")

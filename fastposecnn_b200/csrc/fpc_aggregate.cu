@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(256) k_argmax_init_v4(const float *__restrict_
                 cur = -1;
             }
         }
-        *reinterpret_cast<int4 *>(label + p) = make_int4(lab[0], lab[1], lab[2], lab[3]);
+        // labels are only read where cls != 0: all-background threads (most of the image) skip the 16-byte store
+        if (nib) *reinterpret_cast<int4 *>(label + p) = make_int4(lab[0], lab[1], lab[2], lab[3]);
         *reinterpret_cast<uchar4 *>(cls + p) = make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3);
     }
 }
@@ -258,6 +259,208 @@ __global__ void __launch_bounds__(256) k_instance_stats(int *label, const int *_
     }
 }
 
+// =============================================================================================
+// Vectorised variants (4 consecutive pixels per thread; need w % 4 == 0 and 16-byte aligned buffers).
+// They read the 1-byte class map first and leave at once when all 4 pixels are background, so the
+// background (78 % of cfg2) costs 1 B/px per pass.  `label` is only defined on foreground pixels
+// until k_instance_stats_v4 rewrites the whole volume.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_ccl_merge_v4(const uint8_t *__restrict__ cls, int *label, int w, int hw, int P4,
+                                                      int span) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P4) return;
+    const int p = t * 4;
+    const uchar4 c = *reinterpret_cast<const uchar4 *>(cls + p);
+    if (!(c.x | c.y | c.z | c.w)) return;
+    const int pix = p % hw;
+    const int y = pix / w, x0 = pix - y * w;
+    const bool fg[4] = {c.x != 0, c.y != 0, c.z != 0, c.w != 0};
+    const bool left0 = x0 > 0 && cls[p - 1];
+    bool up[4] = {false, false, false, false};
+    bool upleft0 = false;
+    if (y > 0) {
+        const uchar4 u = *reinterpret_cast<const uchar4 *>(cls + p - w);
+        up[0] = u.x != 0; up[1] = u.y != 0; up[2] = u.z != 0; up[3] = u.w != 0;
+        upleft0 = x0 > 0 && cls[p - w - 1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (!fg[j]) continue;
+        const bool left = j ? fg[j - 1] : left0;
+        // horizontal adjacency not yet linked by the label initialisation (span = 128: only at span starts;
+        // span = 1: every pixel)
+        if (left && ((p + j) % span) == 0) uf_unite(label, p + j, p + j - 1);
+        if (!up[j]) continue;
+        const bool upleft = j ? up[j - 1] : upleft0;
+        if (!(left && upleft)) uf_unite(label, p + j, p + j - w);
+    }
+}
+
+// tile = 1024 consecutive pixels = 256 threads x 4
+__global__ void __launch_bounds__(256) k_ccl_flatten_v4(const uint8_t *__restrict__ cls, int *label,
+                                                        int *__restrict__ tile_roots, int P4) {
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    int n = 0;
+    if (t < P4) {
+        const int p = t * 4;
+        const uchar4 c = *reinterpret_cast<const uchar4 *>(cls + p);
+        if (c.x | c.y | c.z | c.w) {
+            const int4 l = *reinterpret_cast<const int4 *>(label + p);
+            const int lv[4] = {l.x, l.y, l.z, l.w};
+            const bool fg[4] = {c.x != 0, c.y != 0, c.z != 0, c.w != 0};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!fg[j]) continue;
+                const int r = uf_find(label, lv[j]);
+                if (r != lv[j]) label[p + j] = r;
+                n += (r == p + j);
+            }
+        }
+    }
+    n = __reduce_add_sync(FULL, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_roots[blockIdx.x] = s_n;
+}
+
+__global__ void __launch_bounds__(256) k_assign_ids_v4(const uint8_t *__restrict__ cls, const int *__restrict__ label,
+                                                       const int *__restrict__ tile_base, int *__restrict__ idmap,
+                                                       InstTables T, int P4, int max_instances) {
+    __shared__ int s_w[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int p = t * 4;
+    int rootbits = 0;
+    if (t < P4) {
+        const uchar4 c = *reinterpret_cast<const uchar4 *>(cls + p);
+        if (c.x | c.y | c.z | c.w) {
+            const int4 l = *reinterpret_cast<const int4 *>(label + p);
+            rootbits = ((c.x && l.x == p) ? 1 : 0) | ((c.y && l.y == p + 1) ? 2 : 0) | ((c.z && l.z == p + 2) ? 4 : 0) |
+                       ((c.w && l.w == p + 3) ? 8 : 0);
+        }
+    }
+    const int mine = __popc(rootbits);
+    const int inc = warp_incl_scan(mine, lane);
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (!rootbits) return;
+    int woff = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) woff += (k < wid) ? s_w[k] : 0;
+    int id = tile_base[blockIdx.x] + woff + inc - mine;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (!((rootbits >> j) & 1)) continue;
+        idmap[p + j] = id;
+        if (id < max_instances) {
+            T.root[id] = p + j;
+            T.count[id] = 0;
+            T.ymin[id] = INT_MAX; T.ymax[id] = -1; T.xmin[id] = INT_MAX; T.xmax[id] = -1;
+            T.mincls[id] = INT_MAX;
+        }
+        ++id;
+    }
+}
+
+// Per-block shared-memory accumulators: a 1024-pixel tile touches one to three instances, so the
+// count/bbox/min-class atomics of a whole tile collapse into six global atomics per (tile, instance)
+// instead of six per (warp, instance) -- the global atomics all land on a handful of cache lines and
+// serialise in L2 otherwise.
+struct StatSlots {
+    int id[8], cnt[8], xmn[8], xmx[8], ymn[8], ymx[8], cmn[8];
+};
+__device__ __forceinline__ void stat_update(StatSlots &S, InstTables &T, int cur, int cnt, int xmn, int xmx, int ymn,
+                                            int ymx, int cmn, int max_instances) {
+    if (cur >= max_instances) return;
+#pragma unroll 1
+    for (int s = 0; s < 8; ++s) {
+        int o = S.id[s];
+        if (o == -1) o = atomicCAS(&S.id[s], -1, cur);
+        if (o == -1 || o == cur) {
+            atomicAdd(&S.cnt[s], cnt);
+            atomicMin(&S.xmn[s], xmn); atomicMax(&S.xmx[s], xmx);
+            atomicMin(&S.ymn[s], ymn); atomicMax(&S.ymx[s], ymx);
+            atomicMin(&S.cmn[s], cmn);
+            return;
+        }
+    }
+    atomicAdd(&T.count[cur], cnt);          // more than 8 instances in one tile: straight to global
+    atomicMin(&T.xmin[cur], xmn); atomicMax(&T.xmax[cur], xmx);
+    atomicMin(&T.ymin[cur], ymn); atomicMax(&T.ymax[cur], ymx);
+    atomicMin(&T.mincls[cur], cmn);
+}
+
+__global__ void __launch_bounds__(256) k_instance_stats_v4(int *label, const int *__restrict__ idmap,
+                                                           const uint8_t *__restrict__ cls, InstTables T, int w, int hw,
+                                                           int P4, int max_instances) {
+    __shared__ StatSlots S;
+    __shared__ int s_any;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 8) {
+        S.id[threadIdx.x] = -1; S.cnt[threadIdx.x] = 0;
+        S.xmn[threadIdx.x] = INT_MAX; S.xmx[threadIdx.x] = -1; S.ymn[threadIdx.x] = INT_MAX; S.ymx[threadIdx.x] = -1;
+        S.cmn[threadIdx.x] = INT_MAX;
+    }
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = t * 4;
+    int id[4] = {-1, -1, -1, -1};
+    int cc[4] = {0, 0, 0, 0};
+    int x0 = 0, y = 0;
+    if (t < P4) {
+        const uchar4 c = *reinterpret_cast<const uchar4 *>(cls + p);
+        if (c.x | c.y | c.z | c.w) {
+            const int4 l = *reinterpret_cast<const int4 *>(label + p);
+            cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = c.w;
+            if (c.x) id[0] = idmap[l.x];
+            if (c.y) id[1] = idmap[l.y];
+            if (c.z) id[2] = idmap[l.z];
+            if (c.w) id[3] = idmap[l.w];
+            const int pix = p % hw;
+            y = pix / w;
+            x0 = pix - y * w;
+        }
+        *reinterpret_cast<int4 *>(label + p) = make_int4(id[0] + 1, id[1] + 1, id[2] + 1, id[3] + 1);
+    }
+    const bool any = (id[0] & id[1] & id[2] & id[3]) != -1;   // some pixel is foreground (ids are >= 0 or -1)
+    if (__any_sync(FULL, any)) {
+        if (lane == 0) s_any = 1;
+        // threads whose four pixels share one id: aggregate across the warp, one update per distinct id
+        const bool uniform = id[0] >= 0 && id[0] == id[1] && id[1] == id[2] && id[2] == id[3];
+        unsigned rem = __ballot_sync(FULL, uniform);
+        while (rem) {
+            const int cur = __shfl_sync(FULL, id[0], __ffs(rem) - 1);
+            const bool mine = uniform && id[0] == cur;
+            const unsigned gm = __ballot_sync(FULL, mine);
+            rem &= ~gm;
+            const int xmn = __reduce_min_sync(FULL, mine ? x0 : INT_MAX);
+            const int xmx = __reduce_max_sync(FULL, mine ? x0 + 3 : -1);
+            const int ymn = __reduce_min_sync(FULL, mine ? y : INT_MAX);
+            const int ymx = __reduce_max_sync(FULL, mine ? y : -1);
+            const int cmn = __reduce_min_sync(FULL, mine ? min(min(cc[0], cc[1]), min(cc[2], cc[3])) : INT_MAX);
+            if (lane == 0) stat_update(S, T, cur, 4 * __popc(gm), xmn, xmx, ymn, ymx, cmn, max_instances);
+        }
+        // threads straddling an instance border: per pixel
+        if (any && !uniform) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (id[j] >= 0) stat_update(S, T, id[j], 1, x0 + j, x0 + j, y, y, cc[j], max_instances);
+        }
+    }
+    __syncthreads();
+    if (s_any && threadIdx.x < 8 && S.id[threadIdx.x] >= 0) {
+        const int s = threadIdx.x, cur = S.id[s];
+        atomicAdd(&T.count[cur], S.cnt[s]);
+        atomicMin(&T.xmin[cur], S.xmn[s]); atomicMax(&T.xmax[cur], S.xmx[s]);
+        atomicMin(&T.ymin[cur], S.ymn[s]); atomicMax(&T.ymax[cur], S.ymx[s]);
+        atomicMin(&T.mincls[cur], S.cmn[s]);
+    }
+}
+
 // G. rows of every instance's bounding box -> rowoff (exclusive scan over instances, single block)
 __global__ void __launch_bounds__(1024) k_scan_rows_per_instance(InstTables T, int *counters, int max_instances,
                                                                   long long max_rows) {
@@ -276,9 +479,9 @@ struct RowItem {
     int i, y, img, x0, x1, cnt;
     bool valid;
 };
-__device__ __forceinline__ RowItem decode_row(const InstTables &T, int N, int r, int hw) {
+__device__ __forceinline__ RowItem decode_row(const InstTables &T, const RowTables &R, int r, int hw) {
     RowItem it;
-    it.i = upper_index(T.rowoff, N, r);
+    it.i = R.inst[r];
     it.y = T.ymin[it.i] + (r - T.rowoff[it.i]);
     it.img = T.root[it.i] / hw;
     it.x0 = T.xmin[it.i];
@@ -293,54 +496,70 @@ __device__ __forceinline__ float select_uniform(const PathParams &pp, int p) {
     return (float)(hash3(pp.seed, (uint32_t)p, 0x5e1ec7u, 0u) >> 8) * (1.0f / 16777216.0f);
 }
 
-// H. pixels that will vote, per (instance,row).  Also zeroes the vote counters of the live instances.
+// H. one block per instance: voting pixels of every row of its bounding box, their exclusive prefix inside
+//    the instance (-> position of the row's first voting record), the row -> instance map, tn, and the
+//    zeroing of the instance's vote counters.
 //    ransac_voting_gpu.py:536-545: fewer than min_num pixels -> the instance does not vote;
 //    more than max_num -> Bernoulli(max_num / count) sub-sampling.
-__global__ void __launch_bounds__(256) k_row_count(const int *__restrict__ label, InstTables T, RowTables R,
-                                                   const int *__restrict__ counters, PathParams pp, int *votes) {
+constexpr int ROWS_PER_PASS = 1024;
+__global__ void __launch_bounds__(128) k_rows(const int *__restrict__ label, InstTables T, RowTables R,
+                                              const int *__restrict__ counters, PathParams pp, int *__restrict__ votes) {
+    __shared__ int s_cnt[ROWS_PER_PASS];
+    __shared__ int s_w[4];
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
-    const int rows = counters[FPC_CNT_ROWS];
-    const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const long long nvotes = (long long)N * pp.hn;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nvotes; k += (long long)gridDim.x * blockDim.x)
-        votes[k] = 0;
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
-        const RowItem it = decode_row(T, N, r, pp.hw);
-        int n = 0;
-        if (it.cnt >= pp.min_num) {
-            const bool sub = it.cnt > pp.max_num;
-            const float thr = (float)pp.max_num / (float)it.cnt;
-            const int rowbase = it.img * pp.hw + it.y * pp.w;
-            for (int xb = it.x0; xb <= it.x1; xb += 32) {
-                const int x = xb + lane;
-                bool m = (x <= it.x1) && (label[rowbase + x] == it.i + 1);
-                if (m && sub) m = select_uniform(pp, rowbase + x) < thr;
-                n += __popc(__ballot_sync(FULL, m));
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    for (int i = blockIdx.x; i < N; i += gridDim.x) {
+        const int r0 = T.rowoff[i], nrows = T.rowoff[i + 1] - r0;
+        const int cnt = T.count[i], ymin = T.ymin[i], x0 = T.xmin[i], x1 = T.xmax[i];
+        const int img = T.root[i] / pp.hw;
+        const bool votes_at_all = cnt >= pp.min_num;
+        const bool sub = cnt > pp.max_num;
+        const float thr = (float)pp.max_num / (float)cnt;
+        for (int k = tid; k < pp.hn; k += 128) votes[(size_t)i * pp.hn + k] = 0;
+        int carry = 0;
+        for (int rb = 0; rb < nrows; rb += ROWS_PER_PASS) {
+            const int nr = min(ROWS_PER_PASS, nrows - rb);
+            for (int rr = wv; rr < nr; rr += 4) {
+                int n = 0;
+                if (votes_at_all) {
+                    const int rowbase = img * pp.hw + (ymin + rb + rr) * pp.w;
+                    for (int xb = x0; xb <= x1; xb += 32) {
+                        const int x = xb + lane;
+                        bool m = (x <= x1) && (label[rowbase + x] == i + 1);
+                        if (m && sub) m = select_uniform(pp, rowbase + x) < thr;
+                        n += __popc(__ballot_sync(FULL, m));
+                    }
+                }
+                if (lane == 0) s_cnt[rr] = n;
             }
+            __syncthreads();
+            // exclusive scan of s_cnt[0..nr): 8 consecutive rows per thread
+            int v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int rr = tid * 8 + k;
+                v[k] = rr < nr ? s_cnt[rr] : 0;
+                sum += v[k];
+            }
+            const int inc = warp_incl_scan(sum, lane);
+            if (lane == 31) s_w[wv] = inc;
+            __syncthreads();
+            int run = carry + inc - sum;
+            for (int k = 0; k < wv; ++k) run += s_w[k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int rr = tid * 8 + k;
+                if (rr < nr) {
+                    R.base[r0 + rb + rr] = run;
+                    R.inst[r0 + rb + rr] = i;
+                }
+                run += v[k];
+            }
+            carry += s_w[0] + s_w[1] + s_w[2] + s_w[3];
+            __syncthreads();
         }
-        if (lane == 0) R.base[r] = n;
-    }
-}
-
-// I1. exclusive prefix of the row counts inside each instance (one warp per instance) -> tn
-__global__ void __launch_bounds__(256) k_row_prefix(InstTables T, RowTables R, const int *__restrict__ counters) {
-    if (counters[FPC_CNT_FLAGS]) return;
-    const int N = counters[FPC_CNT_INSTANCES];
-    const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += nwarps) {
-        const int r0 = T.rowoff[i], r1 = T.rowoff[i + 1];
-        int running = 0;
-        for (int rb = r0; rb < r1; rb += 32) {
-            const int r = rb + lane;
-            const int v = (r < r1) ? R.base[r] : 0;
-            const int inc = warp_incl_scan(v, lane);
-            if (r < r1) R.base[r] = running + inc - v;
-            running += __shfl_sync(FULL, inc, 31);
-        }
-        if (lane == 0) T.tn[i] = running;
+        if (tid == 0) T.tn[i] = carry;
     }
 }
 
@@ -385,7 +604,7 @@ __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, c
     const int K = pp.num_classes - 1;
     const size_t hw = (size_t)pp.hw;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
-        const RowItem it = decode_row(T, N, r, pp.hw);
+        const RowItem it = decode_row(T, R, r, pp.hw);
         const int tn = T.tn[it.i];
         const bool sub = it.cnt > pp.max_num;
         const float thr = (float)pp.max_num / (float)it.cnt;
@@ -601,17 +820,35 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
         k_init_from_catmask<<<ceil_div(P, 256), 256, 0, st>>>(cat_mask_i64, ws.cls, ws.label, P);
         FPC_LAUNCH_CHECK("k_init_from_catmask");
     }
-    k_ccl_merge<<<ceil_div(P, 256), 256, 0, st>>>(ws.cls, ws.label, pp.w, pp.hw, P, span);
-    FPC_LAUNCH_CHECK("k_ccl_merge");
-    k_ccl_flatten<<<ntiles, 256, 0, st>>>(ws.label, ws.tile_roots, P);
-    FPC_LAUNCH_CHECK("k_ccl_flatten");
+    const bool v4 = (pp.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(ws.label) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(ws.cls) & 3) == 0);
+    const int P4 = P / 4;
+    if (v4) {
+        k_ccl_merge_v4<<<ceil_div(P4, 256), 256, 0, st>>>(ws.cls, ws.label, pp.w, pp.hw, P4, span);
+        FPC_LAUNCH_CHECK("k_ccl_merge");
+        k_ccl_flatten_v4<<<ntiles, 256, 0, st>>>(ws.cls, ws.label, ws.tile_roots, P4);
+        FPC_LAUNCH_CHECK("k_ccl_flatten");
+    } else {
+        k_ccl_merge<<<ceil_div(P, 256), 256, 0, st>>>(ws.cls, ws.label, pp.w, pp.hw, P, span);
+        FPC_LAUNCH_CHECK("k_ccl_merge");
+        k_ccl_flatten<<<ntiles, 256, 0, st>>>(ws.label, ws.tile_roots, P);
+        FPC_LAUNCH_CHECK("k_ccl_flatten");
+    }
     k_scan_tiles<<<1, 1024, 0, st>>>(ws.tile_roots, ntiles, ws.counters, pp.max_instances);
     FPC_LAUNCH_CHECK("k_scan_tiles");
-    k_assign_ids<<<ntiles, 256, 0, st>>>(ws.label, ws.tile_roots, ws.idmap, ws.T, P, pp.max_instances);
-    FPC_LAUNCH_CHECK("k_assign_ids");
-    k_instance_stats<<<ceil_div(P, 128 * 8), 256, 0, st>>>(ws.label, ws.idmap, ws.cls, ws.T, pp.w, pp.hw, P,
-                                                           pp.max_instances);
-    FPC_LAUNCH_CHECK("k_instance_stats");
+    if (v4) {
+        k_assign_ids_v4<<<ntiles, 256, 0, st>>>(ws.cls, ws.label, ws.tile_roots, ws.idmap, ws.T, P4, pp.max_instances);
+        FPC_LAUNCH_CHECK("k_assign_ids");
+        k_instance_stats_v4<<<ceil_div(P4, 256), 256, 0, st>>>(ws.label, ws.idmap, ws.cls, ws.T, pp.w, pp.hw, P4,
+                                                               pp.max_instances);
+        FPC_LAUNCH_CHECK("k_instance_stats");
+    } else {
+        k_assign_ids<<<ntiles, 256, 0, st>>>(ws.label, ws.tile_roots, ws.idmap, ws.T, P, pp.max_instances);
+        FPC_LAUNCH_CHECK("k_assign_ids");
+        k_instance_stats<<<ceil_div(P, 128 * 8), 256, 0, st>>>(ws.label, ws.idmap, ws.cls, ws.T, pp.w, pp.hw, P,
+                                                               pp.max_instances);
+        FPC_LAUNCH_CHECK("k_instance_stats");
+    }
     k_scan_rows_per_instance<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_instances, pp.max_rows);
     FPC_LAUNCH_CHECK("k_scan_rows_per_instance");
     return FPC_OK;
@@ -619,11 +856,9 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
 
 int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, int gather_mode,
                             bool want_records, int vote_chunk, cudaStream_t st) {
-    const int grid = sm_count() * 8;
-    k_row_count<<<grid, 256, 0, st>>>(ws.label, ws.T, ws.R, ws.counters, pp, ws.votes);
-    FPC_LAUNCH_CHECK("k_row_count");
-    k_row_prefix<<<grid, 256, 0, st>>>(ws.T, ws.R, ws.counters);
-    FPC_LAUNCH_CHECK("k_row_prefix");
+    const int grid = sm_count() * 32;   // one warp per (instance,row) item, grid-stride: plenty of loads in flight
+    k_rows<<<grid, 128, 0, st>>>(ws.label, ws.T, ws.R, ws.counters, pp, ws.votes);
+    FPC_LAUNCH_CHECK("k_rows");
     k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk);
     FPC_LAUNCH_CHECK("k_scan_records");
     float4 *rec = want_records ? ws.rec : nullptr;

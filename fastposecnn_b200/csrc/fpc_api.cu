@@ -43,7 +43,7 @@ void stage_mark() {
 }
 void stage_end() { g_stage = StageRec(); }
 
-__global__ void __launch_bounds__(256) k_bench_fma(float *sink, int iters) {
+__global__ void __launch_bounds__(256) fpc_fma_peak_kernel(float *sink, int iters) {
     float a[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) a[k] = (float)(threadIdx.x + k) * 1e-3f;
@@ -181,6 +181,7 @@ static size_t carve(Workspace &ws, void *base, long long P, int max_instances, i
     ws.T.pxoff = c.take<int>(ni);
     ws.T.workoff = c.take<int>(ni);
     ws.R.base = c.take<int>((size_t)max_rows);
+    ws.R.inst = c.take<int>((size_t)max_rows);
     ws.R.sum = c.take<float>((size_t)max_rows * 8);
     ws.rec = c.take<float4>((size_t)max_records);
     if (own_hyp) ws.hyp = c.take<float2>((size_t)max_instances * hn);
@@ -274,20 +275,20 @@ size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *a) {
     return carve(ws, nullptr, P, a->max_instances, a->hn, a->max_records, a->max_rows, true, true, true, true) + 256;
 }
 
-int fpc_pose_recover_num_launches(void) { return 13; }
+int fpc_pose_recover_num_launches(void) { return 12; }
 
 const char *fpc_pose_recover_kernel_name(int k) {
-    static const char *names[13] = {"k_argmax_init",  "k_ccl_merge",   "k_ccl_flatten", "k_scan_tiles",
+    static const char *names[12] = {"k_argmax_init",  "k_ccl_merge",   "k_ccl_flatten", "k_scan_tiles",
                                     "k_assign_ids",   "k_instance_stats", "k_scan_rows_per_instance",
-                                    "k_row_count",    "k_row_prefix",  "k_scan_records", "k_gather",
+                                    "k_rows",         "k_scan_records", "k_gather",
                                     "k_vote",         "k_finalize"};
-    return (k >= 0 && k < 13) ? names[k] : "";
+    return (k >= 0 && k < 12) ? names[k] : "";
 }
 
 int fpc_bench_fp32_fma(float *sink, int blocks, int iters, void *stream) {
     if (!sink || blocks <= 0 || iters <= 0) return fail(FPC_EINVAL, "bad argument");
-    k_bench_fma<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters);
-    FPC_LAUNCH_CHECK("k_bench_fma");
+    fpc_fma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+    FPC_LAUNCH_CHECK("fpc_fma_peak_kernel");
     return FPC_OK;
 }
 

@@ -115,34 +115,35 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
     return v;
 }
 
-// Exclusive scan of data[0..n) in place by ONE thread block (any blockDim multiple of 32, <= 1024).
-// Returns the total in every thread.
+// Exclusive scan of data[0..n) in place by ONE thread block (blockDim a multiple of 32, <= 1024).
+// Each thread owns a contiguous chunk (serial scan), the chunk totals are scanned once across the
+// block: two passes over the data and three barriers regardless of n.  Returns the total in every thread.
 __device__ inline int block_exclusive_scan_inplace(int *data, int n) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
+    __shared__ int s_total;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
+    int sum = 0;
+    for (int i = beg; i < end; ++i) sum += data[i];
+    const int inc = warp_incl_scan(sum, lane);
+    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        int v = (i < n) ? data[i] : 0;
-        int inc = warp_incl_scan(v, lane);
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            int w = (lane < nw) ? s_warp[lane] : 0;
-            int winc = warp_incl_scan(w, lane);
-            s_warp[lane] = winc - w;  // exclusive offset of each warp
-        }
-        __syncthreads();
-        int carry = s_carry;
-        int woff = s_warp[wid];
-        if (i < n) data[i] = carry + woff + inc - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + inc;  // last thread holds the chunk total
-        __syncthreads();
+    if (wid == 0) {
+        const int w = (lane < nw) ? s_warp[lane] : 0;
+        const int winc = warp_incl_scan(w, lane);
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_total = winc;
     }
-    return s_carry;
+    __syncthreads();
+    int run = s_warp[wid] + inc - sum;
+    for (int i = beg; i < end; ++i) {
+        const int v = data[i];
+        data[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    return s_total;
 }
 
 }  // namespace fpc

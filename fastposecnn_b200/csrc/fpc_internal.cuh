@@ -19,7 +19,8 @@ struct InstTables {
 
 // Per-(instance,row) tables.
 struct RowTables {
-    int *base;     // voting pixels in the row, then their exclusive prefix inside the instance
+    int *base;     // exclusive prefix (inside the instance) of the voting pixels per row
+    int *inst;     // row item -> instance
     float *sum;    // [rows,8] partial sums: q0..q3, s0..s2, z
 };
 

@@ -1,6 +1,6 @@
 """Fused entry of the path: per-pixel head outputs -> per-instance pose table.
 
-Replaces, in one stream of 13 kernel launches with no host synchronisation,
+Replaces, in one stream of 12 kernel launches with no host synchronisation,
 ``Model.class_compression`` -> ``aggregate`` -> ``hough_voting`` ->
 ``perform_RT_calculation`` (lib/pose_regressor.py:445-504 of the reference).
 The dense intermediates of the reference (``instance_masks [N,h,w]``,
@@ -51,6 +51,7 @@ class PoseRecoveryEngine:
         self.hyp = torch.empty((self.max_instances, hn, 2), dtype=torch.float32, device=self.device)
         self.votes = torch.empty((self.max_instances, hn), dtype=torch.int32, device=self.device)
         self.num_launches = int(L.fpc_pose_recover_num_launches())
+        self._fetch_event = None
 
     def _base_args(self) -> RecoverArgs:
         a = RecoverArgs()
@@ -62,7 +63,7 @@ class PoseRecoveryEngine:
 
     def launch(self, logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, idxs: Optional[torch.Tensor] = None,
                select_u: Optional[torch.Tensor] = None, stage_events=None) -> None:
-        """Enqueues the 13 kernels on the current stream.  No synchronisation."""
+        """Enqueues the 12 kernels on the current stream.  No synchronisation."""
         b, h, w, C, K = self.b, self.h, self.w, self.num_classes, self.num_classes - 1
         f32 = torch.float32
         mask = _lib.require_device_readable(logits["mask"], "logits['mask']", f32)
@@ -114,10 +115,22 @@ class PoseRecoveryEngine:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().fpc_pose_recover(ctypes.byref(a)))
 
-    def fetch_count(self) -> int:
-        """The path's single device->host read: N (and the capacity flags)."""
+    def enqueue_fetch(self) -> None:
+        """Enqueues the path's single device->host read (the 16 counters: N and the capacity flags) behind the
+        kernels and records an event; ``wait_count`` later blocks on that event only, so the next batch can
+        already be in the stream (see ``PoseRecoveryPipeline``)."""
         self.counters_host.copy_(self.counters, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if self._fetch_event is None:
+            self._fetch_event = torch.cuda.Event()
+        self._fetch_event.record(torch.cuda.current_stream(self.device))
+
+    def fetch_count(self) -> int:
+        """launch()'s companion: enqueue the read of N and wait for it."""
+        self.enqueue_fetch()
+        return self.wait_count()
+
+    def wait_count(self) -> int:
+        self._fetch_event.synchronize()
         c = self.counters_host
         flags = int(c[_lib.CNT_FLAGS])
         if flags:
@@ -159,6 +172,37 @@ def table_to_agg(table: torch.Tensor, n: int, sample_offset: int = 0) -> Dict[st
         "refine_inliers": ti[:, L.ROW_REFINE_INL].to(torch.int64),
     }
     return agg
+
+
+class PoseRecoveryPipeline:
+    """``depth`` engines used round-robin on one stream: batch k+1 is enqueued before the host waits for
+    batch k's instance count, so the GPU never idles on the host round trip.  Every batch still performs its
+    own device->host read; results of the last ``depth`` batches stay valid (each engine owns its tables)."""
+
+    def __init__(self, depth: int, *engine_args, **engine_kw):
+        self.engines = [PoseRecoveryEngine(*engine_args, **engine_kw) for _ in range(depth)]
+        self._k = 0
+        self._pending = []
+
+    def submit(self, logits, inv_intrinsics, idxs=None, select_u=None, stage_events=None, after_launch=None):
+        """Enqueue one batch.  Returns (engine, N) of the OLDEST in-flight batch once ``depth`` are in flight,
+        else None."""
+        eng = self.engines[self._k % len(self.engines)]
+        self._k += 1
+        eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u, stage_events=stage_events)
+        if after_launch is not None:
+            after_launch(eng)
+        eng.enqueue_fetch()
+        self._pending.append(eng)
+        if len(self._pending) >= len(self.engines):
+            old = self._pending.pop(0)
+            return old, old.wait_count()
+        return None
+
+    def drain(self):
+        out = [(e, e.wait_count()) for e in self._pending]
+        self._pending = []
+        return out
 
 
 _engines: Dict[tuple, PoseRecoveryEngine] = {}
