@@ -564,13 +564,14 @@ __global__ void __launch_bounds__(128) k_rows(const int *__restrict__ label, Ins
 }
 
 // I2. record offsets and vote work items per instance (single block)
-__global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counters, long long max_records, int chunk) {
+__global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counters, long long max_records, int chunk,
+                                                       int nbatch) {
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const int tn = T.tn[i];
-        T.pxoff[i] = tn;
-        T.workoff[i] = (tn + chunk - 1) / chunk;
+        T.pxoff[i] = (tn + 3) & ~3;                          // 16-byte aligned record ranges (bulk copies)
+        T.workoff[i] = ((tn + chunk - 1) / chunk) * nbatch;
     }
     __syncthreads();
     const int total = block_exclusive_scan_inplace(T.pxoff, N);
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counte
 template <int MODE>
 __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, const uint8_t *__restrict__ cls,
                                                 InstTables T, RowTables R, const int *__restrict__ counters,
-                                                PathParams pp, FieldSrc F, float4 *__restrict__ rec) {
+                                                PathParams pp, FieldSrc F, RecPlanes rec, bool want_rec) {
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
     const int rows = counters[FPC_CNT_ROWS];
@@ -655,9 +656,9 @@ __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, c
             bool sel = mem && tn > 0;
             if (sel && sub) sel = select_uniform(pp, p) < thr;
             const unsigned bal = __ballot_sync(FULL, sel);
-            if (sel && rec) {
+            if (sel && want_rec) {
                 const int idx = rec0 + running + __popc(bal & ((1u << lane) - 1u));
-                rec[idx] = make_float4((float)x, (float)it.y, vx, vy);
+                rec.x[idx] = (float)x; rec.y[idx] = (float)it.y; rec.nx[idx] = vx; rec.ny[idx] = vy;
             }
             running += __popc(bal);
         }
@@ -859,15 +860,14 @@ int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const Fie
     const int grid = sm_count() * 32;   // one warp per (instance,row) item, grid-stride: plenty of loads in flight
     k_rows<<<grid, 128, 0, st>>>(ws.label, ws.T, ws.R, ws.counters, pp, ws.votes);
     FPC_LAUNCH_CHECK("k_rows");
-    k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk);
+    k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk, vote_batches(pp.hn));
     FPC_LAUNCH_CHECK("k_scan_records");
-    float4 *rec = want_records ? ws.rec : nullptr;
     if (gather_mode == 0)
-        k_gather<0><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+        k_gather<0><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);
     else if (gather_mode == 1)
-        k_gather<1><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+        k_gather<1><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);
     else
-        k_gather<2><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, rec);
+        k_gather<2><<<grid, 256, 0, st>>>(ws.label, ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);
     FPC_LAUNCH_CHECK("k_gather");
     return FPC_OK;
 }

@@ -183,7 +183,11 @@ static size_t carve(Workspace &ws, void *base, long long P, int max_instances, i
     ws.R.base = c.take<int>((size_t)max_rows);
     ws.R.inst = c.take<int>((size_t)max_rows);
     ws.R.sum = c.take<float>((size_t)max_rows * 8);
-    ws.rec = c.take<float4>((size_t)max_records);
+    ws.rec.x = c.take<float>((size_t)max_records);
+    ws.rec.y = c.take<float>((size_t)max_records);
+    ws.rec.nx = c.take<float>((size_t)max_records);
+    ws.rec.ny = c.take<float>((size_t)max_records);
+    ws.work = c.take<int4>(((size_t)max_records / VOTE_CHUNK + (size_t)max_instances + 1) * (size_t)vote_batches(hn));
     if (own_hyp) ws.hyp = c.take<float2>((size_t)max_instances * hn);
     if (own_votes) ws.votes = c.take<int>((size_t)max_instances * hn);
     return (c.off + 255) & ~size_t(255);
@@ -275,14 +279,14 @@ size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *a) {
     return carve(ws, nullptr, P, a->max_instances, a->hn, a->max_records, a->max_rows, true, true, true, true) + 256;
 }
 
-int fpc_pose_recover_num_launches(void) { return 12; }
+int fpc_pose_recover_num_launches(void) { return 13; }
 
 const char *fpc_pose_recover_kernel_name(int k) {
-    static const char *names[12] = {"k_argmax_init",  "k_ccl_merge",   "k_ccl_flatten", "k_scan_tiles",
+    static const char *names[13] = {"k_argmax_init",  "k_ccl_merge",   "k_ccl_flatten", "k_scan_tiles",
                                     "k_assign_ids",   "k_instance_stats", "k_scan_rows_per_instance",
                                     "k_rows",         "k_scan_records", "k_gather",
-                                    "k_vote",         "k_finalize"};
-    return (k >= 0 && k < 12) ? names[k] : "";
+                                    "k_hypotheses",   "k_vote",         "k_finalize"};
+    return (k >= 0 && k < 13) ? names[k] : "";
 }
 
 int fpc_bench_fp32_fma(float *sink, int blocks, int iters, void *stream) {

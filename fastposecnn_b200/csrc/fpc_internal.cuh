@@ -46,6 +46,12 @@ struct PathParams {
     int refine;                  // 1: inlier refinement (v3); 0: winning hypothesis as is (v1)
 };
 
+// Voting records as four SoA planes, instance-major, raster order inside an instance; every instance's range
+// starts at a multiple of 4 records so that chunks can be bulk-copied (16-byte aligned) into shared memory.
+struct RecPlanes {
+    float *x, *y, *nx, *ny;
+};
+
 struct Workspace {
     uint8_t *cls;      // [P]
     int *label;        // [P]
@@ -54,7 +60,8 @@ struct Workspace {
     int *counters;     // [FPC_NUM_COUNTERS]
     InstTables T;
     RowTables R;
-    float4 *rec;       // [max_records] (x, y, dir_x, dir_y)
+    RecPlanes rec;     // 4 x [max_records]
+    int4 *work;        // vote work descriptors
     float2 *hyp;       // [max_instances, hn]
     int *votes;        // [max_instances, hn]
 };
@@ -77,6 +84,7 @@ int launch_generate_hypothesis(const float *direct, const float *coords, const i
 int launch_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo, uint8_t *inliers, int tn,
                                  int vn, int hn, float thresh, int arith, cudaStream_t st);
 void set_vote_packed(int v);
+int vote_batches(int hn);
 int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st);
 int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp, const int *votes, const float *inv_k,
                     float *pose_table, cudaStream_t st);

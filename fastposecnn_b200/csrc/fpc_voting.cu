@@ -8,6 +8,7 @@
 //   lib/gpu_tensor_funcs.py:204-253, 306-326                         translation / rotation / RT
 #include "fpc_internal.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 namespace fpc {
@@ -57,31 +58,74 @@ __global__ void __launch_bounds__(256) k_voting_for_hypothesis(const float *__re
 }
 
 // =============================================================================================
-// Fused hypothesis generation + vote counting
+// Hypotheses (K1) for every live instance: one thread per (instance, hypothesis)
 // =============================================================================================
-// Work item = (instance, chunk of <= VOTE_CHUNK voting records), handed out through an atomic ticket
-// so every resident block stays busy until the work runs out.  The chunk's pixels are staged in
-// shared memory once as six SoA planes (-x, -y, dir_x, dir_y, k_hi, k_lo); every lane keeps VQ
-// hypotheses in registers and walks the pixels with broadcast LDS.128 loads (4 pixels per load).
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__restrict__ counters, PathParams pp, RecPlanes rec,
+                                                    float2 *__restrict__ hyp_g, int4 *__restrict__ work, int nb) {
+    if (counters[FPC_CNT_FLAGS]) return;
+    const int N = counters[FPC_CNT_INSTANCES];
+    const int hn = pp.hn;
+    const long long total = (long long)N * hn;
+    // work descriptors of the vote kernel: (instance, first record, pixels | hypotheses << 16, first hypothesis)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int tn = T.tn[i], w0 = T.workoff[i];
+        const int chunks = (tn + VOTE_CHUNK - 1) / VOTE_CHUNK;
+        for (int c = 0; c < chunks; ++c)
+            for (int b = 0; b < nb; ++b) {
+                const int npx = min(VOTE_CHUNK, tn - c * VOTE_CHUNK), nh = min(1024, hn - b * 1024);
+                work[w0 + c * nb + b] = make_int4(i, T.pxoff[i] + c * VOTE_CHUNK, npx | (nh << 16), b * 1024);
+            }
+    }
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / hn), h = (int)(idx - (long long)i * hn);
+        const int tn = T.tn[i];
+        float2 hp = make_float2(0.f, 0.f);
+        if (tn > 0) {
+            int t0, t1;
+            if (pp.idxs) {
+                t0 = min(max(pp.idxs[idx * 2], 0), tn - 1);
+                t1 = min(max(pp.idxs[idx * 2 + 1], 0), tn - 1);
+            } else {
+                t0 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 0u) % (uint32_t)tn);
+                t1 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 1u) % (uint32_t)tn);
+            }
+            const size_t b0 = (size_t)T.pxoff[i] + t0, b1 = (size_t)T.pxoff[i] + t1;
+            float x, y;
+            if (hypothesis_exact<ARITH>(rec.nx[b0], rec.ny[b0], rec.x[b0], rec.y[b0], rec.nx[b1], rec.ny[b1], rec.x[b1],
+                                        rec.y[b1], x, y))
+                hp = make_float2(x, y);
+        }
+        hyp_g[idx] = hp;
+    }
+}
+
+// =============================================================================================
+// Vote counting
+// =============================================================================================
+// Work item = (instance, chunk of <= VOTE_CHUNK voting records, batch of <= VHB hypotheses), handed out through
+// an atomic ticket so every resident block stays busy until the work runs out.  Staging is double buffered and
+// done by the copy engine: one thread arms an mbarrier and issues five bulk copies (cp.async.bulk: the four
+// SoA record planes x, y, dir_x, dir_y of the chunk and the hypotheses of the batch) for the NEXT item while
+// all warps vote on the current one.  Every lane keeps VQ hypotheses in registers and walks the pixels with
+// broadcast LDS.128 loads (4 pixels per load), two pixels per packed f32x2 instruction (FFMA2/FMUL2/FADD2).
 // No inlier matrix is ever written (the reference materialises hn*tn bytes and re-reads them,
 // ransac_voting_gpu.py:562-566).
 //
-// Exactness.  The reference decides   dot(d,n) / (|n| |d|) > thresh   in rounded binary32 ops.
-// The fast test compares  s = (d.n)|d.n|  with  |d|^2 * (|n| thresh)^2 * (1 +- e),  e = 2^-18 = 64 u:
-//   hi = s - k_hi |d|^2 >= 0  -> certainly an inlier,   lo = s - k_lo |d|^2 < 0 -> certainly not.
-// Worst-case relative rounding error of the fast ratio is 12 u and of the reference's squared cosine
-// 16 u, so the two decisions can only differ inside the band (28 u < e; derivation in DESIGN.md).
-// Votes that land inside the band (a few per 10^4) are queued in shared memory and settled afterwards
-// by all lanes in parallel with the reference expression itself (explicitly rounded intrinsics), as
-// are all votes of hypotheses within 1e-3 of a pixel-lattice point (where |d| may fall under the
-// reference's 1e-6 guard).  Both sign bits of every vote are collected with funnel shifts, so the hot
-// loop has no branch.
+// Exactness.  The reference decides   cos = dot(d,n) / (|n| |d|) > t   in rounded binary32 ops; its rounded
+// cosine is within (7 + 1/t) u of the true one (u = 2^-24).  The fast test works in tangent form, which is far
+// better conditioned next to cos = 1:  with U = d.n and W = d x n,   cos > c  <=>  U > 0 and |W| < T(c) U,
+// T(c) = sqrt(1 - c^2) / c.  Two thresholds tau_hi < tau_lo bracket the reference's uncertainty plus our own
+// rounding (derivation in DESIGN.md):   |W| - tau_hi U < 0  -> certainly an inlier;   |W| - tau_lo U >= 0 ->
+// certainly not.  Votes in between (about one in 10^4) are queued in shared memory and settled afterwards by
+// all lanes in parallel with the reference expression itself (explicitly rounded intrinsics), as are all votes
+// of hypotheses within 1e-3 of a pixel-lattice point (where |d| may fall under the reference's 1e-6 guard).
+// Both sign bits of every vote are collected with funnel shifts, so the hot loop has no branch.
 constexpr int VT = 256;            // threads per block
 constexpr int VQ = 4;              // hypotheses per lane
-constexpr int VHB = 1024;          // hypotheses per shared-memory batch (8 groups of 32 lanes x VQ)
+constexpr int VHB = 1024;          // hypotheses per batch (8 groups of 32 lanes x VQ)
 constexpr int VROUND = 16;         // pixels per sign-collection round (2 bits per vote in a 32-bit word)
 constexpr int VQCAP = 2048;        // deferred exact-vote queue entries
-constexpr float BAND_E = 3.814697265625e-06f;  // 2^-18
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
@@ -90,9 +134,9 @@ __device__ __forceinline__ u64 pk2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ void unpk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
     u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
@@ -106,230 +150,282 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     return r;
 }
 
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 __device__ __forceinline__ bool near_lattice(float x, float y) {
     return fabsf(x - rintf(x)) < 1e-3f && fabsf(y - rintf(y)) < 1e-3f;
 }
 
-struct VoteSmem {
-    float ncx[VOTE_CHUNK], ncy[VOTE_CHUNK], nx[VOTE_CHUNK], ny[VOTE_CHUNK], khi[VOTE_CHUNK], klo[VOTE_CHUNK];
+struct __align__(128) VoteBuf {
+    float cx[VOTE_CHUNK], cy[VOTE_CHUNK], nx[VOTE_CHUNK], ny[VOTE_CHUNK];
     float2 hyp[VHB];
+};
+struct VoteItem {
+    int wi, i, hb, nh, npx;
+};
+struct __align__(128) VoteSmem {
+    VoteBuf buf[2];
     unsigned queue[VQCAP];
     unsigned short exlist[VHB];
-    int qn, nex, wi;
+    u64 bar[2];
+    VoteItem item[2];
+    int qn[2], nex[2];
 };
 
-// one vote on the fast path: appends sign(hi), sign(lo) to acc
-__device__ __forceinline__ void vote_fast(float hx, float hy, float ncx, float ncy, float nx, float ny, float khi,
-                                          float klo, unsigned &acc) {
-    const float dx = hx + ncx, dy = hy + ncy;
-    const float d2 = fmaf(dy, dy, dx * dx);
-    const float dt = fmaf(dy, ny, dx * nx);
-    const float s = dt * fabsf(dt);
-    const float hi = fmaf(d2, khi, s);
-    const float lo = fmaf(d2, klo, s);
-    acc = __funnelshift_l(__float_as_uint(hi), acc, 1);
-    acc = __funnelshift_l(__float_as_uint(lo), acc, 1);
+// one vote on the fast path (tangent form): appends sign(r_hi), sign(r_lo) to acc
+__device__ __forceinline__ void vote_fast(float hx, float hy, float cx, float cy, float nx, float ny, float ntau_hi,
+                                          float ntau_lo, unsigned &acc) {
+    const float dx = hx - cx, dy = hy - cy;
+    const float u = fmaf(dy, ny, dx * nx);
+    const float w = fmaf(dy, nx, -(dx * ny));
+    const float rhi = fmaf(u, ntau_hi, fabsf(w));
+    const float rlo = fmaf(u, ntau_lo, fabsf(w));
+    acc = __funnelshift_l(__float_as_uint(rhi), acc, 1);
+    acc = __funnelshift_l(__float_as_uint(rlo), acc, 1);
 }
-// two pixels (a, b) against one hypothesis, packed f32x2 arithmetic
-__device__ __forceinline__ void vote_fast2(u64 hx2, u64 hy2, u64 ncx2, u64 ncy2, u64 nx2, u64 ny2, u64 khi2, u64 klo2,
-                                           unsigned &acc) {
-    const u64 dx = add2(hx2, ncx2), dy = add2(hy2, ncy2);
-    const u64 d2 = fma2(dy, dy, mul2(dx, dx));
-    const u64 dt = fma2(dy, ny2, mul2(dx, nx2));
-    float dta, dtb;
-    unpk2(dt, dta, dtb);
-    const u64 s = pk2(dta * fabsf(dta), dtb * fabsf(dtb));
-    const u64 hi = fma2(d2, khi2, s), lo = fma2(d2, klo2, s);
+// two pixels (a, b) against one hypothesis, packed f32x2 arithmetic; nny2 = -dir_y of the two pixels
+__device__ __forceinline__ void vote_fast2(u64 hx2, u64 hy2, u64 cx2, u64 cy2, u64 nx2, u64 ny2, u64 nny2, u64 ntau_hi2,
+                                           u64 ntau_lo2, unsigned &acc) {
+    const u64 dx = sub2(hx2, cx2), dy = sub2(hy2, cy2);
+    const u64 u = fma2(dy, ny2, mul2(dx, nx2));
+    const u64 w = fma2(dy, nx2, mul2(dx, nny2));
+    float wa, wb;
+    unpk2(w, wa, wb);
+    const u64 aw = pk2(fabsf(wa), fabsf(wb));
+    const u64 rhi = fma2(u, ntau_hi2, aw), rlo = fma2(u, ntau_lo2, aw);
     float hia, hib, loa, lob;
-    unpk2(hi, hia, hib);
-    unpk2(lo, loa, lob);
+    unpk2(rhi, hia, hib);
+    unpk2(rlo, loa, lob);
     acc = __funnelshift_l(__float_as_uint(hia), acc, 1);
     acc = __funnelshift_l(__float_as_uint(loa), acc, 1);
     acc = __funnelshift_l(__float_as_uint(hib), acc, 1);
     acc = __funnelshift_l(__float_as_uint(lob), acc, 1);
 }
 
+struct VoteConsts {
+    float ntau_hi, ntau_lo;   // -tau_hi, -tau_lo
+    int all_exact;            // thresh <= 0 or otherwise outside the fast test's domain: settle every vote exactly
+    int nb;                   // hypothesis batches per (instance, chunk)
+    int hyp_bulk;             // hypotheses can be bulk-copied (hn even -> 16-byte aligned batches)
+};
+
 template <int ARITH, bool PACKED>
-__global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ counters, PathParams pp,
-                                                const float4 *__restrict__ rec, float2 *__restrict__ hyp_g,
-                                                int *__restrict__ votes) {
-    __shared__ __align__(16) VoteSmem sm;
+__global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ counters, PathParams pp, RecPlanes rec,
+                                                const float2 *__restrict__ hyp_g, int *__restrict__ votes,
+                                                const int4 *__restrict__ work, VoteConsts vc) {
+    extern __shared__ __align__(128) unsigned char vote_smem_raw[];
+    VoteSmem &sm = *reinterpret_cast<VoteSmem *>(vote_smem_raw);
     if (counters[FPC_CNT_FLAGS]) return;
-    const int N = counters[FPC_CNT_INSTANCES];
     const int W = counters[FPC_CNT_WORK];
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int hn = pp.hn;
     const float thresh = pp.inlier_thresh;
-    const bool all_exact = !(thresh > 0.f);
-    const float t2 = thresh * thresh;
 
+    // thread 0: if ticket `wi` is live, arm the buffer's barrier and start its bulk copies
+    auto fetch = [&](int b, int wi) {
+        VoteItem it;
+        it.wi = wi;
+        it.i = it.hb = it.nh = it.npx = 0;
+        if (wi < W) {
+            const int4 d = work[wi];
+            it.i = d.x;
+            it.npx = d.z & 0xffff;
+            it.nh = d.z >> 16;
+            it.hb = d.w;
+            const uint32_t pbytes = (uint32_t)((it.npx + 3) & ~3) * 4u;
+            const uint32_t hbytes = vc.hyp_bulk ? (uint32_t)it.nh * 8u : 0u;
+            const size_t src = (size_t)d.y;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
+            mbar_expect_tx(&sm.bar[b], 4u * pbytes + hbytes);
+            bulk_g2s(sm.buf[b].cx, rec.x + src, pbytes, &sm.bar[b]);
+            bulk_g2s(sm.buf[b].cy, rec.y + src, pbytes, &sm.bar[b]);
+            bulk_g2s(sm.buf[b].nx, rec.nx + src, pbytes, &sm.bar[b]);
+            bulk_g2s(sm.buf[b].ny, rec.ny + src, pbytes, &sm.bar[b]);
+            if (hbytes) bulk_g2s(sm.buf[b].hyp, hyp_g + (size_t)it.i * hn + it.hb, hbytes, &sm.bar[b]);
+        }
+        sm.item[b] = it;
+        sm.qn[b] = 0;
+        sm.nex[b] = 0;
+    };
+
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int ticket_ahead = 0;   // thread 0 only: ticket of the item after the one being prefetched (hides the atomic's latency)
+    if (tid == 0) {
+        const int t0 = atomicAdd(&counters[FPC_CNT_TICKET], 1);
+        ticket_ahead = atomicAdd(&counters[FPC_CNT_TICKET], 1);
+        fetch(0, t0);
+    }
+    __syncthreads();
+    int cur = 0;
+    uint32_t phase[2] = {0u, 0u};
     while (true) {
-        __syncthreads();  // previous work item is done with shared memory
-        if (tid == 0) {
-            sm.wi = atomicAdd(&counters[FPC_CNT_TICKET], 1);
-            sm.qn = 0;
-            sm.nex = 0;
+        const VoteItem it = sm.item[cur];
+        if (it.wi >= W) break;
+        if (tid == 0) {                        // prefetch the next item while this one is voted on
+            fetch(cur ^ 1, ticket_ahead);
+            ticket_ahead = atomicAdd(&counters[FPC_CNT_TICKET], 1);
+        }
+        mbar_wait(&sm.bar[cur], phase[cur]);
+        phase[cur] ^= 1u;
+        VoteBuf &B = sm.buf[cur];
+        const int i = it.i, npx = it.npx, nh = it.nh, hb = it.hb;
+        const int nrounds = (npx + VROUND - 1) / VROUND;
+        // ---- fix-up: padding pixels and pixels with |n| < 1e-6 (.cu:119) can never be inliers ----
+        if (tid * 4 < nrounds * VROUND) {
+            float4 cx = *reinterpret_cast<float4 *>(&B.cx[tid * 4]), cy = *reinterpret_cast<float4 *>(&B.cy[tid * 4]);
+            float4 nx = *reinterpret_cast<float4 *>(&B.nx[tid * 4]), ny = *reinterpret_cast<float4 *>(&B.ny[tid * 4]);
+            float *pcx = &cx.x, *pcy = &cy.x, *pnx = &nx.x, *pny = &ny.x;
+            bool dirty = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (tid * 4 + j >= npx) {
+                    pcx[j] = 1e18f; pcy[j] = 1e18f; pnx[j] = 0.f; pny[j] = 0.f;
+                    dirty = true;
+                } else if (below_1e6(__fsqrt_rn(sum_prod<ARITH>(pnx[j], pnx[j], pny[j], pny[j])))) {
+                    pnx[j] = 0.f; pny[j] = 0.f;
+                    dirty = true;
+                }
+            }
+            if (dirty) {
+                *reinterpret_cast<float4 *>(&B.cx[tid * 4]) = cx; *reinterpret_cast<float4 *>(&B.cy[tid * 4]) = cy;
+                *reinterpret_cast<float4 *>(&B.nx[tid * 4]) = nx; *reinterpret_cast<float4 *>(&B.ny[tid * 4]) = ny;
+            }
+        }
+        const int G = (nh + 127) >> 7;  // groups of 128 hypotheses (32 lanes x VQ)
+        for (int k = tid; k < G * 128; k += VT) {
+            float2 hp = make_float2(0.f, 0.f);
+            if (k < nh) {
+                hp = vc.hyp_bulk ? B.hyp[k] : hyp_g[(size_t)i * hn + hb + k];
+                if (vc.all_exact || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex[cur], 1)] = (unsigned short)k;
+            }
+            if (!vc.hyp_bulk || k >= nh) B.hyp[k] = hp;
         }
         __syncthreads();
-        const int wi = sm.wi;
-        if (wi >= W) break;
-        const int i = upper_index(T.workoff, N, wi);
-        const int chunk = wi - T.workoff[i];
-        const int tn = T.tn[i];
-        const int px0 = chunk * VOTE_CHUNK;
-        const int npx = min(VOTE_CHUNK, tn - px0);
-        const int nrounds = (npx + VROUND - 1) / VROUND;
-        const float4 *rec_i = rec + T.pxoff[i];
-        // ---- stage the chunk's pixels ----
-        for (int k = tid; k < nrounds * VROUND; k += VT) {
-            float ncx = -1e18f, ncy = -1e18f, nx = 0.f, ny = 0.f, khi = -1.f, klo = -1.f;  // padding: never an inlier
-            if (k < npx) {
-                const float4 r = rec_i[px0 + k];
-                ncx = -r.x; ncy = -r.y; nx = r.z; ny = r.w;
-                const float n1sq = sum_prod<ARITH>(nx, nx, ny, ny);
-                if (below_1e6(__fsqrt_rn(n1sq))) {
-                    khi = -1e30f; klo = -1e30f;      // the reference skips pixels with |n| < 1e-6 (.cu:119)
-                } else {
-                    const float m = n1sq * t2;
-                    khi = -(m * (1.0f + BAND_E));
-                    klo = -(m * (1.0f - BAND_E));
-                }
+        // ---- fast voting: warp -> (hypothesis group g, every parts-th round) ----
+        const int parts = 8 / G;  // G <= 8 because VHB = 8 * 128
+        if (wv < G * parts) {
+            const int g = wv % G, part = wv / G;
+            float hx[VQ], hy[VQ];
+            int cnt[VQ];
+            bool ex[VQ];
+#pragma unroll
+            for (int q = 0; q < VQ; ++q) {
+                const int idx = g * 128 + q * 32 + lane;
+                const float2 hp = B.hyp[idx];
+                hx[q] = hp.x; hy[q] = hp.y;
+                cnt[q] = 0;
+                ex[q] = (idx >= nh) || vc.all_exact || near_lattice(hp.x, hp.y);   // not counted on the fast path
             }
-            sm.ncx[k] = ncx; sm.ncy[k] = ncy; sm.nx[k] = nx; sm.ny[k] = ny; sm.khi[k] = khi; sm.klo[k] = klo;
-        }
-        for (int hb = 0; hb < hn; hb += VHB) {
-            const int nh = min(VHB, hn - hb);
-            const int G = (nh + 127) >> 7;  // groups of 128 hypotheses (32 lanes x VQ)
-            // ---- hypotheses of this batch (ransac_voting_kernel.cu:11-49) ----
-            for (int k = tid; k < G * 128; k += VT) {
-                float2 hp = make_float2(0.f, 0.f);
-                if (k < nh) {
-                    const int h = hb + k;
-                    int t0, t1;
-                    if (pp.idxs) {
-                        t0 = pp.idxs[((size_t)i * hn + h) * 2];
-                        t1 = pp.idxs[((size_t)i * hn + h) * 2 + 1];
-                        t0 = min(max(t0, 0), tn - 1);
-                        t1 = min(max(t1, 0), tn - 1);
+            const u64 nthi2 = pk2(vc.ntau_hi, vc.ntau_hi), ntlo2 = pk2(vc.ntau_lo, vc.ntau_lo);
+            for (int rd = part; rd < nrounds; rd += parts) {
+                unsigned acc[VQ];
+#pragma unroll
+                for (int q = 0; q < VQ; ++q) acc[q] = 0u;
+                const int kb = rd * VROUND;
+#pragma unroll
+                for (int j4 = 0; j4 < VROUND; j4 += 4) {
+                    const float4 cx = *reinterpret_cast<const float4 *>(&B.cx[kb + j4]);
+                    const float4 cy = *reinterpret_cast<const float4 *>(&B.cy[kb + j4]);
+                    const float4 nx = *reinterpret_cast<const float4 *>(&B.nx[kb + j4]);
+                    const float4 ny = *reinterpret_cast<const float4 *>(&B.ny[kb + j4]);
+                    if (PACKED) {
+                        const u64 cxa = pk2(cx.x, cx.y), cxb = pk2(cx.z, cx.w), cya = pk2(cy.x, cy.y), cyb = pk2(cy.z, cy.w);
+                        const u64 nxa = pk2(nx.x, nx.y), nxb = pk2(nx.z, nx.w), nya = pk2(ny.x, ny.y), nyb = pk2(ny.z, ny.w);
+                        const u64 nnya = pk2(-ny.x, -ny.y), nnyb = pk2(-ny.z, -ny.w);
+#pragma unroll
+                        for (int q = 0; q < VQ; ++q) {
+                            const u64 hx2 = pk2(hx[q], hx[q]), hy2 = pk2(hy[q], hy[q]);
+                            vote_fast2(hx2, hy2, cxa, cya, nxa, nya, nnya, nthi2, ntlo2, acc[q]);
+                            vote_fast2(hx2, hy2, cxb, cyb, nxb, nyb, nnyb, nthi2, ntlo2, acc[q]);
+                        }
                     } else {
-                        t0 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 0u) % (uint32_t)tn);
-                        t1 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 1u) % (uint32_t)tn);
-                    }
-                    const float4 r0 = rec_i[t0], r1 = rec_i[t1];
-                    float x, y;
-                    if (hypothesis_exact<ARITH>(r0.z, r0.w, r0.x, r0.y, r1.z, r1.w, r1.x, r1.y, x, y)) hp = make_float2(x, y);
-                    if (chunk == 0) hyp_g[(size_t)i * hn + h] = hp;
-                    if (all_exact || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex, 1)] = (unsigned short)k;
-                }
-                sm.hyp[k] = hp;
-            }
-            __syncthreads();
-            // ---- fast voting: warp -> (hypothesis group g, every parts-th round) ----
-            const int parts = 8 / G;  // G <= 8 because VHB = 8 * 128
-            if (wv < G * parts) {
-                const int g = wv % G, part = wv / G;
-                float hx[VQ], hy[VQ];
-                int cnt[VQ];
-                bool ex[VQ];
 #pragma unroll
-                for (int q = 0; q < VQ; ++q) {
-                    const int idx = g * 128 + q * 32 + lane;
-                    const float2 hp = sm.hyp[idx];
-                    hx[q] = hp.x; hy[q] = hp.y;
-                    cnt[q] = 0;
-                    ex[q] = (idx >= nh) || all_exact || near_lattice(hp.x, hp.y);   // not counted on the fast path
-                }
-                for (int rd = part; rd < nrounds; rd += parts) {
-                    unsigned acc[VQ];
-#pragma unroll
-                    for (int q = 0; q < VQ; ++q) acc[q] = 0u;
-                    const int kb = rd * VROUND;
-#pragma unroll
-                    for (int j4 = 0; j4 < VROUND; j4 += 4) {
-                        const float4 ncx = *reinterpret_cast<const float4 *>(&sm.ncx[kb + j4]);
-                        const float4 ncy = *reinterpret_cast<const float4 *>(&sm.ncy[kb + j4]);
-                        const float4 nx = *reinterpret_cast<const float4 *>(&sm.nx[kb + j4]);
-                        const float4 ny = *reinterpret_cast<const float4 *>(&sm.ny[kb + j4]);
-                        const float4 khi = *reinterpret_cast<const float4 *>(&sm.khi[kb + j4]);
-                        const float4 klo = *reinterpret_cast<const float4 *>(&sm.klo[kb + j4]);
-                        if (PACKED) {
-                            const u64 ncxa = pk2(ncx.x, ncx.y), ncxb = pk2(ncx.z, ncx.w);
-                            const u64 ncya = pk2(ncy.x, ncy.y), ncyb = pk2(ncy.z, ncy.w);
-                            const u64 nxa = pk2(nx.x, nx.y), nxb = pk2(nx.z, nx.w);
-                            const u64 nya = pk2(ny.x, ny.y), nyb = pk2(ny.z, ny.w);
-                            const u64 kha = pk2(khi.x, khi.y), khb = pk2(khi.z, khi.w);
-                            const u64 kla = pk2(klo.x, klo.y), klb = pk2(klo.z, klo.w);
-#pragma unroll
-                            for (int q = 0; q < VQ; ++q) {
-                                const u64 hx2 = pk2(hx[q], hx[q]), hy2 = pk2(hy[q], hy[q]);
-                                vote_fast2(hx2, hy2, ncxa, ncya, nxa, nya, kha, kla, acc[q]);
-                                vote_fast2(hx2, hy2, ncxb, ncyb, nxb, nyb, khb, klb, acc[q]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < VQ; ++q) {
-                                vote_fast(hx[q], hy[q], ncx.x, ncy.x, nx.x, ny.x, khi.x, klo.x, acc[q]);
-                                vote_fast(hx[q], hy[q], ncx.y, ncy.y, nx.y, ny.y, khi.y, klo.y, acc[q]);
-                                vote_fast(hx[q], hy[q], ncx.z, ncy.z, nx.z, ny.z, khi.z, klo.z, acc[q]);
-                                vote_fast(hx[q], hy[q], ncx.w, ncy.w, nx.w, ny.w, khi.w, klo.w, acc[q]);
-                            }
+                        for (int q = 0; q < VQ; ++q) {
+                            vote_fast(hx[q], hy[q], cx.x, cy.x, nx.x, ny.x, vc.ntau_hi, vc.ntau_lo, acc[q]);
+                            vote_fast(hx[q], hy[q], cx.y, cy.y, nx.y, ny.y, vc.ntau_hi, vc.ntau_lo, acc[q]);
+                            vote_fast(hx[q], hy[q], cx.z, cy.z, nx.z, ny.z, vc.ntau_hi, vc.ntau_lo, acc[q]);
+                            vote_fast(hx[q], hy[q], cx.w, cy.w, nx.w, ny.w, vc.ntau_hi, vc.ntau_lo, acc[q]);
                         }
                     }
-                    // pixel j of the round sits at bits (2*(15-j)+1: sign(hi), 2*(15-j): sign(lo))
+                }
+                // pixel j of the round sits at bits (2*(15-j)+1: sign(r_hi), 2*(15-j): sign(r_lo))
 #pragma unroll
-                    for (int q = 0; q < VQ; ++q) {
-                        const unsigned a = acc[q];
-                        cnt[q] += __popc(~a & 0xAAAAAAAAu);                 // hi >= 0
-                        unsigned b = (a >> 1) & ~a & 0x55555555u;          // hi < 0 and lo >= 0: inside the band
-                        if (b && !ex[q]) {
-                            const unsigned hidx = (unsigned)(g * 128 + q * 32 + lane);
-                            while (b) {
-                                const int pos = __ffs(b) - 1;
-                                b &= b - 1;
-                                const int k = kb + 15 - (pos >> 1);
-                                if (k < npx) {
-                                    const int slot = atomicAdd(&sm.qn, 1);
-                                    if (slot < VQCAP) {
-                                        sm.queue[slot] = ((unsigned)k << 16) | hidx;
-                                    } else if (vote_exact<ARITH>(-sm.ncx[k], -sm.ncy[k], sm.nx[k], sm.ny[k], hx[q], hy[q], thresh)) {
-                                        atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);   // queue full: settle it right here
-                                    }
-                                }
+                for (int q = 0; q < VQ; ++q) {
+                    const unsigned a = acc[q];
+                    cnt[q] += __popc(a & 0xAAAAAAAAu);                  // r_hi < 0: certainly in
+                    unsigned b = a & ~(a >> 1) & 0x55555555u;          // r_lo < 0 <= r_hi: inside the band
+                    if (b && !ex[q]) {
+                        const unsigned hidx = (unsigned)(g * 128 + q * 32 + lane);
+                        while (b) {
+                            const int pos = __ffs(b) - 1;
+                            b &= b - 1;
+                            const int k = kb + 15 - (pos >> 1);
+                            const int slot = atomicAdd(&sm.qn[cur], 1);
+                            if (slot < VQCAP) {
+                                sm.queue[slot] = ((unsigned)k << 16) | hidx;
+                            } else if (vote_exact<ARITH>(B.cx[k], B.cy[k], B.nx[k], B.ny[k], hx[q], hy[q], thresh)) {
+                                atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);   // queue full: settle it right here
                             }
                         }
                     }
                 }
+            }
 #pragma unroll
-                for (int q = 0; q < VQ; ++q) {
-                    const int idx = g * 128 + q * 32 + lane;
-                    if (!ex[q] && cnt[q]) atomicAdd(&votes[(size_t)i * hn + hb + idx], cnt[q]);
-                }
+            for (int q = 0; q < VQ; ++q) {
+                const int idx = g * 128 + q * 32 + lane;
+                if (!ex[q] && cnt[q]) atomicAdd(&votes[(size_t)i * hn + hb + idx], cnt[q]);
             }
-            __syncthreads();
-            // ---- band votes: the reference expression, one queued vote per thread ----
-            const int nq = min(sm.qn, VQCAP);
-            for (int e = tid; e < nq; e += VT) {
-                const unsigned ent = sm.queue[e];
-                const int k = (int)(ent >> 16), hidx = (int)(ent & 0xffffu);
-                const float2 hp = sm.hyp[hidx];
-                if (vote_exact<ARITH>(-sm.ncx[k], -sm.ncy[k], sm.nx[k], sm.ny[k], hp.x, hp.y, thresh))
-                    atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);
-            }
-            // ---- hypotheses on (or within 1e-3 of) the pixel lattice: every vote with the reference expression ----
-            const int nex = sm.nex;
-            for (int e = 0; e < nex; ++e) {
-                const int hidx = sm.exlist[e];
-                const float2 hp = sm.hyp[hidx];
-                int c = 0;
-                for (int k = tid; k < npx; k += VT)
-                    c += vote_exact<ARITH>(-sm.ncx[k], -sm.ncy[k], sm.nx[k], sm.ny[k], hp.x, hp.y, thresh) ? 1 : 0;
-                c = __reduce_add_sync(FULL, c);
-                if (lane == 0 && c) atomicAdd(&votes[(size_t)i * hn + hb + hidx], c);
-            }
-            __syncthreads();
-            if (tid == 0) { sm.qn = 0; sm.nex = 0; }
-            __syncthreads();
         }
+        __syncthreads();
+        // ---- band votes: the reference expression, one queued vote per thread ----
+        const int nq = min(sm.qn[cur], VQCAP);
+        for (int e = tid; e < nq; e += VT) {
+            const unsigned ent = sm.queue[e];
+            const int k = (int)(ent >> 16), hidx = (int)(ent & 0xffffu);
+            const float2 hp = B.hyp[hidx];
+            if (vote_exact<ARITH>(B.cx[k], B.cy[k], B.nx[k], B.ny[k], hp.x, hp.y, thresh))
+                atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);
+        }
+        // ---- hypotheses on (or within 1e-3 of) the pixel lattice: every vote with the reference expression ----
+        const int nex = sm.nex[cur];
+        for (int e = 0; e < nex; ++e) {
+            const int hidx = sm.exlist[e];
+            const float2 hp = B.hyp[hidx];
+            int c = 0;
+            for (int k = tid; k < npx; k += VT)
+                c += vote_exact<ARITH>(B.cx[k], B.cy[k], B.nx[k], B.ny[k], hp.x, hp.y, thresh) ? 1 : 0;
+            c = __reduce_add_sync(FULL, c);
+            if (lane == 0 && c) atomicAdd(&votes[(size_t)i * hn + hb + hidx], c);
+        }
+        __syncthreads();   // every read of buffer `cur` is done: it may be refilled by the next prefetch
+        cur ^= 1;
     }
 }
 
@@ -370,7 +466,7 @@ __device__ inline void solve_sym2_pinv(double a, double b, double c, double r0, 
 
 template <int ARITH>
 __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, const int *__restrict__ counters,
-                                                  PathParams pp, const float4 *__restrict__ rec,
+                                                  PathParams pp, RecPlanes rec,
                                                   const float2 *__restrict__ hyp_g, const int *__restrict__ votes,
                                                   const float *__restrict__ inv_k, float *__restrict__ table) {
     __shared__ double s_d[4][13];
@@ -415,9 +511,9 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
         // ---- refinement vote + normal equations over the inliers (ransac_voting_gpu.py:584-598)
         double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
         int ninl = 0;
-        const float4 *rec_i = rec + T.pxoff[i];
+        const size_t rb = (size_t)T.pxoff[i];
         for (int k = tid; k < tn; k += 128) {
-            const float4 r = rec_i[k];
+            const float4 r = make_float4(rec.x[rb + k], rec.y[rb + k], rec.nx[rb + k], rec.ny[rb + k]);
             if (vote_exact<ARITH>(r.x, r.y, r.z, r.w, wx, wy, pp.inlier_thresh)) {
                 const double nx = r.w, ny = -(double)r.z;    // normal = (dir_y, -dir_x)
                 const double bb = nx * r.x + ny * r.y;
@@ -535,26 +631,77 @@ static int vote_packed() {
     return g_vote_packed;
 }
 
+// Thresholds of the tangent-form fast test (see the comment above k_vote and DESIGN.md).
+static VoteConsts vote_consts(const PathParams &pp) {
+    VoteConsts vc;
+    vc.nb = (pp.hn + VHB - 1) / VHB;
+    vc.hyp_bulk = (pp.hn % 2 == 0) ? 1 : 0;
+    vc.all_exact = 0;
+    vc.ntau_hi = 0.f;
+    vc.ntau_lo = 0.f;
+    const double t = (double)pp.inlier_thresh;
+    const double u = ldexp(1.0, -24);
+    if (!(t > 1e-3) || !(t < 1.0)) {          // outside the fast test's domain: settle every vote exactly
+        vc.all_exact = 1;
+        return vc;
+    }
+    const double eps_r = 1.25 * (7.0 + 1.0 / t) * u;          // reference's rounded cosine vs the true one
+    const double c_hi = t * (1.0 + eps_r), c_lo = t * (1.0 - eps_r);
+    auto T = [](double c) { return c < 1.0 ? sqrt(1.0 - c * c) / c : 0.0; };
+    const double sin_hi = c_hi < 1.0 ? sqrt(1.0 - c_hi * c_hi) : 0.0;
+    double tau_hi = 0.0;
+    const double tau_lo_raw = T(c_lo);
+    double m = 1.0;
+    if (sin_hi > 0.0) {
+        m = 2.0 * (2.0 * u / sin_hi + 2.0 * u / t);            // our own rounding of |W| / U, with a factor 2 of slack
+        tau_hi = T(c_hi) * (1.0 - m);
+        if (tau_hi < 0.0) tau_hi = 0.0;
+    }
+    const double tau_lo = tau_lo_raw * (1.0 + m);
+    float fhi = (float)tau_hi, flo = (float)tau_lo;
+    if ((double)fhi > tau_hi) fhi = nextafterf(fhi, 0.f);      // round the certain-inlier bound down ...
+    if ((double)flo < tau_lo) flo = nextafterf(flo, INFINITY); // ... and the certain-outlier bound up
+    vc.ntau_hi = -fhi;
+    vc.ntau_lo = -flo;
+    return vc;
+}
+
+template <int ARITH>
+static int launch_hypotheses_t(const Workspace &ws, const PathParams &pp, float2 *hyp_out, cudaStream_t st) {
+    const VoteConsts vc = vote_consts(pp);
+    k_hypotheses<ARITH><<<sm_count() * 8, 256, 0, st>>>(ws.T, ws.counters, pp, ws.rec, hyp_out, ws.work, vc.nb);
+    FPC_LAUNCH_CHECK("k_hypotheses");
+    return FPC_OK;
+}
+
 template <int ARITH, bool PACKED>
-static int launch_vote_t(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st) {
+static int launch_vote_t(const Workspace &ws, const PathParams &pp, const float2 *hyp, int *votes, cudaStream_t st) {
     static thread_local int blocks_per_sm = 0;
+    const int smem = (int)sizeof(VoteSmem);
     if (blocks_per_sm == 0) {
+        FPC_CUDA_TRY(cudaFuncSetAttribute(k_vote<ARITH, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vote<ARITH, PACKED>, VT, 0) != cudaSuccess || n < 1) n = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vote<ARITH, PACKED>, VT, smem) != cudaSuccess || n < 1) n = 2;
         blocks_per_sm = n;
     }
-    k_vote<ARITH, PACKED><<<sm_count() * blocks_per_sm, VT, 0, st>>>(ws.T, ws.counters, pp, ws.rec, hyp_out, votes);
+    const VoteConsts vc = vote_consts(pp);
+    k_vote<ARITH, PACKED><<<sm_count() * blocks_per_sm, VT, smem, st>>>(ws.T, ws.counters, pp, ws.rec, hyp, votes, ws.work, vc);
     FPC_LAUNCH_CHECK("k_vote");
     return FPC_OK;
 }
 
 int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st) {
+    int rc = pp.arith == FPC_ARITH_IEEE ? launch_hypotheses_t<FPC_ARITH_IEEE>(ws, pp, hyp_out, st)
+                                        : launch_hypotheses_t<FPC_ARITH_NVCC_FMA>(ws, pp, hyp_out, st);
+    if (rc != FPC_OK) return rc;
     if (pp.arith == FPC_ARITH_IEEE)
         return vote_packed() ? launch_vote_t<FPC_ARITH_IEEE, true>(ws, pp, hyp_out, votes, st)
                              : launch_vote_t<FPC_ARITH_IEEE, false>(ws, pp, hyp_out, votes, st);
     return vote_packed() ? launch_vote_t<FPC_ARITH_NVCC_FMA, true>(ws, pp, hyp_out, votes, st)
                          : launch_vote_t<FPC_ARITH_NVCC_FMA, false>(ws, pp, hyp_out, votes, st);
 }
+
+int vote_batches(int hn) { return (hn + VHB - 1) / VHB; }
 
 int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp, const int *votes, const float *inv_k,
                     float *pose_table, cudaStream_t st) {

@@ -1,6 +1,6 @@
 """Fused entry of the path: per-pixel head outputs -> per-instance pose table.
 
-Replaces, in one stream of 12 kernel launches with no host synchronisation,
+Replaces, in one stream of 13 kernel launches with no host synchronisation,
 ``Model.class_compression`` -> ``aggregate`` -> ``hough_voting`` ->
 ``perform_RT_calculation`` (lib/pose_regressor.py:445-504 of the reference).
 The dense intermediates of the reference (``instance_masks [N,h,w]``,
@@ -31,7 +31,7 @@ class PoseRecoveryEngine:
         self.b, self.h, self.w, self.num_classes, self.hn = b, h, w, num_classes, hn
         P = b * h * w
         self.max_instances = int(max_instances if max_instances is not None else max(1024, 128 * b))
-        self.max_records = int(max_records if max_records is not None else P)
+        self.max_records = int(max_records if max_records is not None else P + 4 * self.max_instances)  # ranges padded to 4
         self.max_rows = int(max_rows if max_rows is not None else min(P, self.max_instances * h))
         self.inlier_thresh, self.min_num, self.max_num = float(inlier_thresh), int(min_num), int(max_num)
         self.arith, self.seed = int(arith), int(seed)
@@ -63,7 +63,7 @@ class PoseRecoveryEngine:
 
     def launch(self, logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, idxs: Optional[torch.Tensor] = None,
                select_u: Optional[torch.Tensor] = None, stage_events=None) -> None:
-        """Enqueues the 12 kernels on the current stream.  No synchronisation."""
+        """Enqueues the 13 kernels on the current stream.  No synchronisation."""
         b, h, w, C, K = self.b, self.h, self.w, self.num_classes, self.num_classes - 1
         f32 = torch.float32
         mask = _lib.require_device_readable(logits["mask"], "logits['mask']", f32)
