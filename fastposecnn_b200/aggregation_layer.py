@@ -18,7 +18,7 @@ def _pipeline_args(b, h, w, num_classes, hn, max_instances, dev, **kw):
     P = b * h * w
     a.b, a.h, a.w, a.num_classes, a.hn = b, h, w, num_classes, hn
     a.max_instances = max_instances
-    a.max_records = max(P, 1) + 4 * max_instances
+    a.max_records = max(P, 1) + 16 * max_instances
     a.max_rows = max(min(P, max_instances * h), 1)
     a.inlier_thresh = kw.get("inlier_thresh", 0.999)
     a.min_num, a.max_num = kw.get("min_num", 5), kw.get("max_num", 30000)

@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(256) k_assign_ids(const int *__restrict__ labe
                 T.xmin[id] = INT_MAX;
                 T.xmax[id] = -1;
                 T.mincls[id] = INT_MAX;
+                T.tiny[id] = 0;
             }
         }
         base += tot;
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(256) k_assign_ids_v4(const uint8_t *__restrict
             T.count[id] = 0;
             T.ymin[id] = INT_MAX; T.ymax[id] = -1; T.xmin[id] = INT_MAX; T.xmax[id] = -1;
             T.mincls[id] = INT_MAX;
+                T.tiny[id] = 0;
         }
         ++id;
     }
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counte
     const int N = counters[FPC_CNT_INSTANCES];
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const int tn = T.tn[i];
-        T.pxoff[i] = (tn + 3) & ~3;                          // 16-byte aligned record ranges (bulk copies)
+        T.pxoff[i] = (tn + 15) & ~15;                        // ranges padded to whole 16-pixel voting rounds
         T.workoff[i] = ((tn + chunk - 1) / chunk) * nbatch;
     }
     __syncthreads();
@@ -657,6 +659,9 @@ __global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, c
             if (sel && sub) sel = select_uniform(pp, p) < thr;
             const unsigned bal = __ballot_sync(FULL, sel);
             if (sel && want_rec) {
+                // a direction the reference's |n| < 1e-6 guard would skip but that is not exactly zero: the fast
+                // vote test cannot see that, so the whole instance is voted with the reference expression
+                if ((vx != 0.f || vy != 0.f) && fmaf(vx, vx, vy * vy) < 1.1e-12f) T.tiny[it.i] = 1;
                 const int idx = rec0 + running + __popc(bal & ((1u << lane) - 1u));
                 rec.x[idx] = (float)x; rec.y[idx] = (float)it.y; rec.nx[idx] = vx; rec.ny[idx] = vy;
             }
@@ -739,6 +744,7 @@ __global__ void __launch_bounds__(256) k_dense_init(InstTables T, int *counters,
     T.count[j] = 0;
     T.xmin[j] = INT_MAX; T.xmax[j] = -1; T.ymin[j] = INT_MAX; T.ymax[j] = -1;
     T.mincls[j] = 0;
+    T.tiny[j] = 0;
 }
 
 // empty problems get a one-row, zero-width box so that the row tables stay well formed

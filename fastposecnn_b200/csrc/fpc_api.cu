@@ -176,6 +176,7 @@ static size_t carve(Workspace &ws, void *base, long long P, int max_instances, i
     ws.T.xmin = c.take<int>(ni);
     ws.T.xmax = c.take<int>(ni);
     ws.T.mincls = c.take<int>(ni);
+    ws.T.tiny = c.take<int>(ni);
     ws.T.rowoff = c.take<int>(ni);
     ws.T.tn = c.take<int>(ni);
     ws.T.pxoff = c.take<int>(ni);

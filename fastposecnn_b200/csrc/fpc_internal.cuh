@@ -11,6 +11,7 @@ struct InstTables {
     int *count;    // pixels in the instance mask
     int *ymin, *ymax, *xmin, *xmax;
     int *mincls;   // min non-zero class id inside the component (aggregation_layer.py:113)
+    int *tiny;     // 1 if some voting pixel has 0 < |dir| <= ~1e-6 (reference skips it, .cu:119): vote it exactly
     int *rowoff;   // [N+1] first (instance,row) item of the instance
     int *tn;       // pixels that vote (0 if count < min_num; ~max_num if sub-sampled)
     int *pxoff;    // [N+1] first voting record of the instance
@@ -66,7 +67,10 @@ struct Workspace {
     int *votes;        // [max_instances, hn]
 };
 
-constexpr int VOTE_CHUNK = 1024;  // pixels per vote work item
+#ifndef FPC_VOTE_CHUNK
+#define FPC_VOTE_CHUNK 1024
+#endif
+constexpr int VOTE_CHUNK = FPC_VOTE_CHUNK;  // pixels per vote work item
 
 // fpc_aggregate.cu
 int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,

@@ -71,6 +71,10 @@ __global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__r
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const int tn = T.tn[i], w0 = T.workoff[i];
         const int chunks = (tn + VOTE_CHUNK - 1) / VOTE_CHUNK;
+        for (int k = tn; k < ((tn + 15) & ~15); ++k) {            // padding records: can never be inliers
+            const size_t o = (size_t)T.pxoff[i] + k;
+            rec.x[o] = 1e18f; rec.y[o] = 1e18f; rec.nx[o] = 0.f; rec.ny[o] = 0.f;
+        }
         for (int c = 0; c < chunks; ++c)
             for (int b = 0; b < nb; ++b) {
                 const int npx = min(VOTE_CHUNK, tn - c * VOTE_CHUNK), nh = min(1024, hn - b * 1024);

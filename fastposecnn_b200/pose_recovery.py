@@ -31,7 +31,7 @@ class PoseRecoveryEngine:
         self.b, self.h, self.w, self.num_classes, self.hn = b, h, w, num_classes, hn
         P = b * h * w
         self.max_instances = int(max_instances if max_instances is not None else max(1024, 128 * b))
-        self.max_records = int(max_records if max_records is not None else P + 4 * self.max_instances)  # ranges padded to 4
+        self.max_records = int(max_records if max_records is not None else P + 16 * self.max_instances)  # ranges padded to 16
         self.max_rows = int(max_rows if max_rows is not None else min(P, self.max_instances * h))
         self.inlier_thresh, self.min_num, self.max_num = float(inlier_thresh), int(min_num), int(max_num)
         self.arith, self.seed = int(arith), int(seed)
