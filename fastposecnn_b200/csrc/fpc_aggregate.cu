@@ -399,22 +399,25 @@ __global__ void __launch_bounds__(256) k_instance_stats_v4(int *label, const int
                                                            const uint8_t *__restrict__ cls, InstTables T, int w, int hw,
                                                            int P4, int max_instances) {
     __shared__ StatSlots S;
-    __shared__ int s_any;
     const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = t * 4;
+    uchar4 c = make_uchar4(0, 0, 0, 0);
+    if (t < P4) c = *reinterpret_cast<const uchar4 *>(cls + p);
     if (threadIdx.x < 8) {
         S.id[threadIdx.x] = -1; S.cnt[threadIdx.x] = 0;
         S.xmn[threadIdx.x] = INT_MAX; S.xmx[threadIdx.x] = -1; S.ymn[threadIdx.x] = INT_MAX; S.ymx[threadIdx.x] = -1;
         S.cmn[threadIdx.x] = INT_MAX;
     }
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int p = t * 4;
+    // all-background tile (most of the image): write the zero labels and leave after this one barrier
+    if (!__syncthreads_or(c.x | c.y | c.z | c.w)) {
+        if (t < P4) *reinterpret_cast<int4 *>(label + p) = make_int4(0, 0, 0, 0);
+        return;
+    }
     int id[4] = {-1, -1, -1, -1};
     int cc[4] = {0, 0, 0, 0};
     int x0 = 0, y = 0;
     if (t < P4) {
-        const uchar4 c = *reinterpret_cast<const uchar4 *>(cls + p);
         if (c.x | c.y | c.z | c.w) {
             const int4 l = *reinterpret_cast<const int4 *>(label + p);
             cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = c.w;
@@ -430,7 +433,6 @@ __global__ void __launch_bounds__(256) k_instance_stats_v4(int *label, const int
     }
     const bool any = (id[0] & id[1] & id[2] & id[3]) != -1;   // some pixel is foreground (ids are >= 0 or -1)
     if (__any_sync(FULL, any)) {
-        if (lane == 0) s_any = 1;
         // threads whose four pixels share one id: aggregate across the warp, one update per distinct id
         const bool uniform = id[0] >= 0 && id[0] == id[1] && id[1] == id[2] && id[2] == id[3];
         unsigned rem = __ballot_sync(FULL, uniform);
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(256) k_instance_stats_v4(int *label, const int
         }
     }
     __syncthreads();
-    if (s_any && threadIdx.x < 8 && S.id[threadIdx.x] >= 0) {
+    if (threadIdx.x < 8 && S.id[threadIdx.x] >= 0) {
         const int s = threadIdx.x, cur = S.id[s];
         atomicAdd(&T.count[cur], S.cnt[s]);
         atomicMin(&T.xmin[cur], S.xmn[s]); atomicMax(&T.xmax[cur], S.xmx[s]);
@@ -477,22 +479,6 @@ __global__ void __launch_bounds__(1024) k_scan_rows_per_instance(InstTables T, i
     }
 }
 
-struct RowItem {
-    int i, y, img, x0, x1, cnt;
-    bool valid;
-};
-__device__ __forceinline__ RowItem decode_row(const InstTables &T, const RowTables &R, int r, int hw) {
-    RowItem it;
-    it.i = R.inst[r];
-    it.y = T.ymin[it.i] + (r - T.rowoff[it.i]);
-    it.img = T.root[it.i] / hw;
-    it.x0 = T.xmin[it.i];
-    it.x1 = T.xmax[it.i];
-    it.cnt = T.count[it.i];
-    it.valid = true;
-    return it;
-}
-
 __device__ __forceinline__ float select_uniform(const PathParams &pp, int p) {
     if (pp.select_u) return pp.select_u[p];
     return (float)(hash3(pp.seed, (uint32_t)p, 0x5e1ec7u, 0u) >> 8) * (1.0f / 16777216.0f);
@@ -504,10 +490,14 @@ __device__ __forceinline__ float select_uniform(const PathParams &pp, int p) {
 //    ransac_voting_gpu.py:536-545: fewer than min_num pixels -> the instance does not vote;
 //    more than max_num -> Bernoulli(max_num / count) sub-sampling.
 constexpr int ROWS_PER_PASS = 1024;
-__global__ void __launch_bounds__(128) k_rows(const int *__restrict__ label, InstTables T, RowTables R,
-                                              const int *__restrict__ counters, PathParams pp, int *__restrict__ votes) {
+constexpr int ROW_CONTIG = 1 << 30;   // the row's members are one contiguous run: no label test needed
+constexpr int ROW_SUB = 1 << 29;      // instance larger than max_num: Bernoulli sub-sampling of the voters
+constexpr int ROW_VOTES = 1 << 28;    // instance has at least min_num pixels
+constexpr int ROW_LEN_MASK = (1 << 28) - 1;
+__global__ void __launch_bounds__(1024) k_rows(const int *__restrict__ label, InstTables T, RowTables R,
+                                               const int *__restrict__ counters, PathParams pp, int *__restrict__ votes) {
     __shared__ int s_cnt[ROWS_PER_PASS];
-    __shared__ int s_w[4];
+    __shared__ int s_w[32];
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -518,47 +508,49 @@ __global__ void __launch_bounds__(128) k_rows(const int *__restrict__ label, Ins
         const bool votes_at_all = cnt >= pp.min_num;
         const bool sub = cnt > pp.max_num;
         const float thr = (float)pp.max_num / (float)cnt;
-        for (int k = tid; k < pp.hn; k += 128) votes[(size_t)i * pp.hn + k] = 0;
+        for (int k = tid; k < pp.hn; k += 1024) votes[(size_t)i * pp.hn + k] = 0;
         int carry = 0;
         for (int rb = 0; rb < nrows; rb += ROWS_PER_PASS) {
             const int nr = min(ROWS_PER_PASS, nrows - rb);
-            for (int rr = wv; rr < nr; rr += 4) {
-                int n = 0;
-                if (votes_at_all) {
-                    const int rowbase = img * pp.hw + (ymin + rb + rr) * pp.w;
-                    for (int xb = x0; xb <= x1; xb += 32) {
-                        const int x = xb + lane;
-                        bool m = (x <= x1) && (label[rowbase + x] == i + 1);
-                        if (m && sub) m = select_uniform(pp, rowbase + x) < thr;
-                        n += __popc(__ballot_sync(FULL, m));
+            for (int rr = wv; rr < nr; rr += 32) {
+                // members of this row: count, extent [xs, xe], and how many of them vote
+                int n = 0, members = 0, xs = INT_MAX, xe = -1;
+                const int rowbase = img * pp.hw + (ymin + rb + rr) * pp.w;
+                for (int xb = x0; xb <= x1; xb += 32) {
+                    const int x = xb + lane;
+                    bool m = (x <= x1) && (label[rowbase + x] == i + 1);
+                    const unsigned mb = __ballot_sync(FULL, m);
+                    if (mb) {
+                        members += __popc(mb);
+                        xs = min(xs, xb + __ffs(mb) - 1);
+                        xe = max(xe, xb + 31 - __clz(mb));
                     }
+                    if (m && sub) m = select_uniform(pp, rowbase + x) < thr;
+                    if (votes_at_all) n += __popc(__ballot_sync(FULL, m));
                 }
-                if (lane == 0) s_cnt[rr] = n;
+                if (lane == 0) {
+                    s_cnt[rr] = n;
+                    if (xe < xs) { xs = x0; xe = x0 - 1; }                 // empty row of a bounding box (dense problems)
+                    const int len = xe - xs + 1;
+                    const int flags = (members == len ? ROW_CONTIG : 0) | (sub ? ROW_SUB : 0) | (votes_at_all ? ROW_VOTES : 0);
+                    R.desc[r0 + rb + rr] = make_int4(i, rowbase + xs, len | flags, 0);   // .w (prefix) is filled in below
+                }
             }
             __syncthreads();
-            // exclusive scan of s_cnt[0..nr): 8 consecutive rows per thread
-            int v[8], sum = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int rr = tid * 8 + k;
-                v[k] = rr < nr ? s_cnt[rr] : 0;
-                sum += v[k];
-            }
-            const int inc = warp_incl_scan(sum, lane);
+            // exclusive scan of s_cnt[0..nr): one row per thread
+            const int v = tid < nr ? s_cnt[tid] : 0;
+            const int inc = warp_incl_scan(v, lane);
             if (lane == 31) s_w[wv] = inc;
             __syncthreads();
-            int run = carry + inc - sum;
-            for (int k = 0; k < wv; ++k) run += s_w[k];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int rr = tid * 8 + k;
-                if (rr < nr) {
-                    R.base[r0 + rb + rr] = run;
-                    R.inst[r0 + rb + rr] = i;
-                }
-                run += v[k];
+            if (wv == 0) {
+                const int w = s_w[lane];
+                const int winc = warp_incl_scan(w, lane);
+                s_w[lane] = winc - w;
+                if (lane == 31) s_cnt[0] = winc;      // total of the pass (s_cnt is free again)
             }
-            carry += s_w[0] + s_w[1] + s_w[2] + s_w[3];
+            __syncthreads();
+            if (tid < nr) R.desc[r0 + rb + tid].w = carry + s_w[wv] + inc - v;
+            carry += s_cnt[0];
             __syncthreads();
         }
         if (tid == 0) T.tn[i] = carry;
@@ -596,89 +588,114 @@ __global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counte
 // MODE 1: class-compressed CategoricalData [b,4|3|2,h,w] (AggregationLayer drop-in)
 // MODE 2: voting records only, directions from a strided `vertex[N,h,w,vn,2]` view (ransac_voting_layer* drop-in)
 template <int MODE>
-__global__ void __launch_bounds__(256) k_gather(const int *__restrict__ label, const uint8_t *__restrict__ cls,
+__global__ void __launch_bounds__(256, 4) k_gather(const int *__restrict__ label, const uint8_t *__restrict__ cls,
                                                 InstTables T, RowTables R, const int *__restrict__ counters,
                                                 PathParams pp, FieldSrc F, RecPlanes rec, bool want_rec) {
     if (counters[FPC_CNT_FLAGS]) return;
-    const int N = counters[FPC_CNT_INSTANCES];
     const int rows = counters[FPC_CNT_ROWS];
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int K = pp.num_classes - 1;
     const size_t hw = (size_t)pp.hw;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
-        const RowItem it = decode_row(T, R, r, pp.hw);
-        const int tn = T.tn[it.i];
-        const bool sub = it.cnt > pp.max_num;
-        const float thr = (float)pp.max_num / (float)it.cnt;
-        const int rowbase = it.img * pp.hw + it.y * pp.w;
-        const int rec0 = T.pxoff[it.i] + R.base[r];
+        const int4 d = R.desc[r];                 // (instance, first member pixel, length | flags, record prefix)
+        const int i = d.x, p0 = d.y, len = d.z & ROW_LEN_MASK;
+        const bool contig = d.z & ROW_CONTIG, sub = d.z & ROW_SUB, votes = d.z & ROW_VOTES;
+        const int img = p0 / pp.hw;
+        const int pix0 = p0 - img * pp.hw;
+        const int y = pix0 / pp.w, x0 = pix0 - y * pp.w;
+        const float thr = sub ? (float)pp.max_num / (float)T.count[i] : 2.f;
+        const int rec0 = (want_rec && votes) ? T.pxoff[i] + d.w : 0;
         int running = 0;
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        for (int xb = it.x0; xb <= it.x1; xb += 32) {
-            const int x = xb + lane;
-            const int p = rowbase + x;
-            const bool mem = (x <= it.x1) && (label[p] == it.i + 1);
+        for (int kb = 0; kb < len; kb += 32) {
+            const int kx = kb + lane;
+            const int p = p0 + kx;
+            const bool mem = (kx < len) && (contig || label[p] == i + 1);
             float vx = 0.f, vy = 0.f;
             if (mem) {
-                const size_t pix = (size_t)(it.y * pp.w + x);
+                const size_t pix = (size_t)(pix0 + kx);
                 float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, zz = 0.f;
                 if (MODE == 2) {
-                    const float *v = F.xy + (long long)(it.img / F.div) * F.sN + (long long)it.y * F.sH + (long long)x * F.sW;
+                    const float *v = F.xy + (long long)(img / F.div) * F.sN + (long long)y * F.sH + (long long)(x0 + kx) * F.sW;
                     vx = v[0];
                     vy = v[F.s2];
                 } else if (MODE == 0) {
-                    const int k = (int)cls[p] - 1;  // predicted class of THIS pixel (class_compress is per pixel)
-                    const float *q = F.quaternion + ((size_t)it.img * 4 * K + 4 * k) * hw + pix;
-                    const float *s = F.scales + ((size_t)it.img * 3 * K + 3 * k) * hw + pix;
-                    const float *v = F.xy + ((size_t)it.img * 2 * K + 2 * k) * hw + pix;
+                    const size_t koff = (size_t)((int)cls[p] - 1) * hw;   // predicted class of THIS pixel (class_compress is per pixel)
+                    const float *q = F.quaternion + (size_t)img * 4 * K * hw + 4 * koff + pix;
+                    const float *s = F.scales + (size_t)img * 3 * K * hw + 3 * koff + pix;
+                    const float *v = F.xy + (size_t)img * 2 * K * hw + 2 * koff + pix;
                     q0 = __ldcs(q); q1 = __ldcs(q + hw); q2 = __ldcs(q + 2 * hw); q3 = __ldcs(q + 3 * hw);
                     s0 = __ldcs(s); s1 = __ldcs(s + hw); s2 = __ldcs(s + 2 * hw);
-                    zz = __ldcs(F.z + ((size_t)it.img * K + k) * hw + pix);
+                    zz = __ldcs(F.z + (size_t)img * K * hw + koff + pix);
                     vx = __ldcs(v); vy = __ldcs(v + hw);
-                    const float qn = __fsqrt_rn(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-                    if (qn != 0.f) { q0 = __fdiv_rn(q0, qn); q1 = __fdiv_rn(q1, qn); q2 = __fdiv_rn(q2, qn); q3 = __fdiv_rn(q3, qn); }
+                    // quaternion: only its masked mean is used (1e-4 budget) -> one reciprocal, four multiplies;
+                    // direction: feeds the votes -> keep the reference's value / norm with IEEE sqrt and divide
+                    const float qq = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+                    if (qq != 0.f) { const float rq = rsqrtf(qq); q0 *= rq; q1 *= rq; q2 *= rq; q3 *= rq; }
                     const float vn = __fsqrt_rn(vx * vx + vy * vy);
                     if (vn != 0.f) { vx = __fdiv_rn(vx, vn); vy = __fdiv_rn(vy, vn); }
                 } else {
                     // already class-compressed CategoricalData (lib/type_hinting.py:12-17): [b,4|3|2,h,w], z [b,h,w]
-                    const float *q = F.quaternion + ((size_t)it.img * 4) * hw + pix;
-                    const float *s = F.scales + ((size_t)it.img * 3) * hw + pix;
-                    const float *v = F.xy + ((size_t)it.img * 2) * hw + pix;
+                    const float *q = F.quaternion + ((size_t)img * 4) * hw + pix;
+                    const float *s = F.scales + ((size_t)img * 3) * hw + pix;
+                    const float *v = F.xy + ((size_t)img * 2) * hw + pix;
                     q0 = q[0]; q1 = q[hw]; q2 = q[2 * hw]; q3 = q[3 * hw];
                     s0 = s[0]; s1 = s[hw]; s2 = s[2 * hw];
-                    zz = F.z[(size_t)it.img * hw + pix];
+                    zz = F.z[(size_t)img * hw + pix];
                     vx = v[0]; vy = v[hw];
                 }
                 acc[0] += q0; acc[1] += q1; acc[2] += q2; acc[3] += q3;
                 acc[4] += s0; acc[5] += s1; acc[6] += s2; acc[7] += zz;
             }
-            bool sel = mem && tn > 0;
+            bool sel = mem && votes;
             if (sel && sub) sel = select_uniform(pp, p) < thr;
             const unsigned bal = __ballot_sync(FULL, sel);
             if (sel && want_rec) {
                 // a direction the reference's |n| < 1e-6 guard would skip but that is not exactly zero: the fast
                 // vote test cannot see that, so the whole instance is voted with the reference expression
-                if ((vx != 0.f || vy != 0.f) && fmaf(vx, vx, vy * vy) < 1.1e-12f) T.tiny[it.i] = 1;
+                if ((vx != 0.f || vy != 0.f) && fmaf(vx, vx, vy * vy) < 1.1e-12f) T.tiny[i] = 1;
                 const int idx = rec0 + running + __popc(bal & ((1u << lane) - 1u));
-                rec.x[idx] = (float)x; rec.y[idx] = (float)it.y; rec.nx[idx] = vx; rec.ny[idx] = vy;
+                rec.x[idx] = (float)(x0 + kx); rec.y[idx] = (float)y; rec.nx[idx] = vx; rec.ny[idx] = vy;
             }
             running += __popc(bal);
         }
+        if (MODE != 2) {
+            // warp sum of 8 values in 9 shuffles: halve the value set at every exchange (lane bit 4 keeps q or s/z, ...)
+            float a4[4], a2[2], a1;
+            {
+                const bool up = lane & 16;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float v = acc[k];
+                for (int k = 0; k < 4; ++k) {
+                    const float send = up ? acc[k] : acc[k + 4];
+                    const float keep = up ? acc[k + 4] : acc[k];
+                    a4[k] = keep + __shfl_xor_sync(FULL, send, 16);
+                }
+            }
+            {
+                const bool up = lane & 8;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-            acc[k] = v;
-        }
-        if (MODE != 2 && lane < 8) {
-            float v = acc[0];
-#pragma unroll
-            for (int k = 1; k < 8; ++k) v = (lane == k) ? acc[k] : v;
-            R.sum[(size_t)r * 8 + lane] = v;
+                for (int k = 0; k < 2; ++k) {
+                    const float send = up ? a4[k] : a4[k + 2];
+                    const float keep = up ? a4[k + 2] : a4[k];
+                    a2[k] = keep + __shfl_xor_sync(FULL, send, 8);
+                }
+            }
+            {
+                const bool up = lane & 4;
+                const float send = up ? a2[0] : a2[1];
+                const float keep = up ? a2[1] : a2[0];
+                a1 = keep + __shfl_xor_sync(FULL, send, 4);
+            }
+            a1 += __shfl_xor_sync(FULL, a1, 2);
+            a1 += __shfl_xor_sync(FULL, a1, 1);
+            // lane L (L % 4 == 0) now holds value index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1)
+            if ((lane & 3) == 0) {
+                const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                R.sum[(size_t)r * 8 + k] = a1;
+            }
         }
     }
 }
@@ -864,7 +881,7 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
 int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, int gather_mode,
                             bool want_records, int vote_chunk, cudaStream_t st) {
     const int grid = sm_count() * 32;   // one warp per (instance,row) item, grid-stride: plenty of loads in flight
-    k_rows<<<grid, 128, 0, st>>>(ws.label, ws.T, ws.R, ws.counters, pp, ws.votes);
+    k_rows<<<sm_count() * 2, 1024, 0, st>>>(ws.label, ws.T, ws.R, ws.counters, pp, ws.votes);
     FPC_LAUNCH_CHECK("k_rows");
     k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk, vote_batches(pp.hn));
     FPC_LAUNCH_CHECK("k_scan_records");

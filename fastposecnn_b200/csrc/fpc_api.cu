@@ -181,8 +181,7 @@ static size_t carve(Workspace &ws, void *base, long long P, int max_instances, i
     ws.T.tn = c.take<int>(ni);
     ws.T.pxoff = c.take<int>(ni);
     ws.T.workoff = c.take<int>(ni);
-    ws.R.base = c.take<int>((size_t)max_rows);
-    ws.R.inst = c.take<int>((size_t)max_rows);
+    ws.R.desc = c.take<int4>((size_t)max_rows);
     ws.R.sum = c.take<float>((size_t)max_rows * 8);
     ws.rec.x = c.take<float>((size_t)max_records);
     ws.rec.y = c.take<float>((size_t)max_records);

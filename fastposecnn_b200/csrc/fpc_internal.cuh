@@ -20,8 +20,7 @@ struct InstTables {
 
 // Per-(instance,row) tables.
 struct RowTables {
-    int *base;     // exclusive prefix (inside the instance) of the voting pixels per row
-    int *inst;     // row item -> instance
+    int4 *desc;    // (instance, first member pixel, length | ROW_* flags, exclusive prefix of voting pixels in the instance)
     float *sum;    // [rows,8] partial sums: q0..q3, s0..s2, z
 };
 

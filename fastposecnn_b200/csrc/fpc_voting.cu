@@ -67,21 +67,24 @@ __global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__r
     const int N = counters[FPC_CNT_INSTANCES];
     const int hn = pp.hn;
     const long long total = (long long)N * hn;
-    // work descriptors of the vote kernel: (instance, first record, pixels | hypotheses << 16, first hypothesis)
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const int tn = T.tn[i], w0 = T.workoff[i];
-        const int chunks = (tn + VOTE_CHUNK - 1) / VOTE_CHUNK;
-        for (int k = tn; k < ((tn + 15) & ~15); ++k) {            // padding records: can never be inliers
-            const size_t o = (size_t)T.pxoff[i] + k;
-            rec.x[o] = 1e18f; rec.y[o] = 1e18f; rec.nx[o] = 0.f; rec.ny[o] = 0.f;
-        }
-        for (int c = 0; c < chunks; ++c)
-            for (int b = 0; b < nb; ++b) {
-                const int npx = min(VOTE_CHUNK, tn - c * VOTE_CHUNK), nh = min(1024, hn - b * 1024);
-                work[w0 + c * nb + b] = make_int4(i, T.pxoff[i] + c * VOTE_CHUNK, npx | (nh << 16), b * 1024);
+    // threads [total, total + N): work descriptors of the vote kernel (instance, first record, pixels | hypotheses << 16,
+    // first hypothesis) and the padding records of one instance each; threads [0, total): one hypothesis each
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total + N; idx += (long long)gridDim.x * blockDim.x) {
+        if (idx >= total) {
+            const int i = (int)(idx - total);
+            const int tn = T.tn[i], w0 = T.workoff[i], px = T.pxoff[i];
+            const int chunks = (tn + VOTE_CHUNK - 1) / VOTE_CHUNK;
+            for (int k = tn; k < ((tn + 15) & ~15); ++k) {            // padding records: can never be inliers
+                const size_t o = (size_t)px + k;
+                rec.x[o] = 1e18f; rec.y[o] = 1e18f; rec.nx[o] = 0.f; rec.ny[o] = 0.f;
             }
-    }
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+            for (int c = 0; c < chunks; ++c)
+                for (int b = 0; b < nb; ++b) {
+                    const int npx = min(VOTE_CHUNK, tn - c * VOTE_CHUNK), nh = min(1024, hn - b * 1024);
+                    work[w0 + c * nb + b] = make_int4(i, px + c * VOTE_CHUNK, npx | (nh << 16), b * 1024);
+                }
+            continue;
+        }
         const int i = (int)(idx / hn), h = (int)(idx - (long long)i * hn);
         const int tn = T.tn[i];
         float2 hp = make_float2(0.f, 0.f);
@@ -515,15 +518,23 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
         // ---- refinement vote + normal equations over the inliers (ransac_voting_gpu.py:584-598)
         double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
         int ninl = 0;
-        const size_t rb = (size_t)T.pxoff[i];
-        for (int k = tid; k < tn; k += 128) {
-            const float4 r = make_float4(rec.x[rb + k], rec.y[rb + k], rec.nx[rb + k], rec.ny[rb + k]);
-            if (vote_exact<ARITH>(r.x, r.y, r.z, r.w, wx, wy, pp.inlier_thresh)) {
-                const double nx = r.w, ny = -(double)r.z;    // normal = (dir_y, -dir_x)
-                const double bb = nx * r.x + ny * r.y;
-                a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;
-                b0 += nx * bb; b1 += ny * bb;
-                ++ninl;
+        const size_t rb = (size_t)T.pxoff[i];     // multiple of 16 records; the range is padded with never-inlier records
+        for (int k4 = tid * 4; k4 < tn; k4 += 128 * 4) {
+            const float4 X = *reinterpret_cast<const float4 *>(rec.x + rb + k4);
+            const float4 Y = *reinterpret_cast<const float4 *>(rec.y + rb + k4);
+            const float4 NX = *reinterpret_cast<const float4 *>(rec.nx + rb + k4);
+            const float4 NY = *reinterpret_cast<const float4 *>(rec.ny + rb + k4);
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w};
+            const float nxs[4] = {NX.x, NX.y, NX.z, NX.w}, nys[4] = {NY.x, NY.y, NY.z, NY.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k4 + j < tn && vote_exact<ARITH>(xs[j], ys[j], nxs[j], nys[j], wx, wy, pp.inlier_thresh)) {
+                    const double nx = nys[j], ny = -(double)nxs[j];    // normal = (dir_y, -dir_x)
+                    const double bb = nx * xs[j] + ny * ys[j];
+                    a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;
+                    b0 += nx * bb; b1 += ny * bb;
+                    ++ninl;
+                }
             }
         }
         // ---- masked sums: add up the (instance,row) partials in a fixed order
