@@ -264,12 +264,12 @@ def run_b200(args):
     bytes_gather = 40 * fg * bpg                                      # predicted class's 4+3+2+1 floats, fg pixels only
     bytes_agg = (4 * wl.num_classes * hw + 40 * fg + 184 * len(discs)) * bpg
     flop_vote = sum(12.0 * tn * (hn + 1) + 4.0 * tn for tn in tn_disc) * bpg
-    i_arg, i_gather, i_vote = kernel_names.index("k_argmax_init"), kernel_names.index("k_gather"), kernel_names.index("k_vote")
+    i_arg, i_gather, i_vote = kernel_names.index("k_argmax_runs"), kernel_names.index("k_gather"), kernel_names.index("k_vote")
     agg_ms = sum(kernel_ms[k] for k in range(nk) if k not in (i_vote,))
     def hbm(bytes_, ms):
         a = bytes_ / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": None}
-    roof_argmax = dict(hbm(bytes_argmax, kernel_ms[i_arg]), kernel="k_argmax_init", ms=kernel_ms[i_arg],
+    roof_argmax = dict(hbm(bytes_argmax, kernel_ms[i_arg]), kernel="k_argmax_runs", ms=kernel_ms[i_arg],
                        algorithmic_bytes=bytes_argmax, peak_source=peak_src)
     roof_gather = dict(hbm(bytes_gather, kernel_ms[i_gather]), kernel="k_gather", ms=kernel_ms[i_gather],
                        algorithmic_bytes=bytes_gather, peak_source=peak_src)

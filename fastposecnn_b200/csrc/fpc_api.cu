@@ -160,15 +160,19 @@ struct Carver {
     }
 };
 
-static size_t carve(Workspace &ws, void *base, long long P, int max_instances, int hn, long long max_records,
-                    long long max_rows, bool own_cls, bool own_label, bool own_votes, bool own_hyp) {
+static size_t carve(Workspace &ws, void *base, long long P, long long rows_total, int max_instances, int hn,
+                    long long max_records, long long max_rows, bool own_cls, bool own_votes, bool own_hyp) {
     Carver c(base);
     const size_t ni = (size_t)max_instances + 1;
     ws.counters = nullptr;
     if (own_cls) ws.cls = c.take<uint8_t>((size_t)P);
-    if (own_label) ws.label = c.take<int>((size_t)P);
-    ws.idmap = c.take<int>((size_t)P);
     ws.tile_roots = c.take<int>((size_t)(P / 1024 + 2));
+    ws.run_tiles = c.take<int>((size_t)(max_rows / 1024 + 2));
+    ws.RT.start = c.take<int>((size_t)max_rows);
+    ws.RT.end = c.take<int>((size_t)max_rows);
+    ws.RT.parent = c.take<int>((size_t)max_rows);
+    ws.RT.inst = c.take<int>((size_t)max_rows);
+    ws.RT.rowrun = c.take<int>((size_t)rows_total + 1);
     ws.T.root = c.take<int>(ni);
     ws.T.count = c.take<int>(ni);
     ws.T.ymin = c.take<int>(ni);
@@ -176,6 +180,7 @@ static size_t carve(Workspace &ws, void *base, long long P, int max_instances, i
     ws.T.xmin = c.take<int>(ni);
     ws.T.xmax = c.take<int>(ni);
     ws.T.mincls = c.take<int>(ni);
+    ws.T.nruns = c.take<int>(ni);
     ws.T.tiny = c.take<int>(ni);
     ws.T.rowoff = c.take<int>(ni);
     ws.T.tn = c.take<int>(ni);
@@ -276,17 +281,16 @@ size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *a) {
     if (check_sizes(a) != FPC_OK) return 0;
     Workspace ws;
     const long long P = (long long)a->b * a->h * a->w;
-    return carve(ws, nullptr, P, a->max_instances, a->hn, a->max_records, a->max_rows, true, true, true, true) + 256;
+    return carve(ws, nullptr, P, (long long)a->b * a->h, a->max_instances, a->hn, a->max_records, a->max_rows, true, true, true) + 256;
 }
 
-int fpc_pose_recover_num_launches(void) { return 13; }
+int fpc_pose_recover_num_launches(void) { return 15; }
 
 const char *fpc_pose_recover_kernel_name(int k) {
-    static const char *names[13] = {"k_argmax_init",  "k_ccl_merge",   "k_ccl_flatten", "k_scan_tiles",
-                                    "k_assign_ids",   "k_instance_stats", "k_scan_rows_per_instance",
-                                    "k_rows",         "k_scan_records", "k_gather",
-                                    "k_hypotheses",   "k_vote",         "k_finalize"};
-    return (k >= 0 && k < 13) ? names[k] : "";
+    static const char *names[15] = {"k_argmax_runs", "k_scan_tiles", "k_emit_runs",    "k_run_merge",  "k_run_flatten",
+                                    "k_scan_roots",  "k_run_assign", "k_run_stats",    "k_scan_slots", "k_run_slots",
+                                    "k_scan_records", "k_gather",    "k_hypotheses",   "k_vote",       "k_finalize"};
+    return (k >= 0 && k < 15) ? names[k] : "";
 }
 
 int fpc_bench_fp32_fma(float *sink, int blocks, int iters, void *stream) {
@@ -305,12 +309,10 @@ static int setup(const fpc_recover_args *a, Workspace &ws, PathParams &pp) {
     if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return fail(FPC_EINVAL, "workspace must be 256-byte aligned");
     const long long P = (long long)a->b * a->h * a->w;
     ws.cls = a->cat_mask_u8;
-    ws.label = a->labels;
     ws.votes = a->vote_counts_out;
     ws.hyp = reinterpret_cast<float2 *>(a->hyp_out);
-    const size_t need = carve(ws, a->workspace, P, a->max_instances, a->hn, a->max_records, a->max_rows,
-                              a->cat_mask_u8 == nullptr, a->labels == nullptr, a->vote_counts_out == nullptr,
-                              a->hyp_out == nullptr);
+    const size_t need = carve(ws, a->workspace, P, (long long)a->b * a->h, a->max_instances, a->hn, a->max_records,
+                              a->max_rows, a->cat_mask_u8 == nullptr, a->vote_counts_out == nullptr, a->hyp_out == nullptr);
     if (need > a->workspace_bytes)
         return fail(FPC_ECAPACITY, "workspace too small: need %zu bytes, got %zu", need, a->workspace_bytes);
     ws.counters = a->counters;
@@ -335,6 +337,7 @@ int fpc_aggregate(const fpc_recover_args *a, const int64_t *cat_mask) {
     FieldSrc F{a->quaternion, a->scales, a->xy, a->z, 0, 0, 0, 0, 1};
     if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/1, /*want_records=*/false, VOTE_CHUNK, st);
     if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, nullptr, a->pose_table, st);
+    if (rc == FPC_OK && a->labels) rc = launch_relabel(ws, pp, a->labels, st);
     return rc;
 }
 
@@ -380,6 +383,7 @@ int fpc_pose_recover(const fpc_recover_args *a) {
     if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/0, /*want_records=*/true, VOTE_CHUNK, st);
     if (rc == FPC_OK) rc = launch_vote(ws, pp, ws.hyp, ws.votes, st);
     if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, a->inv_intrinsics, a->pose_table, st);
+    if (rc == FPC_OK && a->labels) rc = launch_relabel(ws, pp, a->labels, st);
     stage_end();
     return rc;
 }

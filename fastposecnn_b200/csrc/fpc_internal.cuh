@@ -11,6 +11,7 @@ struct InstTables {
     int *count;    // pixels in the instance mask
     int *ymin, *ymax, *xmin, *xmax;
     int *mincls;   // min non-zero class id inside the component (aggregation_layer.py:113)
+    int *nruns;    // runs (horizontal segments) of the instance
     int *tiny;     // 1 if some voting pixel has 0 < |dir| <= ~1e-6 (reference skips it, .cu:119): vote it exactly
     int *rowoff;   // [N+1] first (instance,row) item of the instance
     int *tn;       // pixels that vote (0 if count < min_num; ~max_num if sub-sampled)
@@ -18,7 +19,20 @@ struct InstTables {
     int *workoff;  // [N+1] first vote work item (chunk of pixels) of the instance
 };
 
-// Per-(instance,row) tables.
+// Run tables (capacity max_rows): maximal horizontal foreground segments in raster order.
+struct RunTables {
+    int *start, *end;   // first / last pixel (linear index over the [b,h,w] volume)
+    int *parent;        // union-find over runs; after flattening: the component's first run
+    int *inst;          // instance id
+    int *rowrun;        // [b*h+1] first run at or after the start of every image row
+};
+
+constexpr int ROW_CONTIG = 1 << 30;   // the slot's members are one contiguous run: no label test needed
+constexpr int ROW_SUB = 1 << 29;      // instance larger than max_num: Bernoulli sub-sampling of the voters
+constexpr int ROW_VOTES = 1 << 28;    // instance has at least min_num pixels
+constexpr int ROW_LEN_MASK = (1 << 28) - 1;
+
+// Per-(instance,run) slot tables, instance-major, raster order inside an instance.
 struct RowTables {
     int4 *desc;    // (instance, first member pixel, length | ROW_* flags, exclusive prefix of voting pixels in the instance)
     float *sum;    // [rows,8] partial sums: q0..q3, s0..s2, z
@@ -54,9 +68,9 @@ struct RecPlanes {
 
 struct Workspace {
     uint8_t *cls;      // [P]
-    int *label;        // [P]
-    int *idmap;        // [P] root pixel -> instance id (written at root positions only)
-    int *tile_roots;   // [ntiles+1]
+    int *tile_roots;   // [ntiles+1] run starts per 1024-pixel tile (scanned in place)
+    int *run_tiles;    // [max_rows/1024+2] component roots per 1024-run tile (scanned in place)
+    RunTables RT;
     int *counters;     // [FPC_NUM_COUNTERS]
     InstTables T;
     RowTables R;
@@ -76,6 +90,8 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
                             const long long *cat_mask_i64, cudaStream_t st);
 int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const FieldSrc &F, int gather_mode,
                             bool want_records, int vote_chunk, cudaStream_t st);
+int launch_slots(const Workspace &ws, const PathParams &pp, cudaStream_t st);
+int launch_relabel(const Workspace &ws, const PathParams &pp, int *labels_out, cudaStream_t st);
 int launch_dense_problems(const Workspace &ws, const PathParams &pp, const float *fmask, const int *imask,
                           int nplanes_per_src, int match_base, int nprob, cudaStream_t st);
 int launch_materialize(const int *label, const float *table, const float *xy_cat, float *masks, float *xy_mask, int n,
@@ -93,6 +109,12 @@ int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp
                     float *pose_table, cudaStream_t st);
 int launch_get_rt(const float *q, const float *xy, const float *z, const float *inv_k, float *R, float *T, float *RT,
                   int n, cudaStream_t st);
+
+// uniform in [0,1) deciding whether pixel p of a > max_num instance votes (ransac_voting_gpu.py:542-545)
+__device__ __forceinline__ float select_uniform(const PathParams &pp, int p) {
+    if (pp.select_u) return pp.select_u[p];
+    return (float)(hash3(pp.seed, (uint32_t)p, 0x5e1ec7u, 0u) >> 8) * (1.0f / 16777216.0f);
+}
 
 // Largest i in [0,n) with a[i] <= v  (a ascending, a[0] == 0 <= v).
 __device__ __forceinline__ int upper_index(const int *__restrict__ a, int n, int v) {

@@ -1,6 +1,6 @@
 """Fused entry of the path: per-pixel head outputs -> per-instance pose table.
 
-Replaces, in one stream of 13 kernel launches with no host synchronisation,
+Replaces, in one stream of 15 kernel launches with no host synchronisation,
 ``Model.class_compression`` -> ``aggregate`` -> ``hough_voting`` ->
 ``perform_RT_calculation`` (lib/pose_regressor.py:445-504 of the reference).
 The dense intermediates of the reference (``instance_masks [N,h,w]``,
@@ -24,7 +24,8 @@ class PoseRecoveryEngine:
 
     def __init__(self, b: int, h: int, w: int, num_classes: int, hn: int, device, *, max_instances: Optional[int] = None,
                  max_records: Optional[int] = None, max_rows: Optional[int] = None, inlier_thresh: float = 0.999,
-                 min_num: int = 5, max_num: int = 30000, arith: int = _lib.ARITH_IEEE, seed: int = 1234):
+                 min_num: int = 5, max_num: int = 30000, arith: int = _lib.ARITH_IEEE, seed: int = 1234,
+                 want_labels: bool = False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("PoseRecoveryEngine needs a CUDA device (no CPU path)")
@@ -47,7 +48,8 @@ class PoseRecoveryEngine:
         self.counters = self.table_full[0, :_lib.NUM_COUNTERS].view(torch.int32)
         self.counters_host = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int32).pin_memory()
         self.cat_mask_u8 = torch.empty((b, h, w), dtype=torch.uint8, device=self.device)
-        self.labels = torch.empty((b, h, w), dtype=torch.int32, device=self.device)
+        # the scipy-style label volume (instance id + 1 per pixel) is an optional output: one extra kernel
+        self.labels = torch.empty((b, h, w), dtype=torch.int32, device=self.device) if want_labels else None
         self.hyp = torch.empty((self.max_instances, hn, 2), dtype=torch.float32, device=self.device)
         self.votes = torch.empty((self.max_instances, hn), dtype=torch.int32, device=self.device)
         self.num_launches = int(L.fpc_pose_recover_num_launches())
@@ -63,7 +65,7 @@ class PoseRecoveryEngine:
 
     def launch(self, logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, idxs: Optional[torch.Tensor] = None,
                select_u: Optional[torch.Tensor] = None, stage_events=None) -> None:
-        """Enqueues the 13 kernels on the current stream.  No synchronisation."""
+        """Enqueues the 15 kernels on the current stream.  No synchronisation."""
         b, h, w, C, K = self.b, self.h, self.w, self.num_classes, self.num_classes - 1
         f32 = torch.float32
         mask = _lib.require_device_readable(logits["mask"], "logits['mask']", f32)
@@ -102,7 +104,9 @@ class PoseRecoveryEngine:
                 raise RuntimeError("select_u must be [b,h,w]")
             a.select_u = select_u.data_ptr()
         a.pose_table, a.counters = self.pose_table.data_ptr(), self.counters.data_ptr()
-        a.cat_mask_u8, a.labels = self.cat_mask_u8.data_ptr(), self.labels.data_ptr()
+        a.cat_mask_u8 = self.cat_mask_u8.data_ptr()
+        if self.labels is not None:
+            a.labels = self.labels.data_ptr()
         a.hyp_out, a.vote_counts_out = self.hyp.data_ptr(), self.votes.data_ptr()
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
         a.stream = _lib.current_stream(self.device)
@@ -228,7 +232,7 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
     b, C, h, w = mask.shape
     # head maps may also be PINNED HOST tensors (read in place over PCIe); the device then comes from inv_intrinsics
     device = mask.device if mask.is_cuda else inv_intrinsics.device
-    eng = get_engine(b, h, w, C, hn, device, **engine_kw)
+    eng = get_engine(b, h, w, C, hn, device, want_labels=True, **engine_kw)
     eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
     n = eng.fetch_count()
     agg = eng.table_to_agg(n)

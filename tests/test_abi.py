@@ -49,8 +49,8 @@ def test_error_codes_not_exit():
     assert L.fpc_pose_recover(None) == _lib.FPC_EINVAL
     with pytest.raises(RuntimeError, match="libfpc_b200 error -1"):
         _lib.check(L.fpc_pose_recover(None))
-    assert L.fpc_pose_recover_num_launches() == 13
-    assert L.fpc_pose_recover_kernel_name(11) == b"k_vote"
+    assert L.fpc_pose_recover_num_launches() == 15
+    assert L.fpc_pose_recover_kernel_name(13) == b"k_vote"
 
 
 def test_no_cpu_fallback():

@@ -55,7 +55,7 @@ def test_fused_vote_counts_close_to_oracle():
     frames, h, w = helpers.scenes()["wide"]
     from fastposecnn_b200.pose_recovery import get_engine
     logits, cat, agg, details, out = _run_both(frames, h, w, hn=128)
-    eng = get_engine(len(frames), h, w, 7, 128, torch.device("cuda:0"))
+    eng = get_engine(len(frames), h, w, 7, 128, torch.device("cuda:0"), want_labels=True)
     votes = eng.votes.cpu()
     hyp = eng.hyp.cpu()
     for i, d in enumerate(details):

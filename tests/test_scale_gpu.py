@@ -78,7 +78,7 @@ def test_many_small_components_noise_mask():
     logits["mask"][:, 1:] += (torch.rand(b, 6, h, w, generator=g) < 0.08) * 3.0
     cat = port.class_compression(logits, 7)
     lab_ref, total = port.label_instances(cat["mask"] != 0)
-    eng = PoseRecoveryEngine(b, h, w, 7, 16, DEV, max_instances=total + 8)
+    eng = PoseRecoveryEngine(b, h, w, 7, 16, DEV, max_instances=total + 8, want_labels=True)
     eng.launch({k: v.to(DEV) for k, v in logits.items()}, torch.inverse(syn.camera_intrinsics()).to(DEV))
     assert eng.fetch_count() == total and total > 1000
     assert torch.equal(eng.labels.cpu(), lab_ref.to(torch.int32))
