@@ -54,6 +54,8 @@ class PoseRecoveryEngine:
         self.votes = torch.empty((self.max_instances, hn), dtype=torch.int32, device=self.device)
         self.num_launches = int(L.fpc_pose_recover_num_launches())
         self._fetch_event = None
+        self._graph = None
+        self._idxs_keepalive = None
 
     def _base_args(self) -> RecoverArgs:
         a = RecoverArgs()
@@ -118,6 +120,26 @@ class PoseRecoveryEngine:
             a.num_stage_events = len(stage_events)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().fpc_pose_recover(ctypes.byref(a)))
+
+    def capture(self, logits, inv_intrinsics, idxs=None, select_u=None) -> None:
+        """Captures the launch sequence for these (fixed-address) inputs into a CUDA graph; ``replay()`` then
+        re-issues all kernels with one driver call.  The inputs' storage must stay alive and in place."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)      # warm-up: pads idxs, fixes addresses
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.launch(logits, inv_intrinsics, idxs=self._idxs_keepalive if idxs is not None else None, select_u=select_u)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph = graph
+        self._graph_inputs = (logits, inv_intrinsics, idxs, select_u)
+
+    def replay(self) -> None:
+        if self._graph is None:
+            raise RuntimeError("PoseRecoveryEngine.replay(): call capture() first")
+        self._graph.replay()
 
     def enqueue_fetch(self) -> None:
         """Enqueues the path's single device->host read (the 16 counters: N and the capacity flags) behind the
@@ -188,12 +210,20 @@ class PoseRecoveryPipeline:
         self._k = 0
         self._pending = []
 
-    def submit(self, logits, inv_intrinsics, idxs=None, select_u=None, stage_events=None, after_launch=None):
-        """Enqueue one batch.  Returns (engine, N) of the OLDEST in-flight batch once ``depth`` are in flight,
-        else None."""
+    def capture(self, logits, inv_intrinsics, idxs=None, select_u=None) -> None:
+        for e in self.engines:
+            e.capture(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
+
+    def submit(self, logits=None, inv_intrinsics=None, idxs=None, select_u=None, stage_events=None, after_launch=None,
+               replay: bool = False):
+        """Enqueue one batch (``replay=True``: re-issue the captured graph of this slot's engine).  Returns
+        (engine, N) of the OLDEST in-flight batch once ``depth`` are in flight, else None."""
         eng = self.engines[self._k % len(self.engines)]
         self._k += 1
-        eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u, stage_events=stage_events)
+        if replay:
+            eng.replay()
+        else:
+            eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u, stage_events=stage_events)
         if after_launch is not None:
             after_launch(eng)
         eng.enqueue_fetch()
