@@ -25,7 +25,7 @@ def b_inv(b_mat: torch.Tensor) -> torch.Tensor:
 
 
 def _vote(nprob, h, w, vn, fmask, imask, nplanes_per_src, match_base, vertex, round_hyp_num, inlier_thresh, min_num,
-          max_num, refine, idxs, select_u, details):
+          max_num, refine, idxs, select_u, details, arith=None):
     dev = vertex.device
     out = torch.zeros((nprob, vn, 2), dtype=torch.float32, device=dev)
     if nprob == 0:
@@ -38,7 +38,8 @@ def _vote(nprob, h, w, vn, fmask, imask, nplanes_per_src, match_base, vertex, ro
     for vi in range(vn):
         with torch.cuda.device(dev):
             a, bufs = _pipeline_args(nprob, h, w, 2, round_hyp_num, nprob, dev, inlier_thresh=float(inlier_thresh),
-                                     min_num=int(min_num), max_num=int(max_num))
+                                     min_num=int(min_num), max_num=int(max_num),
+                                     arith=_lib.ARITH_IEEE if arith is None else int(arith))
             hyp = torch.empty((nprob, round_hyp_num, 2), dtype=torch.float32, device=dev)
             votes = torch.empty((nprob, round_hyp_num), dtype=torch.int32, device=dev)
             a.hyp_out, a.vote_counts_out = hyp.data_ptr(), votes.data_ptr()
@@ -79,13 +80,15 @@ def _select_u(select_mask, select_u, shape, dev):
 def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
                            min_num=5, max_num=30000, *, idxs: Optional[torch.Tensor] = None,
                            select_mask: Optional[torch.Tensor] = None, select_u: Optional[torch.Tensor] = None,
-                           details: Optional[list] = None):
+                           details: Optional[list] = None, arith: Optional[int] = None):
     """
     :param mask:      [b,h,w]   (any dtype; non-zero = pixel of instance b)
     :param vertex:    [b,h,w,vn,2]  (may be a non-contiguous view)
     :param round_hyp_num: hypotheses per instance
     :return: [b,vn,2] refined centres (x = column, y = row); (0,0) for instances with < min_num pixels
 
+    ``arith``: ``_lib.ARITH_IEEE`` (default; what a CPU build of the reference kernels computes) or
+    ``_lib.ARITH_NVCC_FMA`` (what an nvcc build of them computes).
     ``confidence`` / ``max_iter`` are accepted and ignored: the reference never re-samples ``idxs`` inside
     its while loop (:552 is outside it), so every further pass recomputes the first one.
     """
@@ -97,7 +100,7 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
     fmask = mask if (mask.dtype == torch.float32 and mask.is_contiguous()) else mask.to(torch.float32).contiguous()
     su = _select_u(select_mask, select_u, (b, h, w), vertex.device)
     return _vote(b, h, w, vn, fmask, None, 1, 0, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num, True,
-                 idxs, su, details)
+                 idxs, su, details, arith)
 
 
 def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
