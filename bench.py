@@ -30,6 +30,8 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "aggregation+voting frames/s @640x480 b32"
+# bytes per launch (dram read + write) measured by ncu on B200 for cfg2, 32 frames (profiles/)
+NCU_TRAFFIC_CFG2_B32 = {"k_argmax_runs": 280.5e6, "k_gather": 155.5e6, "k_vote": 36.5e6}
 UNIT = "frames/s"
 
 
@@ -286,18 +288,23 @@ def run_b200(args):
     flop_vote = sum(12.0 * tn * (hn + 1) + 4.0 * tn for tn in tn_disc) * bpg
     i_arg, i_gather, i_vote = kernel_names.index("k_argmax_runs"), kernel_names.index("k_gather"), kernel_names.index("k_vote")
     agg_ms = sum(kernel_ms[k] for k in range(nk) if k not in (i_vote,))
-    def hbm(bytes_, ms):
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this very
+    # command (profiles/r01_ncu_full_all_kernels_final.md); only meaningful for the default workload
+    ncu_traffic = NCU_TRAFFIC_CFG2_B32 if (args.workload == "cfg2" and bpg == 32) else {}
+
+    def hbm(bytes_, ms, kernel=None):
         a = bytes_ / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": None}
-    roof_argmax = dict(hbm(bytes_argmax, kernel_ms[i_arg]), kernel="k_argmax_runs", ms=kernel_ms[i_arg],
+        return {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                "traffic": ncu_traffic.get(kernel)}
+    roof_argmax = dict(hbm(bytes_argmax, kernel_ms[i_arg], "k_argmax_runs"), kernel="k_argmax_runs", ms=kernel_ms[i_arg],
                        algorithmic_bytes=bytes_argmax, peak_source=peak_src)
-    roof_gather = dict(hbm(bytes_gather, kernel_ms[i_gather]), kernel="k_gather", ms=kernel_ms[i_gather],
+    roof_gather = dict(hbm(bytes_gather, kernel_ms[i_gather], "k_gather"), kernel="k_gather", ms=kernel_ms[i_gather],
                        algorithmic_bytes=bytes_gather, peak_source=peak_src)
     roof_agg = dict(hbm(bytes_agg, agg_ms), kernel="all aggregation kernels (everything but k_vote)", ms=agg_ms,
                     algorithmic_bytes=bytes_agg, peak_source=peak_src)
     a_v = flop_vote / (kernel_ms[i_vote] * 1e-3) / 1e12
     roof_vote = {"bound": "fp32", "achieved": a_v, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": a_v / fp32_peak_tflops,
-                 "traffic": None, "kernel": "k_vote", "ms": kernel_ms[i_vote], "algorithmic_flop": flop_vote,
+                 "traffic": ncu_traffic.get("k_vote"), "kernel": "k_vote", "ms": kernel_ms[i_vote], "algorithmic_flop": flop_vote,
                  "votes_per_s": flop_vote / 12.0 / (kernel_ms[i_vote] * 1e-3),
                  "peak_source": "measured in this run: fpc_bench_fp32_fma (pure FFMA loop), 2 flop per FMA"}
     dominant = max(range(nk), key=lambda k: kernel_ms[k])

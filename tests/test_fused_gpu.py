@@ -99,3 +99,29 @@ def test_zero_copy_pinned_host_inputs_match_device_inputs():
         assert torch.equal(v, b[k]), k
     with pytest.raises(RuntimeError, match="pinned"):
         pose_recover(logits, inv_k, HN)          # pageable host memory is refused
+
+
+def test_pipeline_and_cuda_graph_replay_are_bit_identical():
+    """Two batches in flight + CUDA-graph replay of the 15-kernel sequence give the eager results bit for bit."""
+    from fastposecnn_b200.pose_recovery import PoseRecoveryEngine, PoseRecoveryPipeline
+    frames, h, w = helpers.scenes()["wide"]
+    dev = torch.device("cuda:0")
+    logits = {k: v.to(dev) for k, v in syn.render_heads(frames, h, w, seed=3).items()}
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(dev).contiguous()
+    eng = PoseRecoveryEngine(len(frames), h, w, 7, HN, dev)
+    eng.launch(logits, inv_k)
+    n = eng.fetch_count()
+    want = eng.pose_table[:n].clone()
+    pipe = PoseRecoveryPipeline(2, len(frames), h, w, 7, HN, dev)
+    pipe.capture(logits, inv_k)
+    got = []
+    for k in range(5):
+        res = pipe.submit(replay=(k % 2 == 0), logits=logits, inv_intrinsics=inv_k)
+        if res is not None:
+            got.append(res)
+    got += pipe.drain()
+    assert len(got) == 5
+    for e, cnt in got:
+        assert cnt == n
+    for e in pipe.engines:
+        assert torch.equal(e.pose_table[:n].view(torch.int32), want.view(torch.int32))
