@@ -190,7 +190,7 @@ struct __align__(128) VoteBuf {
     float2 hyp[VHB];
 };
 struct VoteItem {
-    int wi, i, hb, nh, npx;
+    int wi, i, hb, nh, npx, exact;
 };
 struct __align__(128) VoteSmem {
     VoteBuf buf[2];
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
     auto fetch = [&](int b, int wi) {
         VoteItem it;
         it.wi = wi;
-        it.i = it.hb = it.nh = it.npx = 0;
+        it.i = it.hb = it.nh = it.npx = it.exact = 0;
         if (wi < W) {
             const int4 d = work[wi];
             it.i = d.x;
@@ -325,12 +325,13 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
                 *reinterpret_cast<float4 *>(&B.nx[tid * 4]) = nx; *reinterpret_cast<float4 *>(&B.ny[tid * 4]) = ny;
             }
         }
+        const bool item_exact = vc.all_exact;
         const int G = (nh + 127) >> 7;  // groups of 128 hypotheses (32 lanes x VQ)
         for (int k = tid; k < G * 128; k += VT) {
             float2 hp = make_float2(0.f, 0.f);
             if (k < nh) {
                 hp = vc.hyp_bulk ? B.hyp[k] : hyp_g[(size_t)i * hn + hb + k];
-                if (vc.all_exact || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex[cur], 1)] = (unsigned short)k;
+                if (item_exact || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex[cur], 1)] = (unsigned short)k;
             }
             if (!vc.hyp_bulk || k >= nh) B.hyp[k] = hp;
         }
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
                 const float2 hp = B.hyp[idx];
                 hx[q] = hp.x; hy[q] = hp.y;
                 cnt[q] = 0;
-                ex[q] = (idx >= nh) || vc.all_exact || near_lattice(hp.x, hp.y);   // not counted on the fast path
+                ex[q] = (idx >= nh) || item_exact || near_lattice(hp.x, hp.y);   // not counted on the fast path
             }
             const u64 nthi2 = pk2(vc.ntau_hi, vc.ntau_hi), ntlo2 = pk2(vc.ntau_lo, vc.ntau_lo);
             for (int rd = part; rd < nrounds; rd += parts) {
