@@ -86,3 +86,42 @@ def test_many_small_components_noise_mask():
     out = eng.table_to_agg(total)
     assert torch.equal(out["class_ids"].cpu(), agg["class_ids"].long())
     assert out["mask_sizes"].cpu().tolist() == [int(v) for v in agg["instance_masks"].sum(dim=(-2, -1)).tolist()]
+
+
+@pytest.mark.parametrize("seed,h,w", [(0, 120, 160), (1, 97, 131), (2, 240, 320)])
+def test_irregular_blobs_with_holes_and_concavities(seed, h, w):
+    """Thresholded smooth random fields: big concave components, holes, U-shapes that merge late, several runs per
+    row per instance, touching classes.  Everything integer must match scipy / the oracle bit for bit."""
+    import torch.nn.functional as F
+    from fastposecnn_b200.pose_recovery import PoseRecoveryEngine
+    from helpers import port
+    g = torch.Generator().manual_seed(seed)
+    b = 3
+    logits = syn.render_heads([[]] * b, h, w, seed=seed)
+    field = torch.randn(b, 6, h // 8 + 2, w // 8 + 2, generator=g)
+    field = F.interpolate(field, size=(h, w), mode="bicubic", align_corners=False)
+    logits["mask"][:, 1:] += torch.round(field * 2.0 * 1024) / 1024       # blobs of every class, quantised like the generator
+    cat = port.class_compression(logits, 7)
+    lab_ref, total = port.label_instances(cat["mask"] != 0)
+    assert total >= 3
+    eng = PoseRecoveryEngine(b, h, w, 7, 32, DEV, max_instances=total + 8, want_labels=True)
+    eng.launch({k: v.to(DEV) for k, v in logits.items()}, torch.inverse(syn.camera_intrinsics()).to(DEV))
+    assert eng.fetch_count() == total
+    assert torch.equal(eng.cat_mask_u8.cpu().long(), cat["mask"])
+    assert torch.equal(eng.labels.cpu(), lab_ref.to(torch.int32))
+    agg = port.aggregate(cat)
+    out = eng.table_to_agg(total)
+    assert torch.equal(out["class_ids"].cpu(), agg["class_ids"].long())
+    assert torch.equal(out["sample_ids"].cpu(), agg["sample_ids"])
+    assert out["mask_sizes"].cpu().tolist() == [int(v) for v in agg["instance_masks"].sum(dim=(-2, -1)).tolist()]
+    for k in ("quaternion", "scales", "z"):
+        import helpers
+        assert helpers.rel_err(out[k], agg[k]) <= helpers.REL_TOL, k
+    # drop-in aggregation on the same categorical data: dense instance masks bit-exact
+    import fastposecnn_b200 as fp
+
+    class HP:
+        HV_NUM_OF_HYPOTHESES = 32
+    got = fp.AggregationLayer(HP, 7, max_instances=total + 8)({k: v.to(DEV) for k, v in cat.items()})
+    assert torch.equal(got["instance_masks"].cpu(), agg["instance_masks"])
+    assert torch.equal(got["xy"].cpu(), agg["xy"])
