@@ -148,7 +148,7 @@ def run_b200(args):
     from fastposecnn_b200 import _lib
     from fastposecnn_b200 import synthetic as syn
     from fastposecnn_b200.pose_recovery import PoseRecoveryEngine, PoseRecoveryPipeline
-    from fastposecnn_b200.sharding import gather_pose_tables
+    from fastposecnn_b200.sharding import OverlappedGather, gather_pose_tables
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -176,9 +176,8 @@ def run_b200(args):
     idxs = torch.zeros((eng.max_instances, hn, 2), dtype=torch.int32)
     idxs[:n_expected] = syn.presampled_idxs(tn_disc * bpg, hn, seed=1234).reshape(n_expected, hn, 2)
     idxs = idxs.to(dev)
-    gathered = [torch.empty((world, eng.max_instances + 1, _lib.POSE_ROW), dtype=torch.float32, device=dev)
-                for _ in range(depth)] if world > 1 else None
-    gather_slot = {id(e): i for i, e in enumerate(pipe.engines)}
+    # the one collective of the path: all-gather of the pose tables, on its own stream (overlaps the next batch)
+    gatherer = OverlappedGather(pipe.engines, world, dev) if world > 1 else None
 
     nk = eng.num_launches
     kernel_names = [_lib.lib().fpc_pose_recover_kernel_name(k).decode() for k in range(nk)]
@@ -190,8 +189,12 @@ def run_b200(args):
         return evs
 
     def after_launch(e):
-        if world > 1:
-            gather_pose_tables(e, gathered[gather_slot[id(e)]])
+        if gatherer is not None:
+            gatherer.after_launch(e)
+
+    def before_launch(e):
+        if gatherer is not None:
+            gatherer.before_reuse(e)
 
     def check(res):
         if res is not None and res[1] != n_expected:
@@ -201,7 +204,8 @@ def run_b200(args):
 
     def step(stage_events=None, replay=False):
         # one pass of the path over one batch; the host waits for the count of the batch `depth-1` steps back
-        check(pipe.submit(logits, inv_k, idxs=idxs, stage_events=stage_events, after_launch=after_launch, replay=replay))
+        check(pipe.submit(logits, inv_k, idxs=idxs, stage_events=stage_events, after_launch=after_launch, replay=replay,
+                          before_launch=before_launch))
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
@@ -247,6 +251,8 @@ def run_b200(args):
         step(replay=use_graph)
     for res in pipe.drain():
         check(res)
+    if gatherer is not None:
+        torch.cuda.current_stream().wait_stream(gatherer.stream)     # the last all-gathers are inside the timed region
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -331,8 +337,8 @@ def run_b200(args):
                 for k in host:
                     dev_in[k].copy_(host[k], non_blocking=True)
             eng.launch(dev_in, inv_k, idxs=idxs)
-            if world > 1:
-                gather_pose_tables(eng, gathered[0])
+            if gatherer is not None:
+                gather_pose_tables(eng, gatherer.out[id(eng)])
             n_ = eng.fetch_count()
             table_host[:n_].copy_(eng.pose_table[:n_], non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -215,11 +215,13 @@ class PoseRecoveryPipeline:
             e.capture(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
 
     def submit(self, logits=None, inv_intrinsics=None, idxs=None, select_u=None, stage_events=None, after_launch=None,
-               replay: bool = False):
+               replay: bool = False, before_launch=None):
         """Enqueue one batch (``replay=True``: re-issue the captured graph of this slot's engine).  Returns
         (engine, N) of the OLDEST in-flight batch once ``depth`` are in flight, else None."""
         eng = self.engines[self._k % len(self.engines)]
         self._k += 1
+        if before_launch is not None:
+            before_launch(eng)
         if replay:
             eng.replay()
         else:

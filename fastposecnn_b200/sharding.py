@@ -38,6 +38,38 @@ def gather_pose_tables(engine, out: torch.Tensor, group=None) -> torch.Tensor:
     return gather_tables(engine.table_full, out, group=group)
 
 
+class OverlappedGather:
+    """Runs the per-batch all-gather on its own stream so that the next batch's kernels (compute stream) overlap with
+    it: ``after_launch(engine)`` right after ``engine.launch`` / ``replay``; ``before_reuse(engine)`` before the same
+    engine is launched again; ``finish()`` before the gathered tables are read."""
+
+    def __init__(self, engines, world: int, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.out = {id(e): torch.empty((world, e.max_instances + 1, _lib.POSE_ROW), dtype=torch.float32, device=self.device)
+                    for e in engines}
+        self.done = {id(e): None for e in engines}
+
+    def after_launch(self, engine, group=None):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            gather_tables(engine.table_full, self.out[id(engine)], group=group)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.done[id(engine)] = done
+        return self.out[id(engine)]
+
+    def before_reuse(self, engine):
+        done = self.done[id(engine)]
+        if done is not None:
+            torch.cuda.current_stream(self.device).wait_event(done)   # the table must be sent before it is overwritten
+
+    def finish(self):
+        self.stream.synchronize()
+
+
 def merge_tables(gathered: torch.Tensor, frames_per_rank: List[int]) -> Dict[str, torch.Tensor]:
     """Concatenates the live rows of every rank's table in rank order and offsets ``sample_ids`` by the
     rank's first frame.  Raises if any rank reported a capacity overflow."""
