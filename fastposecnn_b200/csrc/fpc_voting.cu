@@ -472,13 +472,14 @@ __device__ inline void solve_sym2_pinv(double a, double b, double c, double r0, 
     y = vy * pr;
 }
 
+constexpr int FT = 256;   // threads per instance in k_finalize
 template <int ARITH>
-__global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, const int *__restrict__ counters,
+__global__ void __launch_bounds__(FT) k_finalize(InstTables T, RowTables R, const int *__restrict__ counters,
                                                   PathParams pp, RecPlanes rec,
                                                   const float2 *__restrict__ hyp_g, const int *__restrict__ votes,
                                                   const float *__restrict__ inv_k, float *__restrict__ table) {
-    __shared__ double s_d[4][13];
-    __shared__ int s_i[4][3];
+    __shared__ double s_d[FT / 32][13];
+    __shared__ int s_i[FT / 32][3];
     __shared__ float s_win[2];
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
         // ---- winner: first maximum of the vote counts (torch.max over dim 0, ransac_voting_gpu.py:567)
         int bv = -1, bi = INT_MAX;
         if (tn > 0)
-            for (int h = tid; h < hn; h += 128) {
+            for (int h = tid; h < hn; h += FT) {
                 const int v = votes[(size_t)i * hn + h];
                 if (v > bv) { bv = v; bi = h; }
             }
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
         if (lane == 0) { s_i[wv][0] = bv; s_i[wv][1] = bi; }
         __syncthreads();
         if (tid == 0) {
-            for (int k = 1; k < 4; ++k)
+            for (int k = 1; k < FT / 32; ++k)
                 if (s_i[k][0] > bv || (s_i[k][0] == bv && s_i[k][1] < bi)) { bv = s_i[k][0]; bi = s_i[k][1]; }
             float2 wpt = make_float2(0.f, 0.f);
             // the running best only moves when the ratio strictly improves on 0 (ransac_voting_gpu.py:572-574)
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
         double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
         int ninl = 0;
         const size_t rb = (size_t)T.pxoff[i];     // multiple of 16 records; the range is padded with never-inlier records
-        for (int k4 = tid * 4; k4 < tn; k4 += 128 * 4) {
+        for (int k4 = tid * 4; k4 < tn; k4 += FT * 4) {
             const float4 X = *reinterpret_cast<const float4 *>(rec.x + rb + k4);
             const float4 Y = *reinterpret_cast<const float4 *>(rec.y + rb + k4);
             const float4 NX = *reinterpret_cast<const float4 *>(rec.nx + rb + k4);
@@ -542,7 +543,7 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
         double sm[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) sm[k] = 0.0;
-        for (int r = T.rowoff[i] + tid; r < T.rowoff[i + 1]; r += 128) {
+        for (int r = T.rowoff[i] + tid; r < T.rowoff[i + 1]; r += FT) {
             const float4 u = *reinterpret_cast<const float4 *>(R.sum + (size_t)r * 8);
             const float4 v = *reinterpret_cast<const float4 *>(R.sum + (size_t)r * 8 + 4);
             sm[0] += u.x; sm[1] += u.y; sm[2] += u.z; sm[3] += u.w;
@@ -560,8 +561,12 @@ __global__ void __launch_bounds__(128) k_finalize(InstTables T, RowTables R, con
         __syncthreads();
         if (tid == 0) {
             double t[13];
-            for (int k = 0; k < 13; ++k) t[k] = s_d[0][k] + s_d[1][k] + s_d[2][k] + s_d[3][k];
-            const int inl = s_i[0][2] + s_i[1][2] + s_i[2][2] + s_i[3][2];
+            int inl = 0;
+            for (int k = 0; k < 13; ++k) t[k] = 0.0;
+            for (int wq = 0; wq < FT / 32; ++wq) {          // fixed order: deterministic sums
+                for (int k = 0; k < 13; ++k) t[k] += s_d[wq][k];
+                inl += s_i[wq][2];
+            }
             double rx = wx, ry = wy;   // v1 (ransac_voting_gpu.py:11-98) returns the winning hypothesis itself
             if (pp.refine) {
                 rx = 0.0; ry = 0.0;
@@ -723,9 +728,9 @@ int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp
                     float *pose_table, cudaStream_t st) {
     const int grid = sm_count() * 8;
     if (pp.arith == FPC_ARITH_IEEE)
-        k_finalize<FPC_ARITH_IEEE><<<grid, 128, 0, st>>>(ws.T, ws.R, ws.counters, pp, ws.rec, hyp, votes, inv_k, pose_table);
+        k_finalize<FPC_ARITH_IEEE><<<grid, FT, 0, st>>>(ws.T, ws.R, ws.counters, pp, ws.rec, hyp, votes, inv_k, pose_table);
     else
-        k_finalize<FPC_ARITH_NVCC_FMA><<<grid, 128, 0, st>>>(ws.T, ws.R, ws.counters, pp, ws.rec, hyp, votes, inv_k, pose_table);
+        k_finalize<FPC_ARITH_NVCC_FMA><<<grid, FT, 0, st>>>(ws.T, ws.R, ws.counters, pp, ws.rec, hyp, votes, inv_k, pose_table);
     FPC_LAUNCH_CHECK("k_finalize");
     return FPC_OK;
 }
