@@ -229,3 +229,47 @@ def test_samplewise_get_rt_and_staged_model():
     full = model(g_logits)                                                 # device-side sampling, no idxs
     assert set(full.keys()) == {"logits", "categorical", "aggregated"}
     assert (full["aggregated"]["xy"].cpu() - agg["xy"]).abs().max() < 0.2  # different random pairs, same centres
+
+
+@pytest.mark.parametrize("hn,thresh", [(129, 0.999), (1000, 0.999), (1030, 0.999), (96, 0.5), (96, 0.99999), (64, -1.0), (64, 1.5)])
+def test_voting_code_paths_bit_exact(hn, thresh):
+    """Odd hn (no bulk copy of the hypotheses), hn that is not a multiple of 128, more than one hypothesis batch
+    (hn > 1024), loose / tight thresholds and thresholds outside the fast test's domain (every vote settled exactly)."""
+    from fastposecnn_b200 import ransac_voting_layer_v3
+    frames, h, w = helpers.scenes()["wide"]
+    agg, vertex = _vote_inputs(frames, h, w)
+    det_ref = []
+    ref = port.ransac_voting_layer_v3(agg["instance_masks"], vertex, hn, inlier_thresh=thresh,
+                                      idx_source=port.seeded_idx_source(13), details=det_ref)
+    idxs = syn.presampled_idxs(helpers.oracle_tns(agg), hn, seed=13)
+    det = []
+    out = ransac_voting_layer_v3(agg["instance_masks"].to(DEV), agg["xy"].to(DEV).permute(0, 2, 3, 1).unsqueeze(3), hn,
+                                 inlier_thresh=thresh, idxs=idxs.to(DEV), details=det)
+    for i, r in enumerate(det_ref):
+        assert torch.equal(det[0]["hyp"][i].cpu(), r["hyp"][:, 0])
+        assert torch.equal(det[0]["counts"][i].cpu(), r["counts"][:, 0].int()), f"instance {i} (hn={hn}, t={thresh})"
+        assert int(det[0]["win_idx"][i]) == int(r["win_idx"][0])
+        assert int(det[0]["refine_inliers"][i]) == r["refine_inliers"]
+    n = out.shape[0]
+    assert helpers.rel_err(out.reshape(n, -1), ref.reshape(n, -1)) <= helpers.REL_TOL
+
+
+def test_voting_multi_keypoint_vn2():
+    """vn > 1 (PVNet generality): every keypoint is voted independently with its own pixel pairs."""
+    from fastposecnn_b200 import ransac_voting_layer_v3
+    frames, h, w = helpers.scenes()["three_frames_one_empty"]
+    agg, vertex1 = _vote_inputs(frames, h, w)
+    n = agg["instance_masks"].shape[0]
+    g = torch.Generator().manual_seed(2)
+    noise = torch.randn(vertex1.shape, generator=g) * 0.01
+    second = port.normalize((vertex1 + noise).squeeze(3).permute(0, 3, 1, 2), 1).permute(0, 2, 3, 1).unsqueeze(3)
+    vertex = torch.cat([vertex1, second * agg["instance_masks"][..., None, None]], dim=3).contiguous()   # [N,h,w,2,2]
+    hn = 40
+    det_ref = []
+    ref = port.ransac_voting_layer_v3(agg["instance_masks"], vertex, hn, idx_source=port.seeded_idx_source(4), details=det_ref)
+    # same stream of pairs: [hn, vn, 2] per instance
+    gi = torch.Generator().manual_seed(4)
+    idxs = torch.stack([torch.randint(0, tn, (hn, 2, 2), generator=gi, dtype=torch.int32) for tn in helpers.oracle_tns(agg)])
+    out = ransac_voting_layer_v3(agg["instance_masks"].to(DEV), vertex.to(DEV), hn, idxs=idxs.to(DEV))
+    assert out.shape == ref.shape == (n, 2, 2)
+    assert helpers.rel_err(out.reshape(n, -1), ref.reshape(n, -1)) <= helpers.REL_TOL
