@@ -171,7 +171,8 @@ def run_b200(args):
     tn_disc = [syn.disc_pixel_count(cx, cy, r, wl.h, wl.w) for (cx, cy, r, _c) in discs]
     n_expected = bpg * len(discs)
     depth = max(1, args.pipeline_depth)
-    pipe = PoseRecoveryPipeline(depth, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected))
+    pipe = PoseRecoveryPipeline(depth, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected),
+                                multi_stream=not args.single_stream)
     eng = pipe.engines[0]
     idxs = torch.zeros((eng.max_instances, hn, 2), dtype=torch.int32)
     idxs[:n_expected] = syn.presampled_idxs(tn_disc * bpg, hn, seed=1234).reshape(n_expected, hn, 2)
@@ -251,8 +252,9 @@ def run_b200(args):
         step(replay=use_graph)
     for res in pipe.drain():
         check(res)
+    pipe.join()                                                      # every slot stream is inside the timed region
     if gatherer is not None:
-        torch.cuda.current_stream().wait_stream(gatherer.stream)     # the last all-gathers are inside the timed region
+        torch.cuda.current_stream().wait_stream(gatherer.stream)     # ... and so are the last all-gathers
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -267,6 +269,7 @@ def run_b200(args):
         step(step_events[k])
     for res in pipe.drain():
         check(res)
+    pipe.join()
     i_end.record()
     torch.cuda.synchronize()
     instrumented_ms_per_step = i_start.elapsed_time(i_end) / args.steps
@@ -384,7 +387,8 @@ def run_b200(args):
             "config": {"workload": wl.name, "frames_per_gpu": bpg, "global_batch": world * bpg, "hypotheses": hn,
                        "instances_per_frame": len(discs), "parallelism": f"image-sharded x{world}",
                        "l2": "inputs (2.6 GB of head maps per GPU) are larger than the 126 MB L2; no flush needed",
-                       "arith": "IEEE (un-contracted) voting arithmetic", "timed": f"{nk} kernels + D2H read of N per step, {depth} steps in flight"
+                       "arith": "IEEE (un-contracted) voting arithmetic", "timed": f"{nk} kernels (one CUDA graph) + D2H read of N per step; {depth} steps in flight"
+                                + ("" if args.single_stream else ", one stream each (kernels of different batches overlap)")
                                 + (" + NCCL all-gather of pose tables" if world > 1 else "")},
             "roofline": roof_argmax if kernel_names[dominant] != "k_gather" else roof_gather,
             "roofline_fp32_voting": roof_vote,
@@ -416,7 +420,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="frames per GPU (default: the workload's batch, 32 for cfg2)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference pass (bounded sample)")
-    ap.add_argument("--pipeline-depth", type=int, default=2, help="batches in flight (1 = wait for N after every step)")
+    ap.add_argument("--pipeline-depth", type=int, default=4, help="batches in flight (1 = wait for N after every step)")
+    ap.add_argument("--single-stream", action="store_true", help="all pipeline slots on one stream (no cross-batch overlap)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches in the timed loop instead of CUDA-graph replay")
     ap.add_argument("--e2e-mode", default="zerocopy", choices=["zerocopy", "copy"])

@@ -8,6 +8,7 @@
 //   lib/gpu_tensor_funcs.py:204-253, 306-326                         translation / rotation / RT
 #include "fpc_internal.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -703,6 +704,9 @@ static int launch_vote_t(const Workspace &ws, const PathParams &pp, const float2
         FPC_CUDA_TRY(cudaFuncSetAttribute(k_vote<ARITH, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vote<ARITH, PACKED>, VT, smem) != cudaSuccess || n < 1) n = 2;
+        // FPC_VOTE_BLOCKS_PER_SM caps the persistent grid (leaves room for kernels of another stream to co-reside)
+        const char *e = getenv("FPC_VOTE_BLOCKS_PER_SM");
+        if (e && atoi(e) >= 1) n = std::min(n, atoi(e));
         blocks_per_sm = n;
     }
     const VoteConsts vc = vote_consts(pp);

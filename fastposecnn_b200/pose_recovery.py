@@ -201,12 +201,15 @@ def table_to_agg(table: torch.Tensor, n: int, sample_offset: int = 0) -> Dict[st
 
 
 class PoseRecoveryPipeline:
-    """``depth`` engines used round-robin on one stream: batch k+1 is enqueued before the host waits for
-    batch k's instance count, so the GPU never idles on the host round trip.  Every batch still performs its
-    own device->host read; results of the last ``depth`` batches stay valid (each engine owns its tables)."""
+    """``depth`` engines used round-robin, each on its OWN stream: batch k+1 is enqueued before the host waits for
+    batch k's instance count, and kernels of different batches overlap on the device -- the HBM-bound arg-max / gather
+    of one batch run next to the FP32-bound vote kernel of another.  Every batch still performs its own device->host
+    read; results of the last ``depth`` batches stay valid (each engine owns its tables)."""
 
-    def __init__(self, depth: int, *engine_args, **engine_kw):
+    def __init__(self, depth: int, *engine_args, multi_stream: bool = True, **engine_kw):
         self.engines = [PoseRecoveryEngine(*engine_args, **engine_kw) for _ in range(depth)]
+        dev = self.engines[0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)] if multi_stream else [None] * depth
         self._k = 0
         self._pending = []
 
@@ -218,17 +221,22 @@ class PoseRecoveryPipeline:
                replay: bool = False, before_launch=None):
         """Enqueue one batch (``replay=True``: re-issue the captured graph of this slot's engine).  Returns
         (engine, N) of the OLDEST in-flight batch once ``depth`` are in flight, else None."""
-        eng = self.engines[self._k % len(self.engines)]
+        slot = self._k % len(self.engines)
+        eng, stream = self.engines[slot], self.streams[slot]
         self._k += 1
-        if before_launch is not None:
-            before_launch(eng)
-        if replay:
-            eng.replay()
-        else:
-            eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u, stage_events=stage_events)
-        if after_launch is not None:
-            after_launch(eng)
-        eng.enqueue_fetch()
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(eng.device))      # inputs produced on the caller's stream
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        with ctx:
+            if before_launch is not None:
+                before_launch(eng)
+            if replay:
+                eng.replay()
+            else:
+                eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u, stage_events=stage_events)
+            if after_launch is not None:
+                after_launch(eng)
+            eng.enqueue_fetch()
         self._pending.append(eng)
         if len(self._pending) >= len(self.engines):
             old = self._pending.pop(0)
@@ -239,6 +247,20 @@ class PoseRecoveryPipeline:
         out = [(e, e.wait_count()) for e in self._pending]
         self._pending = []
         return out
+
+    def join(self) -> None:
+        """Makes the caller's current stream wait for everything enqueued on the slot streams."""
+        for s in self.streams:
+            if s is not None:
+                torch.cuda.current_stream(self.engines[0].device).wait_stream(s)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 _engines: Dict[tuple, PoseRecoveryEngine] = {}
