@@ -260,16 +260,22 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
-    # ---- same K steps again, instrumented: the library records a CUDA event between every two kernels
-    #      (eager launches; the 16 event records per step cost ~15 %, so this pass only attributes time to kernels)
+    # ---- same K steps again, instrumented: serial (one stream, eager launches), the library records a CUDA event
+    #      between every two kernels.  The 16 event records per step and the missing cross-batch overlap make this pass
+    #      slower than the headline loop; it only attributes time to kernels, each measured running alone.
+    pipe_i = PoseRecoveryPipeline(2, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected),
+                                  multi_stream=False)
+    for _ in range(3):
+        check(pipe_i.submit(logits, inv_k, idxs=idxs))
+    for res in pipe_i.drain():
+        check(res)
     torch.cuda.synchronize()
     i_start, i_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     i_start.record()
     for k in range(args.steps):
-        step(step_events[k])
-    for res in pipe.drain():
+        check(pipe_i.submit(logits, inv_k, idxs=idxs, stage_events=step_events[k]))
+    for res in pipe_i.drain():
         check(res)
-    pipe.join()
     i_end.record()
     torch.cuda.synchronize()
     instrumented_ms_per_step = i_start.elapsed_time(i_end) / args.steps
@@ -396,8 +402,9 @@ def run_b200(args):
             "roofline_aggregation_total": roof_agg,
             "dominant_kernel": kernel_names[dominant],
             "kernel_ms": {kernel_names[k]: round(kernel_ms[k], 5) for k in range(nk)},
-            "kernel_ms_note": "per-kernel CUDA-event times from an instrumented repeat of the same K steps "
-                              f"({instrumented_ms_per_step:.4f} ms/step with the 16 event records; the headline loop has none)",
+            "kernel_ms_note": "per-kernel CUDA-event times from an instrumented, serial repeat of the same K steps "
+                              f"({instrumented_ms_per_step:.4f} ms/step: one stream, eager launches, 16 event records per "
+                              "step; the headline loop replays graphs on one stream per in-flight batch)",
             "cuda_graph": use_graph,
             "fp32_peak_tflops_measured": fp32_peak_tflops,
             "cpu_baseline": cpu,
