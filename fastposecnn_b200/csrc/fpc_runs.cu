@@ -164,13 +164,28 @@ __global__ void __launch_bounds__(256) k_emit_runs(const uint8_t *__restrict__ c
             }
         }
     }
+    const bool row_start = (x0 == 0) || (x0 + 3 >= w);
+    // all-background tile (most of the image): no run starts or ends here; only the row index needs this tile's base
+    if (!__syncthreads_or(fgb)) {
+        if (p < P) {
+            const int base = tile_base[blockIdx.x];
+            if (row_start) {
+                int x = x0;
+                for (int j = 0; j < 4; ++j) {
+                    if (p + j < P && x == 0) RT.rowrun[(p + j) / w] = base;
+                    if (++x == w) x = 0;
+                }
+            }
+            if (p + 4 >= P) RT.rowrun[P / w] = tile_base[gridDim.x];
+        }
+        return;
+    }
     const int mine = __popc(stb);
     const int inc = warp_incl_scan(mine, lane);
     if (lane == 31) s_w[wid] = inc;
     __syncthreads();
     if (p >= P) return;
     // only threads that start/end a run or own the first pixel of an image row have anything to write
-    const bool row_start = (x0 == 0) || (x0 + 3 >= w);
     if (!(stb | enb) && !row_start && p + 4 < P) return;
     int before = tile_base[blockIdx.x] + inc - mine;           // run starts before my first pixel
 #pragma unroll
