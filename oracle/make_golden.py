@@ -56,7 +56,29 @@ def main():
         print(name, "N =", agg["class_ids"].shape[0], "centres", agg["xy"].tolist())
 
 
+def matching_main():
+    """tests/golden/matching_*.npz: (preds, gts) -> the reference's own batchwise_get_2d_iou / batchwise_find_matches
+    (lib/matching.py:226-325) outputs.  Masks are stored as uint8 (they are 0/1), everything else as produced."""
+    import helpers
+    ref = ref_import.load()
+    for name in helpers.MATCHING_SCENES:
+        preds, gts = helpers.matching_scene(name)
+        out = {}
+        for side, d in (("preds", preds), ("gts", gts)):
+            for k, v in d.items():
+                out[f"{side}__{k}"] = v.numpy().astype(np.uint8) if k == "instance_masks" else v.numpy()
+        out["iou"] = ref.gtf.batchwise_get_2d_iou(gts["instance_masks"], preds["instance_masks"]).numpy()
+        m = ref.mg.batchwise_find_matches(preds, gts)
+        out["has_matches"] = np.array(m is not None)
+        if m is not None:
+            for k, v in m.items():
+                out[f"matches__{k}"] = v.numpy().astype(np.uint8) if k == "instance_masks" else v.numpy()
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"matching_{name}.npz"), **out)
+        print("matching", name, "M =", 0 if m is None else m["class_ids"].shape[0])
+
+
 if __name__ == "__main__":
     if not ref_import.available():
         raise SystemExit("reference sources not found; golden fixtures can only be regenerated in the build container")
     main()
+    matching_main()

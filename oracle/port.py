@@ -346,3 +346,122 @@ def pose_recover(logits, inv_intrinsics, round_hyp_num: int, num_of_classes: Opt
     agg = hough_voting(agg, round_hyp_num, **vote_kwargs)
     agg = samplewise_get_RT(agg, inv_intrinsics)
     return cat, agg
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ground-truth <-> prediction matching (lib/matching.py, lib/gpu_tensor_funcs.py:380-409)
+# ---------------------------------------------------------------------------------------------------------------------
+
+# lib/matching.py:29-35 -- the keys stack_and_store_data() stacks (the longer local list at :243-250 is never used)
+MATCH_STACK_KEYS = ("instance_masks", "quaternion", "R", "scales", "xy", "z", "T", "RT")
+
+
+def torch_get_2d_iou(t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:380-384: |A and B| / |A or B| of two masks (non-zero = set), one float32 scalar."""
+    a, b = (t1 != 0), (t2 != 0)
+    return torch.true_divide((a & b).sum(), (a | b).sum())
+
+
+def batchwise_get_2d_iou(masks1: torch.Tensor, masks2: torch.Tensor) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:386-409: IoU of every mask of ``masks1 [n1,h,w]`` with every mask of
+    ``masks2 [n2,h,w]`` -> ``[n1,n2]`` float32.  The reference expands both to ``[n1,n2,h,w]`` and sums
+    ``logical_and`` / ``logical_or`` as int64; here the same integers come from one integer matrix
+    product (|A and B|) and inclusion-exclusion (|A or B| = |A| + |B| - |A and B|).  int64 / int64 is torch's true
+    division: both sides converted to float32, IEEE divide, 0/0 = NaN."""
+    a = (masks1 != 0).reshape(masks1.shape[0], -1).to(torch.int64)
+    b = (masks2 != 0).reshape(masks2.shape[0], -1).to(torch.int64)
+    inter = a @ b.t()
+    union = a.sum(dim=1, keepdim=True) + b.sum(dim=1).unsqueeze(0) - inter
+    return inter / union
+
+
+def match_pairs(gt_class: torch.Tensor, pred_class: torch.Tensor, iou: torch.Tensor):
+    """The pairing rule of lib/matching.py:253-296 for all classes at once.  Returns ``(best_pred [n_gt] (-1 = no
+    match), order [M] gt indices in the reference's output order)``: for each ground-truth instance the FIRST
+    prediction of the same class (any frame -- the reference never compares sample ids) with the largest IoU, kept
+    only if that IoU > 0; output order = ascending class id (torch.unique, :253), then ascending gt index."""
+    n_gt = gt_class.shape[0]
+    best = torch.full((n_gt,), -1, dtype=torch.int64)
+    for i in range(n_gt):
+        best_v = 0.0
+        for j in range(pred_class.shape[0]):
+            if int(pred_class[j]) != int(gt_class[i]):
+                continue
+            v = float(iou[i, j])
+            if v > best_v:            # strict: first maximum wins; NaN (0/0) never wins and never validates
+                best_v, best[i] = v, j
+    keep = [i for i in range(n_gt) if best[i] >= 0]
+    keep.sort(key=lambda i: (int(gt_class[i]), i))
+    return best, torch.tensor(keep, dtype=torch.int64)
+
+
+def batchwise_find_matches(preds, gts):
+    """lib/matching.py:226-325.  ``None`` when either side is empty/None, when there are no predictions (:233-234)
+    or when nothing matches (:318-319); else a dict with ``sample_ids / class_ids / symmetric_ids [M]`` taken from
+    the ground truth and, for every key of ``gts`` in MATCH_STACK_KEYS, ``[2, M, ...]`` = (gt rows, matched pred
+    rows)."""
+    if not preds or not gts:
+        return None
+    if preds["class_ids"].shape[0] == 0:
+        return None
+    iou = batchwise_get_2d_iou(gts["instance_masks"], preds["instance_masks"])
+    best, order = match_pairs(gts["class_ids"], preds["class_ids"], iou)
+    if order.numel() == 0:
+        return None
+    out = {"sample_ids": gts["sample_ids"][order], "class_ids": gts["class_ids"][order],
+           "symmetric_ids": gts["symmetric_ids"][order]}
+    for key in gts.keys():
+        if key in MATCH_STACK_KEYS:
+            out[key] = torch.stack((gts[key][order], preds[key][best[order]]))
+    return out
+
+
+def standard_pred_row(gts, key: str) -> torch.Tensor:
+    """lib/matching.py:184-207: the stand-in prediction for an unmatched ground truth -- zeros with the shape of
+    one gt row, except quaternion = (1,0,0,0), RT = eye(4), z[0] = 1000."""
+    row = torch.zeros_like(gts[key][0])
+    if key == "quaternion":
+        row[0] = 1
+    elif key == "RT":
+        row = torch.eye(4, dtype=gts[key].dtype)
+    elif key == "z":
+        row[0] = 1000
+    return row
+
+
+def batchwise_find_matches2(preds, gts):
+    """lib/matching.py:64-182, the variant that fills unmatched ground truths with the standard prediction.
+    Per class (ascending): matched gts first, then the unmatched ones paired with standard rows.  One quirk of the
+    reference is kept on purpose: for the unmatched rows of a class that HAS predictions it indexes ``gts`` with the
+    class-LOCAL positions (:166-172 pass ``invalid_gt_ids``, not ``gts_class_instances[invalid_gt_ids]``)."""
+    iou = batchwise_get_2d_iou(gts["instance_masks"], preds["instance_masks"]) if preds["class_ids"].shape[0] else None
+    gt_rows, pred_rows, meta_rows = [], [], []          # pred_rows: -1 = standard prediction
+    for c in sorted(set(int(v) for v in gts["class_ids"])):
+        members = [i for i in range(gts["class_ids"].shape[0]) if int(gts["class_ids"][i]) == c]
+        cand = [j for j in range(preds["class_ids"].shape[0]) if int(preds["class_ids"][j]) == c]
+        if not cand:
+            for i in members:
+                gt_rows.append(i); pred_rows.append(-1); meta_rows.append((i, c))
+            continue
+        hits, misses = [], []
+        for local, i in enumerate(members):
+            best_v, best_j = 0.0, -1
+            for j in cand:
+                v = float(iou[i, j])
+                if v > best_v:
+                    best_v, best_j = v, j
+            (hits if best_j >= 0 else misses).append((local, i, best_j))
+        for local, i, j in hits:
+            gt_rows.append(i); pred_rows.append(j); meta_rows.append((i, c))
+        for local, i, j in misses:
+            gt_rows.append(local); pred_rows.append(-1); meta_rows.append((i, c))     # the quirk: gts[local]
+    meta_idx = torch.tensor([m[0] for m in meta_rows], dtype=torch.int64)
+    out = {"sample_ids": gts["sample_ids"][meta_idx], "symmetric_ids": gts["symmetric_ids"][meta_idx],
+           "class_ids": torch.tensor([m[1] for m in meta_rows], dtype=gts["class_ids"].dtype)}
+    g_idx = torch.tensor(gt_rows, dtype=torch.int64)
+    for key in gts.keys():
+        if key in MATCH_STACK_KEYS:
+            std = standard_pred_row(gts, key)
+            p = torch.stack([preds[key][j] if j >= 0 else std for j in pred_rows])
+            out[key] = torch.stack((gts[key][g_idx], p))
+    return out

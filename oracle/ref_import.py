@@ -41,7 +41,7 @@ _loaded = None
 
 
 def load():
-    """Returns a namespace with the reference modules: gtf, agg, hv, rvg."""
+    """Returns a namespace with the reference modules: gtf, agg, hv, rvg, mg (matching)."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -83,6 +83,7 @@ def load():
     ns.rvg = importlib.import_module("ransac_voting_gpu_layer.ransac_voting_gpu")
     ns.hv = importlib.import_module("hough_voting")
     ns.agg = importlib.import_module("aggregation_layer")
+    ns.mg = importlib.import_module("matching")
     _loaded = ns
     return ns
 

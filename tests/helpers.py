@@ -53,3 +53,46 @@ def run_oracle(logits, hn, seed=1234, num_classes=None, **kw):
 
 def oracle_tns(agg):
     return [int(v) for v in agg["instance_masks"].sum(dim=(-2, -1)).tolist()]
+
+
+def matching_scene(name="shifted", h=96, w=128, hn=16):
+    """(preds, gts) AggData pairs on CPU for the matching tests: both sides come from the oracle path on two renders of
+    related scenes (gt discs shifted / missing / re-classed / duplicated across frames), so every stacked key exists."""
+    if name == "shifted":
+        pred_frames = [[(30, 30, 14, 1), (90, 40, 18, 3), (60, 75, 12, 6)], [(40, 50, 20, 2), (100, 30, 12, 1)], [(64, 48, 22, 3)]]
+        gt_frames = [[(33, 31, 14, 1), (88, 44, 17, 3), (20, 80, 8, 6)], [(42, 50, 19, 2), (100, 70, 12, 1)], [(60, 50, 22, 3), (15, 15, 9, 5)]]
+    elif name == "cross_frame_ties":
+        # the same class at the same place in every frame: every gt ties with several predictions -> first one wins
+        pred_frames = [[(40, 40, 15, 2), (90, 60, 12, 4)] for _ in range(3)]
+        gt_frames = [[(40, 40, 15, 2), (90, 60, 12, 4)] for _ in range(2)]
+    elif name == "no_overlap":
+        pred_frames = [[(30, 30, 10, 1)], [(90, 60, 10, 2)]]
+        gt_frames = [[(90, 60, 10, 1)], [(30, 30, 10, 2)]]
+    elif name == "class_without_preds":
+        pred_frames = [[(30, 30, 12, 1), (80, 30, 12, 1)], [(60, 60, 15, 1)]]
+        gt_frames = [[(31, 30, 12, 1), (80, 31, 12, 4)], [(100, 20, 9, 1), (60, 61, 15, 1)]]
+    else:
+        raise KeyError(name)
+    out = []
+    for seed, frames in ((21, pred_frames), (22, gt_frames)):
+        logits = syn.render_heads(frames, h, w, seed=seed)
+        _, agg, _ = run_oracle(logits, hn, seed=seed)
+        agg = {k: v for k, v in agg.items()}
+        agg["symmetric_ids"] = agg["class_ids"] % 2
+        out.append(agg)
+    return out[0], out[1]
+
+
+MATCHING_SCENES = ("shifted", "cross_frame_ties", "no_overlap", "class_without_preds")
+
+
+def load_matching_golden(name):
+    """tests/golden/matching_<name>.npz (oracle/make_golden.py:matching_main) -> (preds, gts, iou, matches or None)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"matching_{name}.npz"))
+    sides = {"preds": {}, "gts": {}, "matches": {}}
+    for key in z.files:
+        if "__" in key:
+            side, k = key.split("__", 1)
+            t = torch.from_numpy(z[key])
+            sides[side][k] = t.float() if k == "instance_masks" else t
+    return sides["preds"], sides["gts"], torch.from_numpy(z["iou"]), (sides["matches"] if bool(z["has_matches"]) else None)

@@ -12,7 +12,7 @@ import torch
 import helpers
 from helpers import port, syn
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "g_*.npz")))
 
 
 def load_golden(path):
