@@ -3,7 +3,8 @@ path: per-pixel head outputs -> per-instance 6D pose and size.
 
 Drop-in names (same call signatures and tensor layouts as the reference):
     AggregationLayer, HoughVotingLayer, ransac_voting_layer_v3, ransac_voting_layer,
-    class_compress, class_compression, normalize, samplewise_get_RT, batchwise_get_RT, Model
+    class_compress, class_compression, normalize, samplewise_get_RT, batchwise_get_RT, Model,
+    matching.batchwise_find_matches / batchwise_find_matches2, batchwise_get_2d_iou, torch_get_2d_iou
 Fused fast entry:
     pose_recover(logits, inv_intrinsics, hn, idxs=None) / PoseRecoveryEngine
 
@@ -13,8 +14,10 @@ non-CUDA tensor raises.
 """
 from . import synthetic  # noqa: F401  (pure torch, importable without the native library)
 from .aggregation_layer import AggregationLayer  # noqa: F401
-from .gpu_tensor_funcs import (batchwise_get_RT, class_compress, class_compression, normalize,  # noqa: F401
-                               quats_2_rotation_matrix, samplewise_get_RT)
+from . import matching  # noqa: F401
+from .gpu_tensor_funcs import (batchwise_get_2d_iou, batchwise_get_RT, class_compress, class_compression,  # noqa: F401
+                               normalize, quats_2_rotation_matrix, samplewise_get_RT, torch_get_2d_iou)
+from .matching import batchwise_find_matches, batchwise_find_matches2  # noqa: F401
 from .hough_voting import HoughVotingLayer  # noqa: F401
 from .model import Model, PoseRecovery  # noqa: F401
 from .pose_recovery import PoseRecoveryEngine, pose_recover  # noqa: F401

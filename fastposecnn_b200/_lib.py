@@ -29,7 +29,10 @@ EXPORTS = (
     "fpc_normalize", "fpc_class_compress", "fpc_get_rt", "fpc_pose_recover_workspace_bytes",
     "fpc_pose_recover", "fpc_pose_recover_num_launches", "fpc_pose_recover_kernel_name", "fpc_bench_fp32_fma",
     "fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances",
+    "fpc_pack_masks", "fpc_pack_labels", "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances",
 )
+MASK_META = 8
+MASK_F32, MASK_U8 = 0, 1
 
 _vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 
@@ -82,7 +85,13 @@ def lib() -> ctypes.CDLL:
     L.fpc_aggregate.argtypes = [ctypes.POINTER(RecoverArgs), _vp]
     L.fpc_vote_dense.argtypes = [ctypes.POINTER(RecoverArgs), _vp, _vp, _i, _i, _vp, _ll, _ll, _ll, _ll, _i]
     L.fpc_materialize_instances.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]
-    for name in ("fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances"):
+    L.fpc_pack_masks.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp]
+    L.fpc_pack_labels.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp]
+    L.fpc_mask_iou.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]
+    L.fpc_match_instances.argtypes = [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+    L.fpc_paint_instances.argtypes = [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]
+    for name in ("fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances", "fpc_pack_masks", "fpc_pack_labels",
+                 "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances"):
         getattr(L, name).restype = _i
     for name in ("fpc_generate_hypothesis", "fpc_voting_for_hypothesis", "fpc_normalize", "fpc_class_compress",
                  "fpc_get_rt", "fpc_pose_recover"):

@@ -111,3 +111,16 @@ def quats_2_rotation_matrix(q: torch.Tensor) -> torch.Tensor:
     eye = torch.eye(3, dtype=torch.float32, device=q.device)
     R, _, _ = batchwise_get_RT(q, zeros2, ones, eye)
     return R
+
+
+def batchwise_get_2d_iou(batch_masks1: torch.Tensor, batch_masks2: torch.Tensor) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:386-409 -- IoU of every ``[n1,h,w]`` mask with every ``[n2,h,w]`` mask -> ``[n1,n2]``
+    float32 (0/0 = NaN).  Each mask is read once and bit-packed; pairs cost popc(a & b) over the overlap of their
+    bounding boxes instead of the reference's ``[n1,n2,h,w]`` logical volumes; values are bit-identical."""
+    from .matching import mask_iou, pack_masks
+    return mask_iou(pack_masks(batch_masks1), pack_masks(batch_masks2))
+
+
+def torch_get_2d_iou(tensor1: torch.Tensor, tensor2: torch.Tensor) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:380-384 -- IoU of two ``[h,w]`` masks, a 0-d float32 tensor."""
+    return batchwise_get_2d_iou(tensor1.reshape(1, *tensor1.shape[-2:]), tensor2.reshape(1, *tensor2.shape[-2:]))[0, 0]

@@ -206,6 +206,44 @@ FPC_API int fpc_vote_dense(const fpc_recover_args *args, const float *fmask, con
 FPC_API int fpc_materialize_instances(const int32_t *labels, const float *pose_table, const float *xy_cat,
                                       float *instance_masks, float *xy_mask, int n, int h, int w, void *stream);
 
+/* ---- ground-truth <-> prediction matching ---------------------------------------
+ * Replaces lib/gpu_tensor_funcs.py:386-409 batchwise_get_2d_iou (expand both mask sets to [n1,n2,h,w], sum
+ * logical_and / logical_or) and the per-class loop of lib/matching.py:253-296 batchwise_find_matches.
+ *
+ * A mask set is held as bit planes: bits [n, h, ceil(w/32)] u32 (bit x%32 of word x/32 = pixel x set, padding bits 0)
+ * plus meta [n, FPC_MASK_META] i32 = {pixel count, ymin, ymax, first word column, last word column, 0, 0, 0}
+ * (empty mask: count 0, ymin > ymax).  Caller-allocated, like everything else. */
+enum { FPC_MASK_META = 8 };
+enum { FPC_MASK_F32 = 0, FPC_MASK_U8 = 1 };
+
+/* Dense masks [n,h,w] (elem = FPC_MASK_F32 or FPC_MASK_U8/bool; non-zero = set, the reference's logical_and rule)
+ * -> bit planes + meta.  Reads every mask element exactly once. */
+FPC_API int fpc_pack_masks(const void *masks, int elem, int n, int h, int w, uint32_t *bits, int32_t *meta, void *stream);
+
+/* Label volume [b,h,w] i32 (0 = background, k = instance k-1; what fpc_pose_recover writes to args->labels)
+ * -> bit planes + meta of instances 0..n-1, without ever building dense instance masks. */
+FPC_API int fpc_pack_labels(const int32_t *labels, int b, int h, int w, int n, uint32_t *bits, int32_t *meta, void *stream);
+
+/* iou [na,nb] f32 = |A_i and B_j| / |A_i or B_j| as float(int) / float(int), 0/0 = NaN: bit-identical to the
+ * reference's int64 true division (gpu_tensor_funcs.py:396-407). */
+FPC_API int fpc_mask_iou(const uint32_t *bits_a, const int32_t *meta_a, int na, const uint32_t *bits_b, const int32_t *meta_b,
+                         int nb, int h, int w, float *iou, void *stream);
+
+/* The pairing of lib/matching.py:253-296 for all classes in one call.  For every ground-truth mask i:
+ * best_pred[i] = the FIRST prediction of the same class (any frame) with the largest IoU, or -1 if that IoU is not > 0;
+ * best_iou[i] = that IoU (0 if none).  pairs [ng,2] i32 receives (gt index, pred index) of the *n_matches matched
+ * ground truths in the reference's output order: class id ascending, then gt index ascending.  class ids are int64
+ * (torch long), as the reference stores them. */
+FPC_API int fpc_match_instances(const uint32_t *bits_g, const int32_t *meta_g, const int64_t *class_g, int ng,
+                                const uint32_t *bits_p, const int32_t *meta_p, const int64_t *class_p, int np, int h, int w,
+                                int32_t *best_pred, float *best_iou, int32_t *pairs, int32_t *n_matches, void *stream);
+
+/* out [m,h,w] f32 0/1: row k = the mask of instance inst_of[k] in frame frame_of[k] of the label volume [b,h,w]
+ * (labels == inst_of[k] + 1).  The stacked `instance_masks` of matched predictions (lib/matching.py:40-58) without ever
+ * holding all N dense masks. */
+FPC_API int fpc_paint_instances(const int32_t *labels, int b, int h, int w, const int64_t *frame_of, const int64_t *inst_of, int m,
+                                float *out, void *stream);
+
 /* Number of kernels fpc_pose_recover launches per call (for launch accounting). */
 FPC_API int fpc_pose_recover_num_launches(void);
 

@@ -49,6 +49,11 @@ def test_error_codes_not_exit():
     assert L.fpc_pose_recover(None) == _lib.FPC_EINVAL
     with pytest.raises(RuntimeError, match="libfpc_b200 error -1"):
         _lib.check(L.fpc_pose_recover(None))
+    assert L.fpc_pack_masks(None, 0, -1, 4, 4, None, None, None) == _lib.FPC_EINVAL
+    assert L.fpc_pack_masks(None, 0, 0, 4, 4, None, None, None) == _lib.FPC_OK                       # no masks: nothing to do
+    assert L.fpc_pack_masks(None, 0, 3, 4, 4, None, None, None) == _lib.FPC_EINVAL
+    assert L.fpc_mask_iou(None, None, 0, None, None, 5, 4, 4, None, None) == _lib.FPC_OK
+    assert L.fpc_match_instances(None, None, None, 2, None, None, None, 2, 4, 4, None, None, None, None, None) == _lib.FPC_EINVAL
     assert L.fpc_pose_recover_num_launches() == 15
     assert L.fpc_pose_recover_kernel_name(13) == b"k_vote"
 
@@ -62,6 +67,11 @@ def test_no_cpu_fallback():
         fp.ransac_voting_layer_v3(torch.ones(1, 8, 8), torch.randn(1, 8, 8, 1, 2), 16)
     with pytest.raises(RuntimeError, match="CUDA"):
         fp.PoseRecoveryEngine(1, 8, 8, 7, 16, "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fp.batchwise_get_2d_iou(torch.ones(2, 8, 8), torch.ones(3, 8, 8))
+    agg = {"class_ids": torch.ones(1, dtype=torch.int64), "instance_masks": torch.ones(1, 8, 8)}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fp.batchwise_find_matches(agg, agg)
     logits = fp.synthetic.render_heads([[(4, 4, 2, 1)]], 8, 8)
     with pytest.raises(RuntimeError):
         fp.class_compression(logits, 7)
