@@ -29,7 +29,7 @@ EXPORTS = (
     "fpc_normalize", "fpc_class_compress", "fpc_get_rt", "fpc_pose_recover_workspace_bytes",
     "fpc_pose_recover", "fpc_pose_recover_num_launches", "fpc_pose_recover_kernel_name", "fpc_bench_fp32_fma",
     "fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances",
-    "fpc_pack_masks", "fpc_pack_labels", "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances",
+    "fpc_pack_masks", "fpc_pack_labels", "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances", "fpc_upsample_bilinear",
 )
 MASK_META = 8
 MASK_F32, MASK_U8 = 0, 1
@@ -51,6 +51,7 @@ class RecoverArgs(ctypes.Structure):
         ("hyp_out", _vp), ("vote_counts_out", _vp),
         ("workspace", _vp), ("workspace_bytes", ctypes.c_size_t), ("stream", _vp),
         ("stage_events", ctypes.POINTER(_vp)), ("num_stage_events", ctypes.c_int32),
+        ("upsample", ctypes.c_int32),
     ]
 
 
@@ -90,6 +91,8 @@ def lib() -> ctypes.CDLL:
     L.fpc_mask_iou.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]
     L.fpc_match_instances.argtypes = [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
     L.fpc_paint_instances.argtypes = [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]
+    L.fpc_upsample_bilinear.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
+    L.fpc_upsample_bilinear.restype = _i
     for name in ("fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances", "fpc_pack_masks", "fpc_pack_labels",
                  "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances"):
         getattr(L, name).restype = _i

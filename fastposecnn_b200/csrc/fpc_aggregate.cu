@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counte
 // MODE 0: raw head maps, class selected per pixel, q/xy normalised here (fused path)
 // MODE 1: class-compressed CategoricalData [b,4|3|2,h,w] (AggregationLayer drop-in)
 // MODE 2: voting records only, directions from a strided `vertex[N,h,w,vn,2]` view (ransac_voting_layer* drop-in)
+// MODE 3: like 0, but the head maps are LOW RESOLUTION and every value is their x S bilinear up-sampling evaluated
+//         here (head-epilogue fusion: 4 cached taps + 6 FP32 operations per channel, foreground pixels only)
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ cls,
                                                 InstTables T, RowTables R, const int *__restrict__ counters,
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
         const int y = pix0 / pp.w, x0 = pix0 - y * pp.w;
         const float thr = sub ? (float)pp.max_num / (float)T.count[i] : 2.f;
         const int rec0 = (want_rec && votes) ? T.pxoff[i] + d.w : 0;
+        LerpCoord LY{0, 0, 0.f, 0.f};
+        if (MODE == 3) LY = lerp_coord(y, pp.up.sy, pp.up.hl);
         int running = 0, cmin = INT_MAX;
         float acc[8];
 #pragma unroll
@@ -79,17 +83,36 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
                     const float *v = F.xy + (long long)(img / F.div) * F.sN + (long long)y * F.sH + (long long)(x0 + kx) * F.sW;
                     vx = v[0];
                     vy = v[F.s2];
-                } else if (MODE == 0) {
+                } else if (MODE == 0 || MODE == 3) {
                     const int cp = (int)cls[p];
                     cmin = min(cmin, cp);
-                    const size_t koff = (size_t)(cp - 1) * hw;            // predicted class of THIS pixel (class_compress is per pixel)
-                    const float *q = F.quaternion + (size_t)img * 4 * K * hw + 4 * koff + pix;
-                    const float *s = F.scales + (size_t)img * 3 * K * hw + 3 * koff + pix;
-                    const float *v = F.xy + (size_t)img * 2 * K * hw + 2 * koff + pix;
-                    q0 = __ldcs(q); q1 = __ldcs(q + hw); q2 = __ldcs(q + 2 * hw); q3 = __ldcs(q + 3 * hw);
-                    s0 = __ldcs(s); s1 = __ldcs(s + hw); s2 = __ldcs(s + 2 * hw);
-                    zz = __ldcs(F.z + (size_t)img * K * hw + koff + pix);
-                    vx = __ldcs(v); vy = __ldcs(v + hw);
+                    if (MODE == 0) {
+                        const size_t koff = (size_t)(cp - 1) * hw;            // predicted class of THIS pixel (class_compress is per pixel)
+                        const float *q = F.quaternion + (size_t)img * 4 * K * hw + 4 * koff + pix;
+                        const float *s = F.scales + (size_t)img * 3 * K * hw + 3 * koff + pix;
+                        const float *v = F.xy + (size_t)img * 2 * K * hw + 2 * koff + pix;
+                        q0 = __ldcs(q); q1 = __ldcs(q + hw); q2 = __ldcs(q + 2 * hw); q3 = __ldcs(q + 3 * hw);
+                        s0 = __ldcs(s); s1 = __ldcs(s + hw); s2 = __ldcs(s + 2 * hw);
+                        zz = __ldcs(F.z + (size_t)img * K * hw + koff + pix);
+                        vx = __ldcs(v); vy = __ldcs(v + hw);
+                    } else {
+                        const LerpCoord LX = lerp_coord(x0 + kx, pp.up.sx, pp.up.wl);
+                        const int wl = pp.up.wl;
+                        const size_t lhw = (size_t)pp.up.hl * wl;
+                        const int o00 = LY.i0 * wl + LX.i0, o01 = LY.i0 * wl + LX.i1, o10 = LY.i1 * wl + LX.i0, o11 = LY.i1 * wl + LX.i1;
+                        auto tap = [&](const float *__restrict__ plane) {
+                            return bilerp(__ldg(plane + o00), __ldg(plane + o01), __ldg(plane + o10), __ldg(plane + o11),
+                                          LX.w0, LX.w1, LY.w0, LY.w1);
+                        };
+                        const size_t kc = (size_t)img * K + (cp - 1);          // (image, predicted class) -> channel group
+                        const float *q = F.quaternion + 4 * kc * lhw;
+                        const float *s = F.scales + 3 * kc * lhw;
+                        const float *v = F.xy + 2 * kc * lhw;
+                        q0 = tap(q); q1 = tap(q + lhw); q2 = tap(q + 2 * lhw); q3 = tap(q + 3 * lhw);
+                        s0 = tap(s); s1 = tap(s + lhw); s2 = tap(s + 2 * lhw);
+                        zz = tap(F.z + kc * lhw);
+                        vx = tap(v); vy = tap(v + lhw);
+                    }
                     // quaternion: only its masked mean is used (1e-4 budget) -> one reciprocal, four multiplies;
                     // direction: feeds the votes -> keep the reference's value / norm with IEEE sqrt and divide
                     const float qq = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
@@ -209,8 +232,10 @@ int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const Fie
         k_gather<0><<<grid, 256, 0, st>>>(ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);
     else if (gather_mode == 1)
         k_gather<1><<<grid, 256, 0, st>>>(ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);
-    else
+    else if (gather_mode == 2)
         k_gather<2><<<grid, 256, 0, st>>>(ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);
+    else
+        k_gather<3><<<grid, 256, 0, st>>>(ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);
     FPC_LAUNCH_CHECK("k_gather");
     return FPC_OK;
 }

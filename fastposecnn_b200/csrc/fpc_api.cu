@@ -198,6 +198,32 @@ static size_t carve(Workspace &ws, void *base, long long P, long long rows_total
     return (c.off + 255) & ~size_t(255);
 }
 
+// nn.UpsamplingBilinear2d(scale_factor=S), align_corners=True, as a stand-alone operator (thread = 4 output pixels when
+// the output width allows it; write-bound: 4 B per output pixel).
+__global__ void __launch_bounds__(256) k_upsample_bilinear(const float *__restrict__ in, float *__restrict__ out, long long total,
+                                                           int h, int w, UpParams up, int px_per_thread) {
+    const long long hw = (long long)h * w;
+    const size_t lhw = (size_t)up.hl * up.wl;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t * px_per_thread < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long p = t * px_per_thread;
+        const long long plane = p / hw;
+        const int pix = (int)(p - plane * hw);
+        const int y = pix / w, x0 = pix - y * w;
+        const LerpCoord Y = lerp_coord(y, up.sy, up.hl);
+        const float *r0 = in + plane * lhw + (size_t)Y.i0 * up.wl, *r1 = in + plane * lhw + (size_t)Y.i1 * up.wl;
+        float v[4];
+        for (int j = 0; j < px_per_thread; ++j) {
+            const LerpCoord X = lerp_coord(x0 + j, up.sx, up.wl);
+            v[j] = bilerp(__ldg(r0 + X.i0), __ldg(r0 + X.i1), __ldg(r1 + X.i0), __ldg(r1 + X.i1), X.w0, X.w1, Y.w0, Y.w1);
+        }
+        if (px_per_thread == 4) __stcs(reinterpret_cast<float4 *>(out + p), make_float4(v[0], v[1], v[2], v[3]));
+        else out[p] = v[0];
+    }
+}
+
+// nn.UpsamplingBilinear2d scale of one axis: static_cast<float>(in - 1) / (out - 1), 0 for a single output (UpSample.h)
+static float up_scale(int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f; }
+
 static int check_sizes(const fpc_recover_args *a) {
     if (!a) return fail(FPC_EINVAL, "args is NULL");
     if (a->b <= 0 || a->h <= 0 || a->w <= 0) return fail(FPC_EINVAL, "b, h, w must be positive (got %d, %d, %d)", a->b, a->h, a->w);
@@ -284,6 +310,20 @@ size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *a) {
     return carve(ws, nullptr, P, (long long)a->b * a->h, a->max_instances, a->hn, a->max_records, a->max_rows, true, true, true) + 256;
 }
 
+int fpc_upsample_bilinear(const float *in, long long planes, int hl, int wl, int scale, float *out, void *stream) {
+    if (planes < 0 || hl <= 0 || wl <= 0 || scale < 1) return fail(FPC_EINVAL, "bad size");
+    if (planes == 0) return FPC_OK;
+    if (!in || !out) return fail(FPC_EINVAL, "NULL pointer");
+    const int h = hl * scale, w = wl * scale;
+    const long long total = planes * h * w;
+    const UpParams up{scale, hl, wl, up_scale(hl, h), up_scale(wl, w)};
+    const int ppt = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 4 : 1;
+    const int grid = (int)std::min<long long>(ceil_div_ll(ceil_div_ll(total, ppt), 256), (long long)sm_count() * 16);
+    k_upsample_bilinear<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, total, h, w, up, ppt);
+    FPC_LAUNCH_CHECK("k_upsample_bilinear");
+    return FPC_OK;
+}
+
 int fpc_pose_recover_num_launches(void) { return 15; }
 
 const char *fpc_pose_recover_kernel_name(int k) {
@@ -322,6 +362,16 @@ static int setup(const fpc_recover_args *a, Workspace &ws, PathParams &pp) {
     pp.inlier_thresh = a->inlier_thresh; pp.min_num = a->min_num; pp.max_num = a->max_num;
     pp.arith = a->arith; pp.seed = a->seed; pp.idxs = a->idxs; pp.select_u = a->select_u;
     pp.refine = 1;
+    pp.up = UpParams{0, a->h, a->w, 0.f, 0.f};
+    return FPC_OK;
+}
+
+
+static int setup_upsample(const fpc_recover_args *a, PathParams &pp) {
+    if (a->upsample <= 1) return FPC_OK;
+    const int s = a->upsample;
+    if (a->h % s || a->w % s) return fail(FPC_EINVAL, "h and w (%d, %d) must be multiples of upsample (%d)", a->h, a->w, s);
+    pp.up = UpParams{s, a->h / s, a->w / s, up_scale(a->h / s, a->h), up_scale(a->w / s, a->w)};
     return FPC_OK;
 }
 
@@ -376,11 +426,14 @@ int fpc_pose_recover(const fpc_recover_args *a) {
     if (!a->mask_logits || !a->quaternion || !a->scales || !a->xy || !a->z || !a->inv_intrinsics)
         return fail(FPC_EINVAL, "NULL input pointer");
 
+    rc = setup_upsample(a, pp);
+    if (rc != FPC_OK) return rc;
     cudaStream_t st = (cudaStream_t)a->stream;
     stage_begin(a->stage_events, a->num_stage_events, st);
     rc = launch_label_and_tables(ws, pp, a->mask_logits, nullptr, st);
     FieldSrc F{a->quaternion, a->scales, a->xy, a->z, 0, 0, 0, 0, 1};
-    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/0, /*want_records=*/true, VOTE_CHUNK, st);
+    if (rc == FPC_OK)
+        rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/pp.up.s > 1 ? 3 : 0, /*want_records=*/true, VOTE_CHUNK, st);
     if (rc == FPC_OK) rc = launch_vote(ws, pp, ws.hyp, ws.votes, st);
     if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, a->inv_intrinsics, a->pose_table, st);
     if (rc == FPC_OK && a->labels) rc = launch_relabel(ws, pp, a->labels, st);

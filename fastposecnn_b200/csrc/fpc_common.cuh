@@ -42,6 +42,36 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // Number of SMs of the current device (cached); grids of persistent kernels are multiples of it.
 int sm_count();
 
+// ---- nn.UpsamplingBilinear2d (align_corners=True), the x S step of smp's SegmentationHead ------------------
+// Source coordinate and weights exactly as ATen computes them (ATen/native/UpSample.h: area_pixel_compute_scale,
+// area_pixel_compute_source_index, guard_index_and_lambda): scale = float(in-1) / float(out-1) (host side),
+// src = scale * dst, i0 = min(floor(src), in-1), w1 = clamp(src - i0, 0, 1), w0 = 1 - w1, i1 = i0 + (i0 < in-1).
+struct UpParams {
+    int s;            // 0/1 = inputs are full resolution
+    int hl, wl;       // low-resolution plane size
+    float sy, sx;     // float(hl-1)/float(h-1), float(wl-1)/float(w-1)
+};
+struct LerpCoord {
+    int i0, i1;
+    float w0, w1;
+};
+__device__ __forceinline__ LerpCoord lerp_coord(int dst, float scale, int in_size) {
+    const float src = __fmul_rn(scale, (float)dst);
+    LerpCoord c;
+    c.i0 = min((int)floorf(src), in_size - 1);
+    c.i1 = c.i0 + (c.i0 < in_size - 1 ? 1 : 0);
+    c.w1 = fminf(fmaxf(__fsub_rn(src, (float)c.i0), 0.f), 1.f);
+    c.w0 = __fsub_rn(1.f, c.w1);
+    return c;
+}
+// Horizontal pair first, then the two rows; each "a*wa + b*wb" is fma(a, wa, b*wb) -- the contraction both ATen's
+// vectorised CPU kernel and nvcc's build of the CUDA kernel end up with (pinned in tests/test_head_epilogue_*.py).
+__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11, float wx0, float wx1, float wy0, float wy1) {
+    const float t0 = __fmaf_rn(v00, wx0, __fmul_rn(v01, wx1));
+    const float t1 = __fmaf_rn(v10, wx0, __fmul_rn(v11, wx1));
+    return __fmaf_rn(t0, wy0, __fmul_rn(t1, wy1));
+}
+
 // ---- reference arithmetic (lib/ransac_voting_gpu_layer/src/ransac_voting_kernel.cu) -----
 // a*b + c*d in the two arithmetic modes of fpc_b200.h.
 template <int ARITH>

@@ -58,6 +58,7 @@ struct PathParams {
     const int *idxs;             // [max_instances,hn,2] or nullptr
     const float *select_u;       // [b,h,w] or nullptr
     int refine;                  // 1: inlier refinement (v3); 0: winning hypothesis as is (v1)
+    UpParams up;                 // head-epilogue fusion: head maps are low resolution, x up.s bilinear on the fly
 };
 
 // Voting records as four SoA planes, instance-major, raster order inside an instance; every instance's range

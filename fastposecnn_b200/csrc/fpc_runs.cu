@@ -91,6 +91,87 @@ __global__ void __launch_bounds__(1024) k_argmax_runs_v1(const float *__restrict
     tile_count(fg && !prev, tile_runs);
 }
 
+// Head-epilogue fusion: the same class map and run-start counts, but the C mask logits of
+// a pixel are the x S bilinear up-sampling (smp SegmentationHead, lib/pose_regressor.py:633-639) of the LOW-RESOLUTION
+// head output, evaluated here -- the [b,C,h,w] logits never exist.  One thread = 4 consecutive output pixels; for
+// S >= 3 they touch at most 3 low-res columns, so a class plane costs 6 cached loads per thread (1/16 of the bytes
+// of the full-resolution kernel at S = 4) and 24 FP32 operations.
+__global__ void __launch_bounds__(256) k_argmax_runs_up4(const float *__restrict__ mask_lr, uint8_t *__restrict__ cls,
+                                                         int *__restrict__ tile_runs, int C, int hw, int w, int P4, UpParams up) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int p = t * 4;
+    int nib = 0, x0 = 0;
+    if (t < P4) {
+        const int bi = p / hw;
+        const int pix = p - bi * hw;
+        const int y = pix / w;
+        x0 = pix - y * w;
+        const LerpCoord Y = lerp_coord(y, up.sy, up.hl);
+        LerpCoord X[4];
+        bool sh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) X[j] = lerp_coord(x0 + j, up.sx, up.wl);
+        const int cA = X[0].i0, cB = min(cA + 1, up.wl - 1), cC = min(cA + 2, up.wl - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh[j] = X[j].i0 != cA;      // pixel j starts one low-res column further right
+        const size_t lhw = (size_t)up.hl * up.wl;
+        const float *r0 = mask_lr + (size_t)bi * C * lhw + (size_t)Y.i0 * up.wl;
+        const float *r1 = mask_lr + (size_t)bi * C * lhw + (size_t)Y.i1 * up.wl;
+        float best[4];
+        int arg[4] = {0, 0, 0, 0};
+        for (int c = 0; c < C; ++c) {
+            const float a0 = __ldg(r0 + cA), b0 = __ldg(r0 + cB), c0 = __ldg(r0 + cC);
+            const float a1 = __ldg(r1 + cA), b1 = __ldg(r1 + cB), c1 = __ldg(r1 + cC);
+            r0 += lhw;
+            r1 += lhw;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v = bilerp(sh[j] ? b0 : a0, sh[j] ? c0 : b0, sh[j] ? b1 : a1, sh[j] ? c1 : b1, X[j].w0, X[j].w1, Y.w0, Y.w1);
+                if (c == 0) best[j] = v;
+                else if (v > best[j]) { best[j] = v; arg[j] = c; }      // strict '>' keeps the first maximum, like torch.argmax
+            }
+        }
+        nib = (arg[0] != 0) | ((arg[1] != 0) << 1) | ((arg[2] != 0) << 2) | ((arg[3] != 0) << 3);
+        *reinterpret_cast<uchar4 *>(cls + p) = make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
+    }
+    int prev_last = __shfl_up_sync(FULL, (nib >> 3) & 1, 1);
+    if (lane == 0 || x0 == 0) prev_last = 0;
+    const int starts = nib & ~((nib << 1) | prev_last);
+    tile_count(__popc(starts & 0xF), tile_runs);
+}
+
+// Scalar variant of the above (any width, any S >= 2): one pixel per thread, 4 taps per class plane.
+__global__ void __launch_bounds__(1024) k_argmax_runs_up1(const float *__restrict__ mask_lr, uint8_t *__restrict__ cls,
+                                                          int *__restrict__ tile_runs, int C, int hw, int w, int P, UpParams up) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int fg = 0, x = 0;
+    if (p < P) {
+        const int bi = p / hw, pix = p - bi * hw;
+        const int y = pix / w;
+        x = pix - y * w;
+        const LerpCoord Y = lerp_coord(y, up.sy, up.hl), X = lerp_coord(x, up.sx, up.wl);
+        const size_t lhw = (size_t)up.hl * up.wl;
+        const float *r0 = mask_lr + (size_t)bi * C * lhw + (size_t)Y.i0 * up.wl;
+        const float *r1 = mask_lr + (size_t)bi * C * lhw + (size_t)Y.i1 * up.wl;
+        float best = 0.f;
+        int arg = 0;
+        for (int c = 0; c < C; ++c) {
+            const float v = bilerp(__ldg(r0 + X.i0), __ldg(r0 + X.i1), __ldg(r1 + X.i0), __ldg(r1 + X.i1), X.w0, X.w1, Y.w0, Y.w1);
+            r0 += lhw;
+            r1 += lhw;
+            if (c == 0) best = v;
+            else if (v > best) { best = v; arg = c; }
+        }
+        cls[p] = (uint8_t)arg;
+        fg = arg != 0;
+    }
+    int prev = __shfl_up_sync(FULL, fg, 1);
+    if (lane == 0 || x == 0) prev = 0;
+    tile_count(fg && !prev, tile_runs);
+}
+
 // Class map from an already categorical mask (AggregationLayer drop-in: cat_mask int64) or from dense problem
 // planes (voting drop-ins: problem j owns plane j; member = fmask != 0, or imask[j / per_src] == match_base + j % per_src).
 // Neighbours can be read directly, so runs are not cut: span = "infinite".
@@ -476,7 +557,16 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
     const int P = pp.P;
     const int ntiles = ceil_div(P, TILE);
     int span;
-    if (mask_logits) {
+    if (mask_logits && pp.up.s > 1) {
+        if (pp.w % 4 == 0 && pp.up.s >= 3 && (reinterpret_cast<uintptr_t>(ws.cls) & 3) == 0) {
+            k_argmax_runs_up4<<<ntiles, 256, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P / 4, pp.up);
+            span = 128;
+        } else {
+            k_argmax_runs_up1<<<ntiles, 1024, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P, pp.up);
+            span = 32;
+        }
+        FPC_LAUNCH_CHECK("k_argmax_runs");
+    } else if (mask_logits) {
         const bool vec_ok = (pp.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mask_logits) & 15) == 0) &&
                             ((reinterpret_cast<uintptr_t>(ws.cls) & 3) == 0);
         if (vec_ok) {

@@ -25,8 +25,13 @@ class PoseRecoveryEngine:
     def __init__(self, b: int, h: int, w: int, num_classes: int, hn: int, device, *, max_instances: Optional[int] = None,
                  max_records: Optional[int] = None, max_rows: Optional[int] = None, inlier_thresh: float = 0.999,
                  min_num: int = 5, max_num: int = 30000, arith: int = _lib.ARITH_IEEE, seed: int = 1234,
-                 want_labels: bool = False):
+                 want_labels: bool = False, upsample: int = 1):
         self.device = torch.device(device)
+        # head-epilogue fusion: inputs are the heads' low-resolution outputs [b,.,h/upsample,w/upsample]; (h, w) stay the
+        # full output resolution every table, mask and coordinate refers to
+        self.upsample = int(upsample)
+        if self.upsample < 1 or h % self.upsample or w % self.upsample:
+            raise RuntimeError(f"h, w ({h}, {w}) must be multiples of upsample ({upsample})")
         if self.device.type != "cuda":
             raise RuntimeError("PoseRecoveryEngine needs a CUDA device (no CPU path)")
         self.b, self.h, self.w, self.num_classes, self.hn = b, h, w, num_classes, hn
@@ -63,12 +68,14 @@ class PoseRecoveryEngine:
         a.max_instances, a.max_records, a.max_rows = self.max_instances, self.max_records, self.max_rows
         a.inlier_thresh, a.min_num, a.max_num = self.inlier_thresh, self.min_num, self.max_num
         a.arith, a.seed = self.arith, self.seed
+        a.upsample = self.upsample
         return a
 
     def launch(self, logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, idxs: Optional[torch.Tensor] = None,
                select_u: Optional[torch.Tensor] = None, stage_events=None) -> None:
         """Enqueues the 15 kernels on the current stream.  No synchronisation."""
-        b, h, w, C, K = self.b, self.h, self.w, self.num_classes, self.num_classes - 1
+        b, C, K = self.b, self.num_classes, self.num_classes - 1
+        h, w = self.h // self.upsample, self.w // self.upsample      # resolution of the head maps handed in
         f32 = torch.float32
         mask = _lib.require_device_readable(logits["mask"], "logits['mask']", f32)
         quat = _lib.require_device_readable(logits["quaternion"], "logits['quaternion']", f32)
@@ -102,7 +109,7 @@ class PoseRecoveryEngine:
             a.idxs = idxs.data_ptr()
         if select_u is not None:
             select_u = _lib.require_cuda(select_u, "select_u", f32)
-            if tuple(select_u.shape) != (b, h, w):
+            if tuple(select_u.shape) != (b, self.h, self.w):
                 raise RuntimeError("select_u must be [b,h,w]")
             a.select_u = select_u.data_ptr()
         a.pose_table, a.counters = self.pose_table.data_ptr(), self.counters.data_ptr()
@@ -267,6 +274,8 @@ _engines: Dict[tuple, PoseRecoveryEngine] = {}
 
 
 def get_engine(b, h, w, num_classes, hn, device, **kw) -> PoseRecoveryEngine:
+    if kw.get("upsample", 1) == 1:
+        kw.pop("upsample", None)          # the default: same cache entry whether or not it was spelled out
     key = (b, h, w, num_classes, hn, str(torch.device(device)), tuple(sorted(kw.items())))
     eng = _engines.get(key)
     if eng is None:
@@ -276,17 +285,23 @@ def get_engine(b, h, w, num_classes, hn, device, **kw) -> PoseRecoveryEngine:
 
 
 def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, hn: int, idxs: Optional[torch.Tensor] = None,
-                 *, select_u: Optional[torch.Tensor] = None, materialize_dense: bool = False, **engine_kw) -> Dict[str, torch.Tensor]:
+                 *, select_u: Optional[torch.Tensor] = None, materialize_dense: bool = False, upsample: int = 1,
+                 **engine_kw) -> Dict[str, torch.Tensor]:
     """logits (LogitData, lib/type_hinting.py:5-10) -> AggData with the reference's keys.
 
     ``idxs``: fixed pre-sampled hypothesis pixel pairs ``[N,hn,2]`` (or ``[N,hn,1,2]``) int32, instance
     order; ``None`` samples on the device.  ``materialize_dense=True`` additionally returns the
-    reference's dense ``instance_masks [N,h,w]`` and ``xy_mask [N,2,h,w]``."""
+    reference's dense ``instance_masks [N,h,w]`` and ``xy_mask [N,2,h,w]``.
+
+    ``upsample=S > 1`` (head-epilogue fusion): ``logits`` are the heads' LOW-RESOLUTION outputs ``[b,.,h/S,w/S]`` (after
+    the 1x1 convolutions, before ``nn.UpsamplingBilinear2d(scale_factor=S)``); the up-sampling is evaluated inside the
+    kernels and the full-resolution head maps never exist.  Results refer to the full ``[h,w]`` resolution."""
     mask = logits["mask"]
     b, C, h, w = mask.shape
+    h, w = h * upsample, w * upsample
     # head maps may also be PINNED HOST tensors (read in place over PCIe); the device then comes from inv_intrinsics
     device = mask.device if mask.is_cuda else inv_intrinsics.device
-    eng = get_engine(b, h, w, C, hn, device, want_labels=True, **engine_kw)
+    eng = get_engine(b, h, w, C, hn, device, want_labels=True, upsample=upsample, **engine_kw)
     eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
     n = eng.fetch_count()
     agg = eng.table_to_agg(n)
@@ -297,5 +312,8 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
         from .aggregation_layer import materialize_instance_masks, materialize_xy_mask
         from .gpu_tensor_funcs import class_compression
         agg["instance_masks"] = materialize_instance_masks(eng.labels, eng.pose_table, n)
+        if upsample > 1:
+            from .head_epilogue import upsample_bilinear
+            logits = {k: upsample_bilinear(v, upsample) for k, v in logits.items()}
         agg["xy_mask"] = materialize_xy_mask(eng.labels, eng.pose_table, class_compression(logits, C)["xy"], n)
     return agg

@@ -129,3 +129,17 @@ def presampled_idxs(tns: Sequence[int], hn: int, vn: int = 1, seed: int = 1234, 
         if tn >= min_num:
             out[i] = torch.randint(0, int(tn), (hn, vn, 2), generator=g, dtype=torch.int32)
     return out
+
+
+def render_lowres_heads(frames: Sequence[Sequence[Disc]], h: int, w: int, scale: int = 4, num_classes: int = 7, seed: int = 0,
+                        device="cpu") -> Dict[str, torch.Tensor]:
+    """The same scenes as ``render_heads`` but as the heads' LOW-RESOLUTION outputs ``[b,.,h/scale,w/scale]`` (what the
+    1x1 convolutions of smp's SegmentationHead emit before ``nn.UpsamplingBilinear2d(scale_factor=scale)``,
+    lib/pose_regressor.py:633-666).  Discs are given in full-resolution pixels and mapped through the align_corners
+    grid, so after up-sampling they sit where ``render_heads`` would put them."""
+    if h % scale or w % scale:
+        raise ValueError("h and w must be multiples of scale")
+    hl, wl = h // scale, w // scale
+    sy, sx = (hl - 1) / max(h - 1, 1), (wl - 1) / max(w - 1, 1)
+    low = [[(cx * sx, cy * sy, r * 0.5 * (sx + sy), cls) for (cx, cy, r, cls) in discs] for discs in frames]
+    return render_heads(low, hl, wl, num_classes=num_classes, seed=seed, device=device)

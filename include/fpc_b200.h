@@ -171,6 +171,12 @@ typedef struct fpc_recover_args {
      * event k after the k-th launch (k = 1..fpc_pose_recover_num_launches()); NULL entries are skipped */
     void **stage_events;
     int32_t num_stage_events;
+    /* Head-epilogue fusion, fpc_pose_recover only.  0 or 1: the five head maps are full
+     * resolution [b,.,h,w] (above).  S > 1: they are the LOW-RESOLUTION outputs of the heads' 1x1 convolutions,
+     * [b,.,h/S,w/S] (h, w multiples of S), and the x S bilinear up-sampling of smp's SegmentationHead
+     * (nn.UpsamplingBilinear2d(scale_factor=S), align_corners=True; lib/pose_regressor.py:633-666) is evaluated on the
+     * fly inside the arg-max and gather kernels -- the [b,67,h,w] head maps are never written or read. */
+    int32_t upsample;
 } fpc_recover_args;
 
 /* Workspace size for fpc_pose_recover with these sizes (only the size fields are read). */
@@ -205,6 +211,12 @@ FPC_API int fpc_vote_dense(const fpc_recover_args *args, const float *fmask, con
  * labels [b,h,w] = instance id + 1; pose_table rows supply each instance's frame. */
 FPC_API int fpc_materialize_instances(const int32_t *labels, const float *pose_table, const float *xy_cat,
                                       float *instance_masks, float *xy_mask, int n, int h, int w, void *stream);
+
+/* nn.UpsamplingBilinear2d(scale_factor=scale) (align_corners=True) of `planes` planes [hl,wl] -> [hl*scale, wl*scale]:
+ * the up-sampling step of smp's SegmentationHead (lib/pose_regressor.py:633-666) as a stand-alone operator.  Same
+ * arithmetic as ATen: src = dst * float(in-1)/float(out-1); value = fma(fma(v00,wx0,v01*wx1), wy0, fma(v10,wx0,v11*wx1)*wy1)
+ * -- bit-identical to torch's CPU kernel (planes of >= 3200 output pixels) and to its CUDA kernel. */
+FPC_API int fpc_upsample_bilinear(const float *in, long long planes, int hl, int wl, int scale, float *out, void *stream);
 
 /* ---- ground-truth <-> prediction matching ---------------------------------------
  * Replaces lib/gpu_tensor_funcs.py:386-409 batchwise_get_2d_iou (expand both mask sets to [n1,n2,h,w], sum

@@ -22,8 +22,8 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the C restatement with the committed Makefile (gcc, no GPU needed)."""
-    src = os.path.join(_HERE, "ransac_voting_ref.c")
-    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    srcs = [os.path.join(_HERE, f) for f in ("ransac_voting_ref.c", "head_epilogue_ref.c")]
+    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _LIB_PATH
@@ -43,6 +43,8 @@ def lib() -> ctypes.CDLL:
             f = getattr(L, name)
             f.argtypes = [fp, fp, fp, up, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float]
             f.restype = None
+        L.fpc_ref_upsample_bilinear.argtypes = [fp, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
+        L.fpc_ref_upsample_bilinear.restype = None
         L.fpc_ref_num_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -91,6 +93,16 @@ class RansacVotingCPU:
 
 ransac_voting = RansacVotingCPU(fma=False)
 ransac_voting_fma = RansacVotingCPU(fma=True)
+
+
+def upsample_bilinear(x: torch.Tensor, scale: int) -> torch.Tensor:
+    """C restatement of nn.UpsamplingBilinear2d(scale_factor=scale) (oracle/head_epilogue_ref.c) on a CPU tensor."""
+    _chk(x, torch.float32, "x")
+    hl, wl = x.shape[-2:]
+    out = torch.empty(tuple(x.shape[:-2]) + (hl * scale, wl * scale), dtype=torch.float32)
+    if x.numel():
+        lib().fpc_ref_upsample_bilinear(x.data_ptr(), x.numel() // (hl * wl), hl, wl, int(scale), out.data_ptr())
+    return out
 
 
 def num_threads() -> int:

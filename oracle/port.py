@@ -465,3 +465,29 @@ def batchwise_find_matches2(preds, gts):
             p = torch.stack([preds[key][j] if j >= 0 else std for j in pred_rows])
             out[key] = torch.stack((gts[key][g_idx], p))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the heads' epilogue (lib/pose_regressor.py:633-666, 706-741)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def split_xyz(xyz_logits: torch.Tensor):
+    """lib/pose_regressor.py:729-732: per class k the translation head emits (x-dir, y-dir, z) = channels 3k..3k+2."""
+    c = xyz_logits.shape[1]
+    xy = [i for i in range(c) if i % 3 != 0]
+    z = [i for i in range(c) if i % 3 == 0]
+    return xyz_logits[:, [i - 1 for i in xy]], xyz_logits[:, [i + 2 for i in z]]
+
+
+def upsample_heads(lowres: Dict[str, torch.Tensor], scale: int = 4) -> Dict[str, torch.Tensor]:
+    """What smp's SegmentationHead does after its 1x1 convolution (``nn.UpsamplingBilinear2d(scale_factor=4)`` then the
+    identity activation; pose_regressor.py:633-666 with the default ``upsampling=4``): low-resolution LogitData
+    ``[b,.,h/4,w/4]`` -> the full-resolution LogitData the path consumes.  torch's own operator is the reference here;
+    ``oracle/head_epilogue_ref.c`` restates its arithmetic and is pinned to it."""
+    up = torch.nn.UpsamplingBilinear2d(scale_factor=scale)
+    return {k: up(v) for k, v in lowres.items()}
+
+
+def pose_recover_lowres(lowres, inv_intrinsics, round_hyp_num: int, scale: int = 4, **kw):
+    """Reference behaviour for low-resolution head outputs: up-sample every head map, then the path."""
+    return pose_recover(upsample_heads(lowres, scale), inv_intrinsics, round_hyp_num, **kw)
