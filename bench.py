@@ -385,9 +385,11 @@ def run_b200(args):
                "sample": f"{args.ref_frames} frames of {wl.name}, 1 warm-up + 3 timed passes of oracle/port.py "
                          f"(torch-CPU aggregation + scipy CCL + C voting kernels, OpenMP threads={omp})"}
 
-    matching = None
+    matching = head_epilogue = None
     if rank == 0 and world == 1 and not args.no_matching:
         matching = matching_section(dev, wl, logits, inv_k, hbm_peak, peak_src)
+    if rank == 0 and world == 1 and not args.no_head_epilogue and wl.h % 4 == 0 and wl.w % 4 == 0:
+        head_epilogue = head_epilogue_section(dev, wl, bpg, hn, inv_k, args.steps, depth, nk, kernel_names)
 
     if rank == 0:
         line = {
@@ -414,6 +416,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "matching": matching,
+            "head_epilogue": head_epilogue,
             "gpu_launches": nk * args.steps,
             "clocks": clocks,
             "instances": n,
@@ -421,6 +424,127 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def head_epilogue_section(dev, wl, bpg, hn, inv_k, steps, depth, nk, kernel_names):
+    """SURVEY.md section 8f rank 2 beside the headline: the same scenes handed over as the heads' LOW-RESOLUTION outputs
+    ([b,67,h/4,w/4], what the 1x1 convolutions of smp's SegmentationHead emit), the x4 bilinear up-sampling evaluated
+    inside the arg-max and gather kernels.  Next to it: what the reference flow spends on producing the full-resolution
+    maps with torch's own CUDA up-sampling kernel, which the fused path never runs."""
+    from fastposecnn_b200 import _lib
+    from fastposecnn_b200 import synthetic as syn
+    from fastposecnn_b200.pose_recovery import PoseRecoveryEngine, PoseRecoveryPipeline
+    S = 4
+    low = syn.render_lowres_heads([wl.discs()] * bpg, wl.h, wl.w, S, wl.num_classes, seed=1000, device=dev)
+    cap = max(1024, 2 * bpg * len(wl.discs()))
+    pipe = PoseRecoveryPipeline(depth, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=cap, upsample=S)
+    n = None
+    for _ in range(3):
+        pipe.submit(low, inv_k)
+    for _e, n in pipe.drain():
+        pass
+    pipe.capture(low, inv_k)
+    for _ in range(2 * depth):
+        pipe.submit(replay=True)
+    pipe.drain()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        pipe.submit(replay=True)
+    pipe.drain()
+    pipe.join()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    # per-kernel times: serial instrumented pass
+    pipe_i = PoseRecoveryPipeline(2, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=cap, upsample=S, multi_stream=False)
+    evs = []
+    for k in range(3 + steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(nk + 1)]
+        for e in ev:
+            e.record()
+        pipe_i.submit(low, inv_k, stage_events=ev)
+        if k >= 3:
+            evs.append(ev)
+    pipe_i.drain()
+    torch.cuda.synchronize()
+    kms = [sum(ev[k].elapsed_time(ev[k + 1]) for ev in evs) / len(evs) for k in range(nk)]
+    # the reference flow's up-sampling (torch CUDA kernel) of the same 67 channels, and the full-resolution path on its output
+    up = torch.nn.UpsamplingBilinear2d(scale_factor=S)
+    full = {k: up(v) for k, v in low.items()}
+    torch.cuda.synchronize()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(5):
+        for v in low.values():
+            up(v)
+    u1.record()
+    torch.cuda.synchronize()
+    up_ms = u0.elapsed_time(u1) / 5
+    eng_full = PoseRecoveryEngine(bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=cap)
+    for _ in range(3):
+        eng_full.launch(full, inv_k)
+    n_full = eng_full.fetch_count()
+    eng_full.capture(full, inv_k)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    f0.record()
+    for _ in range(steps):
+        eng_full.replay()
+    f1.record()
+    torch.cuda.synchronize()
+    full_ms = f0.elapsed_time(f1) / steps
+    eng_low = pipe.engines[0]
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(steps):
+        eng_low.replay()
+    g1.record()
+    torch.cuda.synchronize()
+    low_serial_ms = g0.elapsed_time(g1) / steps
+    same = bool(torch.equal(eng_low.cat_mask_u8, eng_full.cat_mask_u8))
+    # end to end from pinned host buffers: H2D copy of the low-resolution maps (1/16 of the bytes), the path, D2H of the table
+    host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in low.items()}
+    for k, v in low.items():
+        host[k].copy_(v)
+    stage = {k: torch.empty_like(v) for k, v in low.items()}
+    table_host = torch.empty((eng_low.max_instances, _lib.POSE_ROW), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for k in host:
+            stage[k].copy_(host[k], non_blocking=True)
+        eng_low.launch(stage, inv_k)
+        n_ = eng_low.fetch_count()
+        table_host[:n_].copy_(eng_low.pose_table[:n_], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return n_
+    for _ in range(2):
+        e2e_step()
+    ksteps = max(3, min(steps, 10))
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    h0.record()
+    for _ in range(ksteps):
+        e2e_step()
+    h1.record()
+    torch.cuda.synchronize()
+    e2e_ms = h0.elapsed_time(h1) / ksteps
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    return {
+        "what": "same scenes as low-resolution head outputs [b,67,%d,%d]; x%d bilinear up-sampling fused into k_argmax_runs / k_gather"
+                % (wl.h // S, wl.w // S, S),
+        "value": bpg / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "instances": n,
+        "kernel_ms": {kernel_names[k]: round(kms[k], 5) for k in range(nk)},
+        "one_stream_graph_replay_ms": {"lowres_fused": low_serial_ms, "full_resolution_path_on_torch_upsampled_maps": full_ms,
+                                       "torch_cuda_upsampling_of_67_channels": up_ms},
+        "class_map_identical_to_full_resolution_path": same, "instances_full_resolution_path": n_full,
+        "input_bytes_per_step": {"lowres": h2d, "full_resolution": h2d * S * S},
+        "e2e": {"value": bpg / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": n * _lib.POSE_ROW * 4 + _lib.NUM_COUNTERS * 4,
+                "note": "pinned host low-resolution head outputs -> H2D copy -> fused path -> D2H of N and the pose table"},
+    }
 
 
 def matching_section(dev, wl, logits, inv_k, hbm_peak, peak_src, iters=10):
@@ -518,6 +642,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches in the timed loop instead of CUDA-graph replay")
     ap.add_argument("--e2e-mode", default="zerocopy", choices=["zerocopy", "copy"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-head-epilogue", action="store_true", help="skip the low-resolution-input (SURVEY 8f rank 2) measurements")
     ap.add_argument("--no-matching", action="store_true", help="skip the matching (SURVEY 8f rank 1) measurements")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

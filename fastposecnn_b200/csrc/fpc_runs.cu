@@ -96,6 +96,12 @@ __global__ void __launch_bounds__(1024) k_argmax_runs_v1(const float *__restrict
 // head output, evaluated here -- the [b,C,h,w] logits never exist.  One thread = 4 consecutive output pixels; for
 // S >= 3 they touch at most 3 low-res columns, so a class plane costs 6 cached loads per thread (1/16 of the bytes
 // of the full-resolution kernel at S = 4) and 24 FP32 operations.
+//
+// CT > 0 (class count known at compile time): the 6 x CT taps are loaded up front (all in flight together), and a thread
+// whose 6 taps are all background-dominant (logit 0 >= every other logit) skips the interpolation: bilinear weights are
+// non-negative and every rounding step is monotone, so background then also wins -- or ties, and arg-max keeps the
+// first maximum -- at all 4 output pixels.  Most of an image is such background.
+template <int CT>
 __global__ void __launch_bounds__(256) k_argmax_runs_up4(const float *__restrict__ mask_lr, uint8_t *__restrict__ cls,
                                                          int *__restrict__ tile_runs, int C, int hw, int w, int P4, UpParams up) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,28 +114,65 @@ __global__ void __launch_bounds__(256) k_argmax_runs_up4(const float *__restrict
         const int y = pix / w;
         x0 = pix - y * w;
         const LerpCoord Y = lerp_coord(y, up.sy, up.hl);
-        LerpCoord X[4];
-        bool sh[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) X[j] = lerp_coord(x0 + j, up.sx, up.wl);
-        const int cA = X[0].i0, cB = min(cA + 1, up.wl - 1), cC = min(cA + 2, up.wl - 1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sh[j] = X[j].i0 != cA;      // pixel j starts one low-res column further right
+        const LerpCoord X0 = lerp_coord(x0, up.sx, up.wl);
+        const int cA = X0.i0, cB = min(cA + 1, up.wl - 1), cC = min(cA + 2, up.wl - 1);
         const size_t lhw = (size_t)up.hl * up.wl;
         const float *r0 = mask_lr + (size_t)bi * C * lhw + (size_t)Y.i0 * up.wl;
         const float *r1 = mask_lr + (size_t)bi * C * lhw + (size_t)Y.i1 * up.wl;
-        float best[4];
         int arg[4] = {0, 0, 0, 0};
-        for (int c = 0; c < C; ++c) {
-            const float a0 = __ldg(r0 + cA), b0 = __ldg(r0 + cB), c0 = __ldg(r0 + cC);
-            const float a1 = __ldg(r1 + cA), b1 = __ldg(r1 + cB), c1 = __ldg(r1 + cC);
-            r0 += lhw;
-            r1 += lhw;
+        if (CT > 0) {
+            float v[CT > 0 ? CT : 1][6];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float v = bilerp(sh[j] ? b0 : a0, sh[j] ? c0 : b0, sh[j] ? b1 : a1, sh[j] ? c1 : b1, X[j].w0, X[j].w1, Y.w0, Y.w1);
-                if (c == 0) best[j] = v;
-                else if (v > best[j]) { best[j] = v; arg[j] = c; }      // strict '>' keeps the first maximum, like torch.argmax
+            for (int c = 0; c < CT; ++c) {
+                v[c][0] = __ldg(r0 + c * lhw + cA); v[c][1] = __ldg(r0 + c * lhw + cB); v[c][2] = __ldg(r0 + c * lhw + cC);
+                v[c][3] = __ldg(r1 + c * lhw + cA); v[c][4] = __ldg(r1 + c * lhw + cB); v[c][5] = __ldg(r1 + c * lhw + cC);
+            }
+            bool bg = true;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                float m = v[CT > 1 ? 1 : 0][k];
+#pragma unroll
+                for (int c = 2; c < CT; ++c) m = fmaxf(m, v[c][k]);
+                bg = bg && (v[0][k] >= m);                                 // false for NaN: falls through to the full evaluation
+            }
+            if (!bg) {
+                LerpCoord X[4];
+                X[0] = X0;
+#pragma unroll
+                for (int j = 1; j < 4; ++j) X[j] = lerp_coord(x0 + j, up.sx, up.wl);
+                float best[4];
+#pragma unroll
+                for (int c = 0; c < CT; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool sh = X[j].i0 != cA;                     // pixel j starts one low-res column further right
+                        const float val = bilerp(sh ? v[c][1] : v[c][0], sh ? v[c][2] : v[c][1], sh ? v[c][4] : v[c][3],
+                                                 sh ? v[c][5] : v[c][4], X[j].w0, X[j].w1, Y.w0, Y.w1);
+                        if (c == 0) best[j] = val;
+                        else if (val > best[j]) { best[j] = val; arg[j] = c; }   // strict '>' keeps the first maximum, like torch.argmax
+                    }
+                }
+            }
+        } else {
+            LerpCoord X[4];
+            bool sh[4];
+            X[0] = X0;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) X[j] = lerp_coord(x0 + j, up.sx, up.wl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sh[j] = X[j].i0 != cA;
+            float best[4];
+            for (int c = 0; c < C; ++c) {
+                const float a0 = __ldg(r0 + cA), b0 = __ldg(r0 + cB), c0 = __ldg(r0 + cC);
+                const float a1 = __ldg(r1 + cA), b1 = __ldg(r1 + cB), c1 = __ldg(r1 + cC);
+                r0 += lhw;
+                r1 += lhw;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float val = bilerp(sh[j] ? b0 : a0, sh[j] ? c0 : b0, sh[j] ? b1 : a1, sh[j] ? c1 : b1, X[j].w0, X[j].w1, Y.w0, Y.w1);
+                    if (c == 0) best[j] = val;
+                    else if (val > best[j]) { best[j] = val; arg[j] = c; }
+                }
             }
         }
         nib = (arg[0] != 0) | ((arg[1] != 0) << 1) | ((arg[2] != 0) << 2) | ((arg[3] != 0) << 3);
@@ -559,7 +602,10 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
     int span;
     if (mask_logits && pp.up.s > 1) {
         if (pp.w % 4 == 0 && pp.up.s >= 3 && (reinterpret_cast<uintptr_t>(ws.cls) & 3) == 0) {
-            k_argmax_runs_up4<<<ntiles, 256, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P / 4, pp.up);
+            if (pp.num_classes == 7)   // the reference's class count (6 objects + background): unrolled, background skip
+                k_argmax_runs_up4<7><<<ntiles, 256, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, 7, pp.hw, pp.w, P / 4, pp.up);
+            else
+                k_argmax_runs_up4<0><<<ntiles, 256, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P / 4, pp.up);
             span = 128;
         } else {
             k_argmax_runs_up1<<<ntiles, 1024, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P, pp.up);
