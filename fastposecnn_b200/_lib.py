@@ -30,6 +30,7 @@ EXPORTS = (
     "fpc_pose_recover", "fpc_pose_recover_num_launches", "fpc_pose_recover_kernel_name", "fpc_bench_fp32_fma",
     "fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances",
     "fpc_pack_masks", "fpc_pack_labels", "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances", "fpc_upsample_bilinear",
+    "fpc_generate_hypothesis_vanishing_point", "fpc_voting_for_hypothesis_vanishing_point",
 )
 MASK_META = 8
 MASK_F32, MASK_U8 = 0, 1
@@ -72,6 +73,9 @@ def lib() -> ctypes.CDLL:
     L.fpc_last_error.restype = ctypes.c_char_p
     L.fpc_generate_hypothesis.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
     L.fpc_voting_for_hypothesis.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]
+    L.fpc_generate_hypothesis_vanishing_point.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+    L.fpc_voting_for_hypothesis_vanishing_point.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]
+    L.fpc_generate_hypothesis_vanishing_point.restype = L.fpc_voting_for_hypothesis_vanishing_point.restype = _i
     L.fpc_normalize.argtypes = [_vp, _vp, _ll, _i, _ll, _vp]
     L.fpc_class_compress.argtypes = [_vp] * 11 + [_i, _i, _i, _i, _vp]
     L.fpc_get_rt.argtypes = [_vp] * 7 + [_i, _vp]

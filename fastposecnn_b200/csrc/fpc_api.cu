@@ -267,6 +267,25 @@ int fpc_voting_for_hypothesis(const float *direct, const float *coords, const fl
                                         (cudaStream_t)stream);
 }
 
+int fpc_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs, float *hypo_pts, int tn,
+                                            int vn, int hn, int arith, void *stream) {
+    if (tn < 0 || vn < 0 || hn < 0) return fail(FPC_EINVAL, "negative size");
+    if (hn * vn == 0) return FPC_OK;
+    if (!direct || !coords || !idxs || !hypo_pts) return fail(FPC_EINVAL, "NULL pointer");
+    if (arith != FPC_ARITH_IEEE && arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", arith);
+    return launch_generate_hypothesis_vp(direct, coords, idxs, hypo_pts, tn, vn, hn, arith, (cudaStream_t)stream);
+}
+
+int fpc_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hypo_pts, uint8_t *inliers,
+                                              int tn, int vn, int hn, float inlier_thresh, int arith, void *stream) {
+    if (tn < 0 || vn < 0 || hn < 0) return fail(FPC_EINVAL, "negative size");
+    if ((long long)tn * vn * hn == 0) return FPC_OK;
+    if (!direct || !coords || !hypo_pts || !inliers) return fail(FPC_EINVAL, "NULL pointer");
+    if (vn > 65535) return fail(FPC_EINVAL, "vn too large");
+    if (arith != FPC_ARITH_IEEE && arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", arith);
+    return launch_voting_for_hypothesis_vp(direct, coords, hypo_pts, inliers, tn, vn, hn, inlier_thresh, arith, (cudaStream_t)stream);
+}
+
 int fpc_normalize(const float *in, float *out, long long outer, int c, long long inner, void *stream) {
     if (outer < 0 || c < 0 || inner < 0) return fail(FPC_EINVAL, "negative size");
     if (outer * inner == 0 || c == 0) return FPC_OK;

@@ -103,6 +103,10 @@ int launch_generate_hypothesis(const float *direct, const float *coords, const i
                                int hn, int arith, cudaStream_t st);
 int launch_voting_for_hypothesis(const float *direct, const float *coords, const float *hypo, uint8_t *inliers, int tn,
                                  int vn, int hn, float thresh, int arith, cudaStream_t st);
+int launch_generate_hypothesis_vp(const float *direct, const float *coords, const int *idxs, float *hypo, int tn, int vn, int hn,
+                                  int arith, cudaStream_t st);
+int launch_voting_for_hypothesis_vp(const float *direct, const float *coords, const float *hypo, uint8_t *inliers, int tn, int vn,
+                                    int hn, float thresh, int arith, cudaStream_t st);
 void set_vote_packed(int v);
 int vote_batches(int hn);
 int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st);

@@ -59,6 +59,76 @@ __global__ void __launch_bounds__(256) k_voting_for_hypothesis(const float *__re
 }
 
 // =============================================================================================
+// Vanishing-point twins of K1/K2 (src/ransac_voting_kernel.cu:170-228, 268-308; pybind names
+// generate_hypothesis_vanishing_point / voting_for_hypothesis_vanishing_point, ransac_voting.cpp:104-105): a hypothesis
+// is the homogeneous point (x, y, z) where the lines of two pixel rays cross.  FPC_ARITH_IEEE evaluates the source
+// expressions un-contracted; FPC_ARITH_NVCC_FMA applies the contraction nvcc makes of the reference source (read from
+// its SASS): a*b - c*d -> fma(a, b, -(c*d)), u - z*c -> fma(-c, z, u), a*a + b*b -> fma(a, a, b*b).
+// =============================================================================================
+template <int ARITH>
+__device__ __forceinline__ float diff_prod(float a, float b, float c, float d) {   // a*b - c*d
+    if (ARITH == FPC_ARITH_IEEE) return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+    return __fmaf_rn(a, b, -__fmul_rn(c, d));
+}
+template <int ARITH>
+__device__ __forceinline__ float sub_prod(float u, float z, float c) {              // u - z*c
+    if (ARITH == FPC_ARITH_IEEE) return __fsub_rn(u, __fmul_rn(z, c));
+    return __fmaf_rn(-c, z, u);
+}
+
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_generate_hypothesis_vp(const float *__restrict__ direct, const float *__restrict__ coords,
+                                                                const int *__restrict__ idxs, float *__restrict__ hypo, int tn,
+                                                                int vn, int hn) {
+    const int hvi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hvi >= hn * vn) return;
+    const int vi = hvi % vn;
+    const int t0 = idxs[2 * hvi], t1 = idxs[2 * hvi + 1];
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (t0 >= 0 && t0 < tn && t1 >= 0 && t1 < tn) {
+        const float dx0 = direct[((size_t)t0 * vn + vi) * 2], dy0 = direct[((size_t)t0 * vn + vi) * 2 + 1];
+        const float dx1 = direct[((size_t)t1 * vn + vi) * 2], dy1 = direct[((size_t)t1 * vn + vi) * 2 + 1];
+        const float cx0 = coords[2 * t0], cy0 = coords[2 * t0 + 1], cx1 = coords[2 * t1], cy1 = coords[2 * t1 + 1];
+        // lines l = (dy, -dx, cy*dx - cx*dy); point = l0 x l1 (signs folded: ly = -dx)
+        const float lz0 = diff_prod<ARITH>(dx0, cy0, dy0, cx0), lz1 = diff_prod<ARITH>(dx1, cy1, dy1, cx1);
+        z = diff_prod<ARITH>(dx0, dy1, dy0, dx1);
+        x = diff_prod<ARITH>(dx1, lz0, dx0, lz1);
+        y = diff_prod<ARITH>(dy1, lz0, dy0, lz1);
+        const float val_x0 = __fmul_rn(dx0, sub_prod<ARITH>(x, z, cx0)), val_x1 = __fmul_rn(dx1, sub_prod<ARITH>(x, z, cx1));
+        const float val_y0 = __fmul_rn(dy0, sub_prod<ARITH>(y, z, cy0)), val_y1 = __fmul_rn(dy1, sub_prod<ARITH>(y, z, cy1));
+        if (val_x0 < 0.f && val_x1 < 0.f && val_y0 < 0.f && val_y1 < 0.f) { x = -x; y = -y; z = -z; }
+        if (__fmul_rn(val_x0, val_x1) < 0.f || __fmul_rn(val_y0, val_y1) < 0.f) { x = 0.f; y = 0.f; z = 0.f; }   // rays do not meet
+    }
+    hypo[3 * hvi] = x;
+    hypo[3 * hvi + 1] = y;
+    hypo[3 * hvi + 2] = z;
+}
+
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_voting_for_hypothesis_vp(const float *__restrict__ direct, const float *__restrict__ coords,
+                                                                  const float *__restrict__ hypo, uint8_t *__restrict__ inliers,
+                                                                  int tn, int vn, int hn, float thresh) {
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x;
+    const int vi = blockIdx.y;
+    if (ti >= tn) return;
+    const float cx = coords[2 * ti], cy = coords[2 * ti + 1];
+    const float dx = direct[((size_t)ti * vn + vi) * 2], dy = direct[((size_t)ti * vn + vi) * 2 + 1];
+    const float norm1 = __fsqrt_rn(sum_prod<ARITH>(dx, dx, dy, dy));
+    if (below_1e6(norm1)) return;
+    const int h0 = blockIdx.z * K2_HYPS_PER_BLOCK, h1 = min(hn, h0 + K2_HYPS_PER_BLOCK);
+    for (int hi = h0; hi < h1; ++hi) {
+        const float *h = hypo + ((size_t)hi * vn + vi) * 3;
+        const float diff_x = sub_prod<ARITH>(h[0], h[2], cx), diff_y = sub_prod<ARITH>(h[1], h[2], cy);
+        const float norm2 = __fsqrt_rn(sum_prod<ARITH>(diff_x, diff_x, diff_y, diff_y));
+        if (below_1e6(norm2)) continue;
+        const float val_x = __fmul_rn(diff_x, dx), val_y = __fmul_rn(diff_y, dy);
+        if (val_x < 0.f || val_y < 0.f) continue;                          // the ray points away from the hypothesis
+        const float angle = __fdiv_rn(__fadd_rn(val_x, val_y), __fmul_rn(norm1, norm2));
+        if (fabsf(angle) > thresh) inliers[((size_t)hi * vn + vi) * tn + ti] = 1;
+    }
+}
+
+// =============================================================================================
 // Hypotheses (K1) for every live instance: one thread per (instance, hypothesis)
 // =============================================================================================
 template <int ARITH>
@@ -638,6 +708,30 @@ int launch_voting_for_hypothesis(const float *direct, const float *coords, const
     else
         k_voting_for_hypothesis<FPC_ARITH_NVCC_FMA><<<grid, 256, 0, st>>>(direct, coords, hypo, inliers, tn, vn, hn, thresh);
     FPC_LAUNCH_CHECK("k_voting_for_hypothesis");
+    return FPC_OK;
+}
+
+int launch_generate_hypothesis_vp(const float *direct, const float *coords, const int *idxs, float *hypo, int tn, int vn, int hn,
+                                  int arith, cudaStream_t st) {
+    const int n = hn * vn;
+    if (n == 0) return FPC_OK;
+    if (arith == FPC_ARITH_IEEE)
+        k_generate_hypothesis_vp<FPC_ARITH_IEEE><<<ceil_div(n, 256), 256, 0, st>>>(direct, coords, idxs, hypo, tn, vn, hn);
+    else
+        k_generate_hypothesis_vp<FPC_ARITH_NVCC_FMA><<<ceil_div(n, 256), 256, 0, st>>>(direct, coords, idxs, hypo, tn, vn, hn);
+    FPC_LAUNCH_CHECK("k_generate_hypothesis_vp");
+    return FPC_OK;
+}
+
+int launch_voting_for_hypothesis_vp(const float *direct, const float *coords, const float *hypo, uint8_t *inliers, int tn, int vn,
+                                    int hn, float thresh, int arith, cudaStream_t st) {
+    if (tn == 0 || vn == 0 || hn == 0) return FPC_OK;
+    dim3 grid(ceil_div(tn, 256), vn, ceil_div(hn, K2_HYPS_PER_BLOCK));
+    if (arith == FPC_ARITH_IEEE)
+        k_voting_for_hypothesis_vp<FPC_ARITH_IEEE><<<grid, 256, 0, st>>>(direct, coords, hypo, inliers, tn, vn, hn, thresh);
+    else
+        k_voting_for_hypothesis_vp<FPC_ARITH_NVCC_FMA><<<grid, 256, 0, st>>>(direct, coords, hypo, inliers, tn, vn, hn, thresh);
+    FPC_LAUNCH_CHECK("k_voting_for_hypothesis_vp");
     return FPC_OK;
 }
 

@@ -1,6 +1,8 @@
-"""Drop-in for the two PVNet drivers FastPoseCNN's path names
-(lib/ransac_voting_gpu_layer/ransac_voting_gpu.py): ``ransac_voting_layer_v3`` (:518-607, the one
-HoughVotingLayer calls) and ``ransac_voting_layer`` (v1, :11-98), plus ``b_inv`` (:503-516).
+"""Drop-in for the PVNet drivers of lib/ransac_voting_gpu_layer/ransac_voting_gpu.py: ``ransac_voting_layer_v3``
+(:518-607, the one HoughVotingLayer calls), ``ransac_voting_layer`` (v1, :11-98), ``b_inv`` (:503-516) and, from the
+"next" rows, ``ransac_voting_layer_v2`` (:100), ``ransac_voting_hypothesis`` (:218), ``estimate_voting_distribution``
+(:263) and ``estimate_voting_distribution_with_mean`` (:333).  (``ransac_voting_vanish_point_layer`` :408 references an
+undefined ``class_num`` and cannot run in the reference; its two kernels are mirrored in ``ransac_voting.py``.)
 
 Same positional/keyword signatures and result layouts.  Instead of a Python loop with ~40 small
 kernels and >=4 host syncs per instance, ALL instances go through one batched launch sequence
@@ -124,3 +126,99 @@ def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.
     out = _vote(b * k, h, w, vn, None, imask, k, 1, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num, False,
                 idxs, su, details)
     return out.reshape(b, k, vn, 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The other PVNet drivers built on the same two kernels.  Same signatures and result
+# layouts as the reference; each is ONE batched launch sequence per keypoint instead of a Python loop per image/class.
+# ---------------------------------------------------------------------------------------------------------------------
+
+def ransac_voting_layer_v2(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=30000, refine_iter_num=1, *, idxs: Optional[torch.Tensor] = None,
+                           select_u: Optional[torch.Tensor] = None, details: Optional[list] = None):
+    """ransac_voting_gpu.py:100-216 -- v1 plus the least-squares refinement over the winner's inliers.
+
+    :param mask:      [b,h,w] class ids
+    :param vertex:    [b,h,w,vn,2]
+    :return: [b,class_num-1,vn,2]
+
+    The reference solves ``pinverse(A) @ b`` over the inlier normals; the kernel solves the same least-squares problem
+    through its 2x2 normal equations in FP64 (<= 1e-4 relative).  ``refine_iter_num`` 0 (= v1) or 1."""
+    if refine_iter_num not in (0, 1):
+        raise NotImplementedError("ransac_voting_layer_v2: refine_iter_num must be 0 or 1")
+    mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
+    vertex = _lib.require_cuda(vertex, "vertex", torch.float32, contiguous=False)
+    b, h, w, vn, two = vertex.shape
+    if two != 2 or tuple(mask.shape) != (b, h, w):
+        raise RuntimeError(f"expected mask [b,h,w] and vertex [b,h,w,vn,2], got {tuple(mask.shape)}, {tuple(vertex.shape)}")
+    k = int(class_num) - 1
+    imask = mask.to(torch.int32).contiguous()
+    su = _select_u(None, select_u, (b * k, h, w), vertex.device)
+    out = _vote(b * k, h, w, vn, None, imask, k, 1, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num,
+                bool(refine_iter_num), idxs, su, details)
+    return out.reshape(b, k, vn, 2)
+
+
+def _class1_hypotheses(mask, vertex, hn, inlier_thresh, min_num, max_num, idxs, select_u):
+    """All hypotheses and vote counts of the class-id-1 pixels of every image: ``hyp [b,hn,vn,2]``, ``counts [b,hn,vn]``
+    int32, ``tn [b]`` voters per image (0 = fewer than ``min_num`` pixels: nothing was computed)."""
+    mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
+    vertex = _lib.require_cuda(vertex, "vertex", torch.float32, contiguous=False)
+    b, h, w, vn, two = vertex.shape
+    if two != 2 or tuple(mask.shape) != (b, h, w):
+        raise RuntimeError(f"expected mask [b,h,w] and vertex [b,h,w,vn,2], got {tuple(mask.shape)}, {tuple(vertex.shape)}")
+    imask = mask.to(torch.int32).contiguous()
+    su = _select_u(None, select_u, (b, h, w), vertex.device)
+    det: list = []
+    _vote(b, h, w, vn, None, imask, 1, 1, vertex, int(hn), inlier_thresh, min_num, max_num, False, idxs, su, det)
+    hyp = torch.stack([d["hyp"] for d in det], dim=2)          # [b,hn,vn,2]
+    counts = torch.stack([d["counts"] for d in det], dim=2)    # [b,hn,vn]
+    return hyp, counts, det[0]["tn"]
+
+
+def ransac_voting_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000, *,
+                             idxs: Optional[torch.Tensor] = None, select_u: Optional[torch.Tensor] = None):
+    """ransac_voting_gpu.py:218-261 -> ``[b,hn,vn,2]`` hypotheses and ``[b,hn,vn]`` int64 vote counts of class id 1
+    (zeros / ones for images with fewer than ``min_num`` such pixels).  ``idxs``: ``[b,hn,vn,2]``."""
+    hyp, counts, tn = _class1_hypotheses(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idxs, select_u)
+    live = (tn > 0).view(-1, 1, 1)
+    return torch.where(live.unsqueeze(3), hyp, torch.zeros_like(hyp)), torch.where(live, counts.long(), torch.ones_like(counts).long())
+
+
+def _hypothesis_rounds(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num, idxs, select_u):
+    """``ceil(min_hyp_num / round_hyp_num)`` rounds in one launch -> points ``[b,vn,H,2]`` and inlier ratios ``[b,vn,H]``
+    (count / voters); images without enough pixels get zero points and ratio 1 like the reference's skip branch."""
+    rounds = -(-int(min_hyp_num) // int(round_hyp_num))
+    hyp, counts, tn = _class1_hypotheses(mask, vertex, rounds * int(round_hyp_num), inlier_thresh, min_num, max_num, idxs, select_u)
+    live = (tn > 0).view(-1, 1, 1)
+    ratio = torch.where(live, counts.float() / tn.clamp_min(1).float().view(-1, 1, 1), torch.ones_like(counts, dtype=torch.float32))
+    pts = torch.where(live.unsqueeze(3), hyp, torch.zeros_like(hyp))
+    return pts.permute(0, 2, 1, 3), ratio.permute(0, 2, 1)
+
+
+def estimate_voting_distribution(mask, vertex, round_hyp_num=256, min_hyp_num=4096, topk=128, inlier_thresh=0.99, min_num=5,
+                                 max_num=30000, *, idxs: Optional[torch.Tensor] = None, select_u: Optional[torch.Tensor] = None):
+    """ransac_voting_gpu.py:263-331 -> ``mean [b,vn,2]``, ``cov [b,vn,2,2]`` of the hypotheses weighted by inlier ratio
+    over the ``topk`` best-supported ones.  ``idxs``: ``[b, rounds*round_hyp_num, vn, 2]``, rounds concatenated."""
+    pts, ratio = _hypothesis_rounds(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num, idxs, select_u)
+    values, indexes = torch.topk(ratio, topk, dim=2, sorted=False)
+    weight = torch.zeros_like(ratio).scatter_(2, indexes, values)
+    total = torch.sum(weight, 2)
+    mean = torch.sum(weight.unsqueeze(3) * pts, 2) / total.unsqueeze(2)
+    diff = pts - mean.unsqueeze(2)
+    cov = torch.matmul(diff.transpose(2, 3), diff * weight.unsqueeze(3)) / total.unsqueeze(2).unsqueeze(3)
+    return mean, cov
+
+
+def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128,
+                                           inlier_thresh=0.99, min_num=5, max_num=30000, output_hyp=False, *,
+                                           idxs: Optional[torch.Tensor] = None, select_u: Optional[torch.Tensor] = None):
+    """ransac_voting_gpu.py:333-406 -> ``(mean, cov)``: covariance about the given mean with ratios more than 0.1 below
+    the best one zeroed and +1e-3 in the normaliser."""
+    pts, ratio = _hypothesis_rounds(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num, idxs, select_u)
+    thresh = torch.max(ratio, 2)[0] - 0.1
+    ratio = torch.where(ratio < thresh.unsqueeze(2), torch.zeros_like(ratio), ratio)
+    diff = pts - mean.unsqueeze(2)
+    cov = torch.matmul(diff.transpose(2, 3), diff * ratio.unsqueeze(3))
+    cov = cov / (torch.sum(ratio, 2).unsqueeze(2).unsqueeze(3) + 1e-3)
+    return mean, cov

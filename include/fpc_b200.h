@@ -70,6 +70,16 @@ FPC_API int fpc_voting_for_hypothesis(const float *direct, const float *coords, 
                               uint8_t *inliers, int tn, int vn, int hn, float inlier_thresh,
                               int arith, void *stream);
 
+/* The vanishing-point twins of the two functions above -- the other half of the reference's pybind module
+ * (src/ransac_voting.cpp:62-73 generate_hypothesis_vanishing_point, :83-97 voting_for_hypothesis_vanishing_point,
+ * kernels src/ransac_voting_kernel.cu:170-228, 268-308).  hypo_pts is [hn,vn,3]: homogeneous (x, y, z), all zero
+ * when the two rays do not meet; a pixel votes when its ray points towards the hypothesis and |cos| > thresh. */
+FPC_API int fpc_generate_hypothesis_vanishing_point(const float *direct, const float *coords, const int32_t *idxs, float *hypo_pts,
+                                                    int tn, int vn, int hn, int arith, void *stream);
+FPC_API int fpc_voting_for_hypothesis_vanishing_point(const float *direct, const float *coords, const float *hypo_pts,
+                                                      uint8_t *inliers, int tn, int vn, int hn, float inlier_thresh, int arith,
+                                                      void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Stage entry points behind the reference's Python operators
  * ---------------------------------------------------------------------------------- */

@@ -22,7 +22,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the C restatement with the committed Makefile (gcc, no GPU needed)."""
-    srcs = [os.path.join(_HERE, f) for f in ("ransac_voting_ref.c", "head_epilogue_ref.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("ransac_voting_ref.c", "head_epilogue_ref.c", "vanishing_point_ref.c")]
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
@@ -40,6 +40,14 @@ def lib() -> ctypes.CDLL:
             f.argtypes = [fp, fp, ip, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
             f.restype = None
         for name in ("fpc_ref_voting_for_hypothesis", "fpc_ref_voting_for_hypothesis_fma"):
+            f = getattr(L, name)
+            f.argtypes = [fp, fp, fp, up, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float]
+            f.restype = None
+        for name in ("fpc_ref_generate_hypothesis_vp", "fpc_ref_generate_hypothesis_vp_fma"):
+            f = getattr(L, name)
+            f.argtypes = [fp, fp, ip, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+            f.restype = None
+        for name in ("fpc_ref_voting_for_hypothesis_vp", "fpc_ref_voting_for_hypothesis_vp_fma"):
             f = getattr(L, name)
             f.argtypes = [fp, fp, fp, up, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float]
             f.restype = None
@@ -87,6 +95,33 @@ class RansacVotingCPU:
         hn = hypo_pts.shape[0]
         if hn * vn * tn:
             getattr(lib(), "fpc_ref_voting_for_hypothesis" + self._sfx)(
+                direct.data_ptr(), coords.data_ptr(), hypo_pts.data_ptr(), inliers.data_ptr(),
+                tn, vn, hn, float(inlier_thresh))
+
+
+    def generate_hypothesis_vanishing_point(self, direct, coords, idxs):
+        """K3 (src/ransac_voting.cpp:62-73): homogeneous hypotheses [hn,vn,3]."""
+        _chk(direct, torch.float32, "direct")
+        _chk(coords, torch.float32, "coords")
+        _chk(idxs, torch.int32, "idxs")
+        tn, vn = direct.shape[0], direct.shape[1]
+        hn = idxs.shape[0]
+        out = torch.zeros((hn, vn, 3), dtype=torch.float32)
+        if hn * vn:
+            getattr(lib(), "fpc_ref_generate_hypothesis_vp" + self._sfx)(
+                direct.data_ptr(), coords.data_ptr(), idxs.data_ptr(), out.data_ptr(), tn, vn, hn)
+        return out
+
+    def voting_for_hypothesis_vanishing_point(self, direct, coords, hypo_pts, inliers, inlier_thresh):
+        """K4 (src/ransac_voting.cpp:83-97): in-place uint8 votes [hn,vn,tn]."""
+        _chk(direct, torch.float32, "direct")
+        _chk(coords, torch.float32, "coords")
+        _chk(hypo_pts, torch.float32, "hypo_pts")
+        _chk(inliers, torch.uint8, "inliers")
+        tn, vn = direct.shape[0], direct.shape[1]
+        hn = hypo_pts.shape[0]
+        if hn * vn * tn:
+            getattr(lib(), "fpc_ref_voting_for_hypothesis_vp" + self._sfx)(
                 direct.data_ptr(), coords.data_ptr(), hypo_pts.data_ptr(), inliers.data_ptr(),
                 tn, vn, hn, float(inlier_thresh))
 

@@ -491,3 +491,150 @@ def upsample_heads(lowres: Dict[str, torch.Tensor], scale: int = 4) -> Dict[str,
 def pose_recover_lowres(lowres, inv_intrinsics, round_hyp_num: int, scale: int = 4, **kw):
     """Reference behaviour for low-resolution head outputs: up-sample every head map, then the path."""
     return pose_recover(upsample_heads(lowres, scale), inv_intrinsics, round_hyp_num, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SURVEY.md section 8f rank 3: the other PVNet drivers built on the same two kernels (ransac_voting_gpu.py)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _class_problem(mask_bi, vertex_bi, k, min_num, max_num):
+    """The shared prologue of every driver (e.g. ransac_voting_gpu.py:117-141): pixels of class id k+1 in raster order,
+    their (x = column, y = row) coordinates and directions.  ``None`` when fewer than ``min_num`` pixels."""
+    cur = mask_bi == k + 1
+    fg = torch.sum(cur)
+    if fg < min_num:
+        return None
+    if fg > max_num:
+        u = torch.zeros(cur.shape, dtype=torch.float32).uniform_(0, 1)
+        cur = cur * (u < (max_num / fg.float()))
+    coords = torch.nonzero(cur).float()[:, [1, 0]]
+    vn = vertex_bi.shape[2]
+    direct = vertex_bi.masked_select(cur.unsqueeze(2).unsqueeze(3)).view([coords.shape[0], vn, 2])
+    return coords, direct
+
+
+def _vote_round(rv, direct, coords, idxs, inlier_thresh):
+    hyp = rv.generate_hypothesis(direct, coords, idxs)
+    inl = torch.zeros([idxs.shape[0], direct.shape[1], direct.shape[0]], dtype=torch.uint8)
+    rv.voting_for_hypothesis(direct, coords, hyp, inl, inlier_thresh)
+    return hyp, inl
+
+
+def ransac_voting_layer_v2(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=30000, refine_iter_num=1, *, idx_source: Optional[IdxSource] = None, kernels=None):
+    """ransac_voting_gpu.py:100-216: v1 followed by ``refine_iter_num`` rounds of "vote for the current point, then
+    least-squares intersection of the inlier rays" (``pinverse(A) @ b``, A = inlier normals, b = normal . pixel)."""
+    rv = kernels or native.ransac_voting
+    if idx_source is None:
+        idx_source = seeded_idx_source()
+    b, h, w, vn, _ = vertex.shape
+    out = torch.zeros((b, class_num - 1, vn, 2), dtype=torch.float32)
+    problem = 0
+    for bi in range(b):
+        for k in range(class_num - 1):
+            prob = _class_problem(mask[bi], vertex[bi], k, min_num, max_num)
+            problem += 1
+            if prob is None:
+                continue
+            coords, direct = prob
+            tn = coords.shape[0]
+            idxs = idx_source(problem - 1, round_hyp_num, vn, tn).contiguous()
+            hyp, inl = _vote_round(rv, direct, coords, idxs, inlier_thresh)       # further passes repeat this one (same idxs)
+            win_counts, win_idx = torch.max(torch.sum(inl, 2), 0)
+            pts = hyp[win_idx, torch.arange(vn)]
+            pts = torch.where((win_counts.float() / tn > 0).unsqueeze(1), pts, torch.zeros_like(pts))   # :166-168, ratio must beat 0
+            normal = torch.stack((direct[:, :, 1], -direct[:, :, 0]), dim=2)
+            for _ in range(refine_iter_num):
+                cur = torch.zeros([1, vn, tn], dtype=torch.uint8)
+                rv.voting_for_hypothesis(direct, coords, pts.unsqueeze(0).contiguous(), cur, inlier_thresh)
+                refined = []
+                for vi in range(vn):
+                    sel = cur[0, vi].bool()
+                    if int(sel.sum()) == 0:
+                        refined.append(torch.zeros([1, 2]))
+                        continue
+                    a_mat = normal[:, vi, :][sel]
+                    rhs = torch.sum(a_mat * coords[sel], 1)
+                    refined.append(torch.matmul(torch.pinverse(a_mat), rhs).unsqueeze(0))
+                pts = torch.cat(refined, 0)
+            out[bi, k] = pts
+    return out
+
+
+def ransac_voting_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, min_num=5, max_num=30000, *,
+                             idx_source: Optional[IdxSource] = None, kernels=None):
+    """ransac_voting_gpu.py:218-261: every hypothesis and its vote count for class id 1 of each image ->
+    ``[b,hn,vn,2]`` float32, ``[b,hn,vn]`` int64 (zeros / ones for images with fewer than ``min_num`` pixels)."""
+    rv = kernels or native.ransac_voting
+    if idx_source is None:
+        idx_source = seeded_idx_source()
+    b, h, w, vn, _ = vertex.shape
+    hyps, counts = [], []
+    for bi in range(b):
+        prob = _class_problem(mask[bi], vertex[bi], 0, min_num, max_num)
+        if prob is None:
+            hyps.append(torch.zeros([1, round_hyp_num, vn, 2], dtype=torch.float32))
+            counts.append(torch.ones([1, round_hyp_num, vn], dtype=torch.int64))
+            continue
+        coords, direct = prob
+        idxs = idx_source(bi, round_hyp_num, vn, coords.shape[0]).contiguous()
+        hyp, inl = _vote_round(rv, direct, coords, idxs, inlier_thresh)
+        hyps.append(hyp.unsqueeze(0))
+        counts.append(torch.sum(inl, 2).unsqueeze(0))
+    return torch.cat(hyps, 0), torch.cat(counts, 0)
+
+
+def _hypothesis_rounds(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num, skip_len, idx_source, rv):
+    """Shared body of the two distribution estimators (:263-312, :333-383): ceil(min_hyp_num / round_hyp_num) rounds of
+    fresh pixel pairs per image -> hypotheses ``[b,vn,H,2]`` and inlier RATIOS (count / voters) ``[b,vn,H]``."""
+    b, h, w, vn, _ = vertex.shape
+    rounds = int(np.ceil(min_hyp_num / round_hyp_num))
+    pts, ratio = [], []
+    for bi in range(b):
+        prob = _class_problem(mask[bi], vertex[bi], 0, min_num, max_num)
+        if prob is None:
+            pts.append(torch.zeros([1, skip_len, vn, 2], dtype=torch.float32))
+            ratio.append(torch.ones([1, skip_len, vn], dtype=torch.float32))
+            continue
+        coords, direct = prob
+        tn = coords.shape[0]
+        p_img, r_img = [], []
+        for r in range(rounds):
+            idxs = idx_source(bi * rounds + r, round_hyp_num, vn, tn).contiguous()
+            hyp, inl = _vote_round(rv, direct, coords, idxs, inlier_thresh)
+            p_img.append(hyp)
+            r_img.append(torch.sum(inl, 2).float() / float(tn))
+        pts.append(torch.cat(p_img, 0).unsqueeze(0))
+        ratio.append(torch.cat(r_img, 0).unsqueeze(0))
+    return torch.cat(pts, 0).permute(0, 2, 1, 3), torch.cat(ratio, 0).permute(0, 2, 1)
+
+
+def estimate_voting_distribution(mask, vertex, round_hyp_num=256, min_hyp_num=4096, topk=128, inlier_thresh=0.99, min_num=5,
+                                 max_num=30000, *, idx_source: Optional[IdxSource] = None, kernels=None):
+    """ransac_voting_gpu.py:263-331: mean and covariance of the hypotheses, weighted by inlier ratio, over the ``topk``
+    best-supported ones -> ``[b,vn,2]``, ``[b,vn,2,2]``."""
+    pts, ratio = _hypothesis_rounds(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num, round_hyp_num,
+                                    idx_source or seeded_idx_source(), kernels or native.ransac_voting)
+    values, indexes = torch.topk(ratio, topk, dim=2, sorted=False)
+    weight = torch.zeros_like(ratio).scatter_(2, indexes, values)
+    total = torch.sum(weight, 2)
+    mean = torch.sum(weight.unsqueeze(3) * pts, 2) / total.unsqueeze(2)
+    diff = pts - mean.unsqueeze(2)
+    cov = torch.matmul(diff.transpose(2, 3), diff * weight.unsqueeze(3)) / total.unsqueeze(2).unsqueeze(3)
+    return mean, cov
+
+
+def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128,
+                                           inlier_thresh=0.99, min_num=5, max_num=30000, output_hyp=False, *,
+                                           idx_source: Optional[IdxSource] = None, kernels=None):
+    """ransac_voting_gpu.py:333-406: covariance about a GIVEN mean; hypotheses whose ratio is more than 0.1 below the best
+    one get weight 0; the normaliser carries +1e-3.  Returns ``(mean, cov)``."""
+    pts, ratio = _hypothesis_rounds(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num, min_hyp_num,
+                                    idx_source or seeded_idx_source(), kernels or native.ransac_voting)
+    ratio = ratio.clone()
+    thresh = torch.max(ratio, 2)[0] - 0.1
+    ratio[ratio < thresh.unsqueeze(2)] = 0.0
+    diff = pts - mean.unsqueeze(2)
+    cov = torch.matmul(diff.transpose(2, 3), diff * ratio.unsqueeze(3))
+    cov = cov / (torch.sum(ratio, 2).unsqueeze(2).unsqueeze(3) + 1e-3)
+    return mean, cov

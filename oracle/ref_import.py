@@ -70,6 +70,8 @@ def load():
     native_mod = types.ModuleType("ransac_voting_gpu_layer.ransac_voting")
     native_mod.generate_hypothesis = native.ransac_voting.generate_hypothesis
     native_mod.voting_for_hypothesis = native.ransac_voting.voting_for_hypothesis
+    native_mod.generate_hypothesis_vanishing_point = native.ransac_voting.generate_hypothesis_vanishing_point
+    native_mod.voting_for_hypothesis_vanishing_point = native.ransac_voting.voting_for_hypothesis_vanishing_point
     sys.modules["ransac_voting_gpu_layer.ransac_voting"] = native_mod
     pkg.ransac_voting = native_mod
 

@@ -1,0 +1,58 @@
+"""CPU, build container only: the oracle restatements of the other PVNet drivers against
+the reference's own ransac_voting_gpu.py imported unmodified, on identical fixed pixel pairs."""
+import pytest
+import torch
+
+import helpers
+from helpers import port, syn
+from oracle import ref_import
+
+pytestmark = [pytest.mark.skipif(not ref_import.available(), reason="reference sources not on this machine"),
+              pytest.mark.filterwarnings("ignore")]
+
+
+def class_scene(vn=1, seed=2):
+    frames = [[(30, 30, 14, 1), (90, 40, 18, 3), (60, 75, 12, 2)], [(40, 50, 20, 1), (100, 30, 9, 2)], [(64, 48, 22, 3)]]
+    logits = syn.render_heads(frames, 96, 128, seed=seed)
+    cat = port.class_compression(logits, 7)
+    vertex = cat["xy"].permute(0, 2, 3, 1).unsqueeze(3)
+    if vn > 1:
+        vertex = torch.cat([vertex, vertex.flip(-1) * torch.tensor([1.0, -1.0])], dim=3)
+    return cat["mask"], vertex.contiguous()
+
+
+@pytest.mark.parametrize("vn", [1, 2])
+def test_v2_equals_reference(vn):
+    ref = ref_import.load()
+    mask, vertex = class_scene(vn)
+    hn = 40
+    a = port.ransac_voting_layer_v2(mask, vertex, 4, hn, idx_source=port.seeded_idx_source(9))
+    with ref_import.fixed_idxs(port.seeded_idx_source(9), hn, vn):
+        b = ref.rvg.ransac_voting_layer_v2(mask, vertex, 4, hn)
+    assert a.shape == b.shape == (3, 3, vn, 2) and torch.equal(a, b)
+
+
+def test_hypothesis_dump_equals_reference():
+    ref = ref_import.load()
+    mask, vertex = class_scene()
+    hn = 48
+    a_h, a_c = port.ransac_voting_hypothesis(mask, vertex, hn, idx_source=port.seeded_idx_source(4))
+    with ref_import.fixed_idxs(port.seeded_idx_source(4), hn):
+        b_h, b_c = ref.rvg.ransac_voting_hypothesis(mask, vertex, hn)
+    assert torch.equal(a_h, b_h) and a_c.dtype == b_c.dtype and torch.equal(a_c, b_c)
+    assert torch.equal(a_c[2], torch.ones_like(a_c[2])) and int(a_h[2].abs().sum()) == 0     # image 2 has no class-1 pixels
+
+
+def test_distribution_estimators_equal_reference():
+    ref = ref_import.load()
+    mask, vertex = class_scene()
+    mask, vertex = mask[:2], vertex[:2]                       # both images have class-1 pixels (see the skip-shape quirk)
+    kw = dict(round_hyp_num=32, min_hyp_num=96, topk=24)
+    a_mean, a_cov = port.estimate_voting_distribution(mask, vertex, idx_source=port.seeded_idx_source(6), **kw)
+    with ref_import.fixed_idxs(port.seeded_idx_source(6), 32):
+        b_mean, b_cov = ref.rvg.estimate_voting_distribution(mask, vertex, **kw)
+    assert torch.equal(a_mean, b_mean) and torch.equal(a_cov, b_cov)
+    _, a_cov2 = port.estimate_voting_distribution_with_mean(mask, vertex, a_mean, idx_source=port.seeded_idx_source(7), **kw)
+    with ref_import.fixed_idxs(port.seeded_idx_source(7), 32):
+        _, b_cov2 = ref.rvg.estimate_voting_distribution_with_mean(mask, vertex, b_mean, **kw)
+    assert torch.equal(a_cov2, b_cov2)
