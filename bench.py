@@ -341,19 +341,45 @@ def run_b200(args):
             dev_in = host
             h2d = bytes_argmax + bytes_gather
 
+        # `--e2e-depth` batches in flight (default 1; with 2, one stream each): while batch k's gather kernel pulls its scattered
+        # foreground rows over PCIe, batch k+1's arg-max streams its mask logits -- the bus stays busy.  Every step still
+        # pays its own host->device traffic and its own device->host read of N and of the pose table.
+        e2e_depth = max(1, args.e2e_depth) if args.e2e_mode == "zerocopy" else 1     # staged copies share one input buffer
+        pipe_e = PoseRecoveryPipeline(e2e_depth, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected),
+                                      multi_stream=e2e_depth > 1)
+        e2e_gather = OverlappedGather(pipe_e.engines, world, dev) if world > 1 else None
+
+        def e2e_after(e):
+            if e2e_gather is not None:
+                e2e_gather.after_launch(e)
+
+        def e2e_before(e):
+            if e2e_gather is not None:
+                e2e_gather.before_reuse(e)
+
+        def e2e_collect(res):
+            eng_o, n_o = res
+            table_host[:n_o].copy_(eng_o.pose_table[:n_o], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return n_o
+
         def e2e_step():
             if args.e2e_mode == "copy":
                 for k in host:
                     dev_in[k].copy_(host[k], non_blocking=True)
-            eng.launch(dev_in, inv_k, idxs=idxs)
-            if gatherer is not None:
-                gather_pose_tables(eng, gatherer.out[id(eng)])
-            n_ = eng.fetch_count()
-            table_host[:n_].copy_(eng.pose_table[:n_], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return n_
-        for _ in range(2):
-            n_ = e2e_step()
+            res = pipe_e.submit(dev_in, inv_k, idxs=idxs, after_launch=e2e_after, before_launch=e2e_before)
+            return e2e_collect(res) if res is not None else None
+
+        def e2e_drain():
+            n_last = None
+            for res in pipe_e.drain():
+                n_last = e2e_collect(res)
+            if e2e_gather is not None:
+                e2e_gather.finish()
+            return n_last
+        for _ in range(2 * e2e_depth):
+            e2e_step()
+        n_ = e2e_drain()
         d2h = n_ * _lib.POSE_ROW * 4 + _lib.NUM_COUNTERS * 4
         ksteps = max(3, min(args.steps, 10))
         if world > 1:
@@ -363,6 +389,7 @@ def run_b200(args):
         s0.record()
         for _ in range(ksteps):
             e2e_step()
+        e2e_drain()
         s1.record()
         torch.cuda.synchronize()
         ems = s0.elapsed_time(s1)
@@ -372,7 +399,7 @@ def run_b200(args):
             ems = float(t.item())
         e2e = {"value": world * bpg / (ems / ksteps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ems / ksteps, "steps": ksteps,
-               "mode": args.e2e_mode,
+               "mode": args.e2e_mode, "batches_in_flight": e2e_depth,
                "note": ("pinned host head maps read in place by the kernels (zero-copy over PCIe: h2d bytes = algorithmic "
                         "28 B/px + 40 B/fg px) -> D2H of N and the pose table, every step" if args.e2e_mode == "zerocopy" else
                         "pinned host head maps -> H2D copy of all 67 channels -> fpc_pose_recover -> D2H of N and the pose table")}
@@ -641,6 +668,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches in the timed loop instead of CUDA-graph replay")
     ap.add_argument("--e2e-mode", default="zerocopy", choices=["zerocopy", "copy"])
+    ap.add_argument("--e2e-depth", type=int, default=1, help="batches in flight in the end-to-end loop (measured: no gain, the loop is PCIe-bound)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-head-epilogue", action="store_true", help="skip the low-resolution-input (SURVEY 8f rank 2) measurements")
     ap.add_argument("--no-matching", action="store_true", help="skip the matching (SURVEY 8f rank 1) measurements")
