@@ -377,9 +377,10 @@ def run_b200(args):
             if e2e_gather is not None:
                 e2e_gather.finish()
             return n_last
+        n_ = None
         for _ in range(2 * e2e_depth):
-            e2e_step()
-        n_ = e2e_drain()
+            n_ = e2e_step() or n_
+        n_ = e2e_drain() or n_
         d2h = n_ * _lib.POSE_ROW * 4 + _lib.NUM_COUNTERS * 4
         ksteps = max(3, min(args.steps, 10))
         if world > 1:

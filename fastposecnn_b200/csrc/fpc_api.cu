@@ -198,26 +198,51 @@ static size_t carve(Workspace &ws, void *base, long long P, long long rows_total
     return (c.off + 255) & ~size_t(255);
 }
 
-// nn.UpsamplingBilinear2d(scale_factor=S), align_corners=True, as a stand-alone operator (thread = 4 output pixels when
-// the output width allows it; write-bound: 4 B per output pixel).
-__global__ void __launch_bounds__(256) k_upsample_bilinear(const float *__restrict__ in, float *__restrict__ out, long long total,
-                                                           int h, int w, UpParams up, int px_per_thread) {
-    const long long hw = (long long)h * w;
-    const size_t lhw = (size_t)up.hl * up.wl;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t * px_per_thread < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long p = t * px_per_thread;
-        const long long plane = p / hw;
-        const int pix = (int)(p - plane * hw);
-        const int y = pix / w, x0 = pix - y * w;
-        const LerpCoord Y = lerp_coord(y, up.sy, up.hl);
-        const float *r0 = in + plane * lhw + (size_t)Y.i0 * up.wl, *r1 = in + plane * lhw + (size_t)Y.i1 * up.wl;
+// nn.UpsamplingBilinear2d(scale_factor=S), align_corners=True, as a stand-alone operator.  Write-bound (4 B per output
+// pixel), so the per-pixel instruction count is what matters: a block owns a strip of 4*blockDim output columns x UP_ROWS output
+// rows of one plane; a thread owns 4 consecutive columns, computes their horizontal coordinates ONCE and reuses them for
+// every row of the strip; for S >= 3 its 4 pixels touch at most 3 low-res columns, so a row costs 6 cached loads, 24 FP32
+// operations and one 16-byte streaming store.
+constexpr int UP_ROWS = 8;
+template <bool THREE_COL>
+__global__ void __launch_bounds__(256) k_upsample_bilinear(const float *__restrict__ in, float *__restrict__ out, int strips_per_plane,
+                                                           int chunks, int h, int w, UpParams up) {
+    const int chunk = blockIdx.x % chunks;
+    const int strip_id = blockIdx.x / chunks;                 // (plane, strip of UP_ROWS rows)
+    const int plane = strip_id / strips_per_plane;
+    const int y0 = (strip_id - plane * strips_per_plane) * UP_ROWS;
+    const int x0 = (chunk * blockDim.x + threadIdx.x) * 4;
+    if (x0 >= w) return;
+    LerpCoord X[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) X[j] = lerp_coord(min(x0 + j, w - 1), up.sx, up.wl);
+    const int cA = X[0].i0, cB = min(cA + 1, up.wl - 1), cC = min(cA + 2, up.wl - 1);
+    const float *src = in + (size_t)plane * up.hl * up.wl;
+    float *dst = out + ((size_t)plane * h + y0) * w + x0;
+    const int rows = min(UP_ROWS, h - y0);
+    for (int r = 0; r < rows; ++r, dst += w) {
+        const LerpCoord Y = lerp_coord(y0 + r, up.sy, up.hl);
+        const float *r0 = src + (size_t)Y.i0 * up.wl, *r1 = src + (size_t)Y.i1 * up.wl;
         float v[4];
-        for (int j = 0; j < px_per_thread; ++j) {
-            const LerpCoord X = lerp_coord(x0 + j, up.sx, up.wl);
-            v[j] = bilerp(__ldg(r0 + X.i0), __ldg(r0 + X.i1), __ldg(r1 + X.i0), __ldg(r1 + X.i1), X.w0, X.w1, Y.w0, Y.w1);
+        if (THREE_COL) {
+            const float a0 = __ldg(r0 + cA), b0 = __ldg(r0 + cB), c0 = __ldg(r0 + cC);
+            const float a1 = __ldg(r1 + cA), b1 = __ldg(r1 + cB), c1 = __ldg(r1 + cC);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool sh = X[j].i0 != cA;
+                v[j] = bilerp(sh ? b0 : a0, sh ? c0 : b0, sh ? b1 : a1, sh ? c1 : b1, X[j].w0, X[j].w1, Y.w0, Y.w1);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = bilerp(__ldg(r0 + X[j].i0), __ldg(r0 + X[j].i1), __ldg(r1 + X[j].i0), __ldg(r1 + X[j].i1), X[j].w0, X[j].w1,
+                              Y.w0, Y.w1);
         }
-        if (px_per_thread == 4) __stcs(reinterpret_cast<float4 *>(out + p), make_float4(v[0], v[1], v[2], v[3]));
-        else out[p] = v[0];
+        if (x0 + 3 < w && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            __stcs(reinterpret_cast<float4 *>(dst), make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+            for (int j = 0; j < 4 && x0 + j < w; ++j) dst[j] = v[j];
+        }
     }
 }
 
@@ -334,11 +359,15 @@ int fpc_upsample_bilinear(const float *in, long long planes, int hl, int wl, int
     if (planes == 0) return FPC_OK;
     if (!in || !out) return fail(FPC_EINVAL, "NULL pointer");
     const int h = hl * scale, w = wl * scale;
-    const long long total = planes * h * w;
     const UpParams up{scale, hl, wl, up_scale(hl, h), up_scale(wl, w)};
-    const int ppt = (w % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 4 : 1;
-    const int grid = (int)std::min<long long>(ceil_div_ll(ceil_div_ll(total, ppt), 256), (long long)sm_count() * 16);
-    k_upsample_bilinear<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, total, h, w, up, ppt);
+    const int threads = std::min(256, ceil_div(ceil_div(w, 4), 32) * 32);      // w = 640 -> 160 threads, no idle lanes
+    const int strips = ceil_div(h, UP_ROWS), chunks = ceil_div(w, 4 * threads);
+    const long long blocks = planes * strips * chunks;
+    if (blocks >= (1ll << 31)) return fail(FPC_EINVAL, "too many planes for one call");
+    if (scale >= 3)
+        k_upsample_bilinear<true><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(in, out, strips, chunks, h, w, up);
+    else
+        k_upsample_bilinear<false><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(in, out, strips, chunks, h, w, up);
     FPC_LAUNCH_CHECK("k_upsample_bilinear");
     return FPC_OK;
 }

@@ -126,14 +126,23 @@ __global__ void __launch_bounds__(256) k_pack_labels(const int *__restrict__ lab
     for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
         const int *__restrict__ src = labels + r * w;
         const int y = (int)(r % h);
-        for (int wi = 0; wi < wpr; ++wi) {
-            const int x = wi * 32 + lane;
-            const int L = x < w ? __ldg(src + x) : 0;
-            if (!__any_sync(FULL, L != 0)) continue;
-            const unsigned group = __match_any_sync(FULL, L);
-            if (L > 0 && L <= n && (__ffs(group) - 1) == lane) {
-                bits[((size_t)(L - 1) * h + y) * wpr + wi] = group;
-                meta_add_row(meta + (size_t)(L - 1) * META, __popc(group), y, wi, wi);
+        constexpr int U = 5;                                   // loads in flight per lane (a 640-px row = 4 batches)
+        for (int base = 0; base < wpr; base += U) {
+            int L[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int x = (base + k) * 32 + lane;
+                L[k] = (base + k < wpr && x < w) ? __ldg(src + x) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (!__any_sync(FULL, L[k] != 0)) continue;
+                const unsigned group = __match_any_sync(FULL, L[k]);
+                if (L[k] > 0 && L[k] <= n && (__ffs(group) - 1) == lane) {
+                    const int wi = base + k;
+                    bits[((size_t)(L[k] - 1) * h + y) * wpr + wi] = group;
+                    meta_add_row(meta + (size_t)(L[k] - 1) * META, __popc(group), y, wi, wi);
+                }
             }
         }
     }
@@ -240,17 +249,21 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_match_best(MaskSet G, cons
 // Output order of the reference: classes ascending (torch.unique, :253), ground-truth index ascending inside a class.
 __global__ void __launch_bounds__(256) k_match_order(const long long *__restrict__ class_g, const int *__restrict__ best_pred, int ng,
                                                      int *__restrict__ pairs, int *__restrict__ n_matches) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ng || best_pred[i] < 0) return;
+    // warp per matched ground truth: its rank = number of matched ground truths that sort before it
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= ng || best_pred[i] < 0) return;               // warp-uniform
     const long long c = class_g[i];
     int rank = 0;
-    for (int k = 0; k < ng; ++k) {
+    for (int k = lane; k < ng; k += 32) {
         const long long ck = class_g[k];
         rank += (best_pred[k] >= 0) && (ck < c || (ck == c && k < i));
     }
-    pairs[2 * rank] = i;
-    pairs[2 * rank + 1] = best_pred[i];
-    atomicAdd(n_matches, 1);
+    rank = __reduce_add_sync(FULL, rank);
+    if (lane == 0) {
+        pairs[2 * rank] = i;
+        pairs[2 * rank + 1] = best_pred[i];
+        atomicAdd(n_matches, 1);
+    }
 }
 
 // Dense [m,h,w] f32 0/1 masks of the listed instances (row k: instance inst_of[k] of frame frame_of[k]) painted from the
@@ -360,7 +373,7 @@ int fpc_match_instances(const uint32_t *bits_g, const int32_t *meta_g, const int
     k_match_best<<<ng, MATCH_WARPS * 32, 0, st>>>(MaskSet{bits_g, meta_g}, (const long long *)class_g, MaskSet{bits_p, meta_p},
                                                   (const long long *)class_p, np, h, (w + 31) / 32, best_pred, best_iou);
     FPC_LAUNCH_CHECK("k_match_best");
-    k_match_order<<<ceil_div(ng, 256), 256, 0, st>>>((const long long *)class_g, best_pred, ng, pairs, n_matches);
+    k_match_order<<<ceil_div(ng, 8), 256, 0, st>>>((const long long *)class_g, best_pred, ng, pairs, n_matches);
     FPC_LAUNCH_CHECK("k_match_order");
     return FPC_OK;
 }
