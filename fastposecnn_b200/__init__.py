@@ -15,8 +15,10 @@ non-CUDA tensor raises.
 from . import synthetic  # noqa: F401  (pure torch, importable without the native library)
 from .aggregation_layer import AggregationLayer  # noqa: F401
 from . import head_epilogue, matching  # noqa: F401
-from .gpu_tensor_funcs import (batchwise_get_2d_iou, batchwise_get_RT, class_compress, class_compression,  # noqa: F401
-                               normalize, quats_2_rotation_matrix, samplewise_get_RT, torch_get_2d_iou)
+from .gpu_tensor_funcs import (batchwise_get_2d_iou, batchwise_get_RT, calculate_aps, class_compress,  # noqa: F401
+                               class_compression, from_Ts_get_offset_error, get_3d_iou, get_3d_ious, get_quat_distance,
+                               get_raw_quat_distance, get_symmetric_quat_distance, normalize, quats_2_rotation_matrix,
+                               samplewise_get_RT, torch_get_2d_iou)
 from .matching import batchwise_find_matches, batchwise_find_matches2  # noqa: F401
 from .head_epilogue import lowres_logits, split_xyz, upsample_bilinear  # noqa: F401
 from .hough_voting import HoughVotingLayer  # noqa: F401

@@ -124,3 +124,125 @@ def batchwise_get_2d_iou(batch_masks1: torch.Tensor, batch_masks2: torch.Tensor)
 def torch_get_2d_iou(tensor1: torch.Tensor, tensor2: torch.Tensor) -> torch.Tensor:
     """lib/gpu_tensor_funcs.py:380-384 -- IoU of two ``[h,w]`` masks, a 0-d float32 tensor."""
     return batchwise_get_2d_iou(tensor1.reshape(1, *tensor1.shape[-2:]), tensor2.reshape(1, *tensor2.shape[-2:]))[0, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Evaluation maths on matched pairs (SURVEY.md section 8f rank 4): one launch of fpc_pose_errors instead of a Python loop
+# ---------------------------------------------------------------------------------------------------------------------
+_SYM_ROTATIONS: Dict[str, torch.Tensor] = {}
+
+
+def _symmetry_rotations(device) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:762-780: the 360 quaternions (w, 0, y, 0) of 0..359 degrees about y, built in float32 on
+    the host exactly like the reference's cached ``rot_q``, then widened -- [360,4] float64 on ``device``."""
+    key = str(device)
+    if key not in _SYM_ROTATIONS:
+        half = torch.deg2rad(torch.arange(0, 360).float()) / 2
+        s, c = torch.sin(half), torch.cos(half)
+        _SYM_ROTATIONS[key] = torch.vstack((c, 0 * s, 1 * s, 0 * s)).T.double().contiguous().to(device)
+    return _SYM_ROTATIONS[key]
+
+
+def _pose_errors(q0=None, q1=None, symmetric_ids=None, rts=None, scales=None, ts=None, want_raw=False, want_sym=False):
+    f32 = torch.float32
+    ref = q0 if q0 is not None else (rts[0] if rts is not None else ts[0])
+    dev, m = ref.device, int(ref.shape[0])
+
+    def chk(t, name, shape):
+        t = _lib.require_cuda(t.contiguous(), name, f32)
+        if tuple(t.shape) != (m,) + shape:
+            raise RuntimeError(f"{name} must be [{m},{','.join(map(str, shape))}], got {tuple(t.shape)}")
+        return t
+    out = {}
+    args = [None] * 10
+    if q0 is not None:
+        args[0], args[1] = chk(q0, "q0", (4,)), chk(q1, "q1", (4,))
+        if symmetric_ids is not None:
+            args[2] = _lib.require_cuda(symmetric_ids.to(torch.int64).contiguous(), "symmetric_ids")
+        if want_sym:
+            args[3] = _symmetry_rotations(dev)
+            out["sym"] = torch.empty((m,), dtype=torch.float64, device=dev)
+        if want_raw:
+            out["raw"] = torch.empty((m,), dtype=f32, device=dev)
+    if rts is not None:
+        args[4], args[5] = chk(rts[0], "RTs_1", (4, 4)), chk(rts[1], "RTs_2", (4, 4))
+        args[6], args[7] = chk(scales[0], "scales_1", (3,)), chk(scales[1], "scales_2", (3,))
+        out["iou"] = torch.empty((m,), dtype=f32, device=dev)
+    if ts is not None:
+        args[8], args[9] = chk(ts[0], "gt_Ts", (3,)), chk(ts[1], "pred_Ts", (3,))
+        out["offset"] = torch.empty((m,), dtype=f32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fpc_pose_errors(*[_lib.ptr(a) for a in args], m, _lib.ptr(out.get("raw")), _lib.ptr(out.get("sym")),
+                                              _lib.ptr(out.get("iou")), _lib.ptr(out.get("offset")), _lib.current_stream(dev)))
+    return out
+
+
+def get_raw_quat_distance(q0: torch.Tensor, q1: torch.Tensor) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:434-455 -- ``[n]`` float32; ``tensor([nan])`` for no data."""
+    if q0.shape[0] == 0:
+        return torch.tensor([float("nan")], device=q0.device)
+    return _pose_errors(q0, q1, want_raw=True)["raw"]
+
+
+def get_symmetric_quat_distance(q0: torch.Tensor, q1: torch.Tensor) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:457-476 -- ``[n]`` float64: the smallest distance over 360 rotations of q1 about y."""
+    if q0.shape[0] == 0:
+        return torch.tensor([float("nan")], device=q0.device)
+    return _pose_errors(q0, q1, want_sym=True)["sym"]
+
+
+def get_quat_distance(q0, q1, symmetric_ids=None):
+    """lib/gpu_tensor_funcs.py:411-432 -- non-symmetric pairs first, then symmetric ones, NaNs dropped (the reference's
+    output order, not the input order)."""
+    if symmetric_ids is None:
+        return get_raw_quat_distance(q0, q1)
+    if q0.shape[0] == 0:
+        return torch.zeros((0,), dtype=torch.float32, device=q0.device)
+    res = _pose_errors(q0, q1, symmetric_ids, want_raw=True, want_sym=True)
+    is_sym = symmetric_ids != 0
+    nan = torch.tensor([float("nan")], device=q0.device)
+    plain = res["raw"][~is_sym] if bool((~is_sym).any()) else nan
+    sym = res["sym"][is_sym] if bool(is_sym.any()) else nan
+    d = torch.cat((plain, sym), dim=0)
+    return d[~torch.isnan(d)]
+
+
+def get_3d_ious(RTs_1, RTs_2, scales_1, scales_2) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:540-549 (+ :503-530) -- ``[n]`` float32, one launch instead of a Python loop with two 4x4
+    inversions per pair."""
+    if RTs_1.shape[0] == 0:
+        return torch.stack([])          # what the reference's torch.stack([]) does: raises
+    return _pose_errors(rts=(RTs_1, RTs_2), scales=(scales_1, scales_2))["iou"]
+
+
+def get_3d_iou(RT_1, RT_2, scales_1, scales_2) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:532-538 (symmetry flag off, as in the reference) -- a 0-d tensor."""
+    return get_3d_ious(RT_1.unsqueeze(0), RT_2.unsqueeze(0), scales_1.unsqueeze(0), scales_2.unsqueeze(0))[0]
+
+
+def from_Ts_get_offset_error(gt_Ts, pred_Ts) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:565-567 -- ``|gt - pred| * 10`` per pair."""
+    if gt_Ts.shape[0] == 0:
+        return torch.zeros((0,), dtype=torch.float32, device=gt_Ts.device)
+    return _pose_errors(ts=(gt_Ts, pred_Ts))["offset"]
+
+
+def calculate_aps(raw_data, metrics_threshold, metrics_operator):
+    """lib/gpu_tensor_funcs.py:611-652 -- per metric and class the fraction of non-NaN values passing each threshold
+    (``torch.less`` / ``torch.lt`` or ``torch.greater`` / ``torch.gt``), plus the mean over classes."""
+    ops = {torch.less: 0, torch.lt: 0, torch.greater: 1, torch.gt: 1}
+    aps = {}
+    for key, per_class in raw_data.items():
+        if metrics_operator[key] not in ops:
+            raise NotImplementedError("calculate_aps: operator must be torch.less or torch.greater")
+        aps[key] = {}
+        for class_id, values in per_class.items():
+            v = _lib.require_cuda(values.double().contiguous(), f"raw_data[{key}][{class_id}]")
+            t = metrics_threshold[key].to(v.device).double().contiguous()
+            out = torch.empty((t.shape[0],), dtype=torch.float32, device=v.device)
+            with torch.cuda.device(v.device):
+                _lib.check(_lib.lib().fpc_threshold_fraction(v.data_ptr(), int(v.shape[0]), t.data_ptr(), int(t.shape[0]),
+                                                             ops[metrics_operator[key]], out.data_ptr(), _lib.current_stream(v.device)))
+            aps[key][class_id] = out
+        aps[key]["mean"] = torch.mean(torch.stack(list(aps[key].values())).float(), dim=0)
+    return aps

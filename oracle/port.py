@@ -638,3 +638,93 @@ def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256
     cov = torch.matmul(diff.transpose(2, 3), diff * ratio.unsqueeze(3))
     cov = cov / (torch.sum(ratio, 2).unsqueeze(2).unsqueeze(3) + 1e-3)
     return mean, cov
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# evaluation maths on matched pairs (lib/gpu_tensor_funcs.py:411-476, 503-578, 611-652, 752-799)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def get_raw_quat_distance(q0: torch.Tensor, q1: torch.Tensor) -> torch.Tensor:
+    """gpu_tensor_funcs.py:434-455: min(|q0 - q1|, |q0 + q1|) converted with rad2deg (q and -q are one rotation);
+    ``tensor([nan])`` for no data."""
+    if q0.shape[0] == 0:
+        return torch.tensor([float("nan")])
+    return torch.rad2deg(torch.minimum((q0 - q1).norm(dim=-1), (q0 + q1).norm(dim=-1)))
+
+
+def symmetry_rotations() -> torch.Tensor:
+    """gpu_tensor_funcs.py:762-780: the 360 unit quaternions (w, 0, y, 0) of 0..359 degrees about the y axis, built in
+    float32 exactly like the reference's cached ``rot_q``."""
+    half = torch.deg2rad(torch.arange(0, 360).float()) / 2
+    s, c = torch.sin(half), torch.cos(half)
+    return torch.vstack((c, 0 * s, 1 * s, 0 * s)).T
+
+
+def get_symmetric_quat_distance(q0: torch.Tensor, q1: torch.Tensor) -> torch.Tensor:
+    """gpu_tensor_funcs.py:457-476 + quat_symmetric_tf :752-799: the smallest raw distance between q0 and q1 composed
+    with each of the 360 rotations; the composition runs in float64 and is re-normalised by a norm rounded to float32
+    (``normalize`` :37-50 casts the norm with ``.float()``), so the result is float64."""
+    if q0.shape[0] == 0:
+        return torch.tensor([float("nan")])
+    r = symmetry_rotations().double().unsqueeze(0)                       # [1,360,4]
+    a = q1.double().unsqueeze(1)                                         # [n,1,4]
+    aw, ax, ay, az = a.unbind(-1)
+    bw, bx, by, bz = r.unbind(-1)
+    prod = torch.stack((aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                        aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw), -1)
+    rot = normalize(prod, dim=-1)
+    e_q0 = q0.unsqueeze(1).expand(q0.shape[0], 360, 4)
+    return torch.min(get_raw_quat_distance(e_q0, rot), dim=-1).values
+
+
+def get_quat_distance(q0, q1, symmetric_ids=None):
+    """gpu_tensor_funcs.py:411-432: non-symmetric pairs first (raw distance), then symmetric pairs (symmetric distance),
+    NaNs dropped -- the output is NOT in the input order."""
+    if symmetric_ids is None:
+        return get_raw_quat_distance(q0, q1)
+    plain, sym = torch.where(symmetric_ids == 0)[0], torch.where(symmetric_ids != 0)[0]
+    d = torch.cat((get_raw_quat_distance(q0[plain], q1[plain]), get_symmetric_quat_distance(q0[sym], q1[sym])), dim=0)
+    return d[~torch.isnan(d)]
+
+
+def get_3d_ious(rts_1, rts_2, scales_1, scales_2) -> torch.Tensor:
+    """gpu_tensor_funcs.py:503-547: per pair, the 8 corners of each scaled unit cube go through inverse(RT) and are
+    de-homogenised; then -- as written in the reference -- ``amax/amin(dim=0)`` reduce over the COORDINATE axis of the
+    [3,8] corner matrix, so the "box" compared has 8 extents, one per corner; IoU = prod(overlap) / union of prods."""
+    cube = torch.tensor([[1, 1, 1], [1, 1, -1], [-1, 1, 1], [-1, 1, -1], [1, -1, 1], [1, -1, -1], [-1, -1, 1], [-1, -1, -1]],
+                        dtype=scales_1.dtype) / 2
+
+    def corners(rt, scales):
+        pts = (cube * scales.unsqueeze(0)).T                                       # [3,8]
+        hom = torch.vstack([pts, torch.ones((1, 8), dtype=pts.dtype)])
+        world = torch.inverse(rt) @ hom
+        return world[:-1, :] / world[-1, :]
+    out = []
+    for i in range(rts_1.shape[0]):
+        b1, b2 = corners(rts_1[i], scales_1[i]), corners(rts_2[i], scales_2[i])
+        max1, min1, max2, min2 = b1.amax(dim=0), b1.amin(dim=0), b2.amax(dim=0), b2.amin(dim=0)
+        ext = torch.minimum(max1, max2) - torch.maximum(min1, min2)
+        inter = torch.prod(ext) if torch.amin(ext) >= 0 else torch.zeros(())
+        union = torch.prod(max1 - min1) + torch.prod(max2 - min2) - inter
+        out.append(inter / union)
+    return torch.stack(out)
+
+
+def from_Ts_get_offset_error(gt_ts, pred_ts) -> torch.Tensor:
+    """gpu_tensor_funcs.py:565-567: Euclidean distance of the translations, times 10."""
+    return torch.linalg.norm(gt_ts - pred_ts, dim=1) * 10
+
+
+def calculate_aps(raw_data, metrics_threshold, metrics_operator):
+    """gpu_tensor_funcs.py:611-652: per metric and class, the fraction of (non-NaN) values that pass each threshold
+    under the metric's comparison operator, plus the mean over classes."""
+    aps = {}
+    for key, per_class in raw_data.items():
+        thresholds, op = metrics_threshold[key], metrics_operator[key]
+        aps[key] = {}
+        for class_id, values in per_class.items():
+            values = values[~torch.isnan(values)]
+            hits = op(values.unsqueeze(0), thresholds.unsqueeze(1))
+            aps[key][class_id] = torch.sum(hits, dim=1) / values.shape[0]
+        aps[key]["mean"] = torch.mean(torch.stack(list(aps[key].values())).float(), dim=0)
+    return aps
