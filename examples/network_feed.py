@@ -6,6 +6,10 @@ FPN decoders, four 1x1 heads, xyz split into xy / z per class, :729-732) with to
 `segmentation_models_pytorch` is not installed here.
 
     python examples/network_feed.py [--batch 64] [--steps 5]      # frames/s of network + path on one GPU
+
+Two flows are timed: the reference's (heads up-sample all 67 channels x4 with nn.UpsamplingBilinear2d, then the
+full-resolution path) and the fused one (only the heads' 1x1 convolutions run in torch; the path interpolates inside its
+kernels).
 """
 from __future__ import annotations
 
@@ -45,17 +49,28 @@ class TorchFeeder(nn.Module):
         k = num_classes - 1
         self.k = k
         self.decoders = nn.ModuleList(_FPNDecoder() for _ in range(4))
-        self.heads = nn.ModuleList(nn.Conv2d(64, c, 1) for c in (num_classes, 4 * k, 3 * k, 3 * k))
+        # smp's SegmentationHead (lib/pose_regressor.py:633-666): Conv2d(k=1) -> UpsamplingBilinear2d(x4) -> identity
+        self.heads = nn.ModuleList(nn.Sequential(nn.Conv2d(64, c, 1), nn.UpsamplingBilinear2d(scale_factor=4), nn.Identity())
+                                   for c in (num_classes, 4 * k, 3 * k, 3 * k))
 
-    def forward(self, x):
-        h, w = x.shape[-2:]
+    def decode(self, x):
+        """The four decoder outputs at 1/4 resolution (mask, rotation, translation, scales)."""
         f = self.stem(x)
         feats = []
         for layer in self.layers:
             f = layer(f)
             feats.append(f)
-        outs = [F.interpolate(head(dec(feats)), size=(h, w), mode="bilinear", align_corners=False)
-                for dec, head in zip(self.decoders, self.heads)]
+        return [dec(feats) for dec in self.decoders]
+
+    def lowres(self, x):
+        """Head convolutions only: the low-resolution LogitData for ``pose_recover(..., upsample=4)``."""
+        from fastposecnn_b200 import lowres_logits
+        d = self.decode(x)
+        names = ("mask", "rotation", "translation", "scales")
+        return lowres_logits(dict(zip(names, self.heads)), dict(zip(names, d)))
+
+    def forward(self, x):
+        outs = [head(d) for head, d in zip(self.heads, self.decode(x))]
         mask, quat, xyz, scales = outs
         idx = torch.arange(3 * self.k, device=x.device)
         xy = xyz[:, idx[idx % 3 != 2]]            # channels 3k, 3k+1 (lib/pose_regressor.py:729-732)
@@ -77,23 +92,26 @@ def main():
     net = TorchFeeder().to(dev).eval()
     imgs = torch.randn(args.batch, 3, 480, 640, device=dev)
     inv_k = torch.inverse(syn.camera_intrinsics()).to(dev).contiguous()
-    eng = PoseRecoveryEngine(args.batch, 480, 640, 7, args.hn, dev, max_instances=65536)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    tn = tp = 0.0
-    with torch.no_grad():
-        for it in range(args.steps + 2):
-            ev[0].record()
-            logits = net(imgs)
-            ev[1].record()
-            eng.launch(logits, inv_k)
-            n = eng.fetch_count()
-            ev[2].record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                tn += ev[0].elapsed_time(ev[1])
-                tp += ev[1].elapsed_time(ev[2])
-    print(f"batch {args.batch}: network {tn / args.steps:.2f} ms, pose recovery {tp / args.steps:.3f} ms ({n} instances), "
-          f"{args.batch / ((tn + tp) / args.steps * 1e-3):.0f} frames/s end to end")
+    for fused in (False, True):
+        eng = PoseRecoveryEngine(args.batch, 480, 640, 7, args.hn, dev, max_instances=65536, upsample=4 if fused else 1)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tn = tp = 0.0
+        with torch.no_grad():
+            for it in range(args.steps + 2):
+                ev[0].record()
+                logits = net.lowres(imgs) if fused else net(imgs)
+                ev[1].record()
+                eng.launch(logits, inv_k)
+                n = eng.fetch_count()
+                ev[2].record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    tn += ev[0].elapsed_time(ev[1])
+                    tp += ev[1].elapsed_time(ev[2])
+        flow = "fused head epilogue (convs only + low-res path)" if fused else "reference flow (x4 up-sampled heads + path)     "
+        print(f"batch {args.batch} {flow}: network {tn / args.steps:.2f} ms, pose recovery {tp / args.steps:.3f} ms "
+              f"({n} instances), {args.batch / ((tn + tp) / args.steps * 1e-3):.0f} frames/s end to end")
+        del eng
 
 
 if __name__ == "__main__":

@@ -43,3 +43,25 @@ def test_random_init_network_feeds_the_path():
     for k in ("quaternion", "scales", "z"):
         assert helpers.rel_err(out[k], agg[k]) <= helpers.REL_TOL, k
     assert torch.isfinite(out["RT"]).all() and torch.isfinite(out["xy"]).all()
+
+
+def test_fused_head_epilogue_equals_upsampled_flow_on_network_outputs():
+    """The same random-init network, two flows on the GPU: heads up-sampled by torch then the full-resolution path, and
+    head convolutions only + the low-resolution path.  Class map, labels and every instance table must be identical."""
+    pytest.importorskip("torchvision")
+    from network_feed import TorchFeeder
+    import fastposecnn_b200 as fp
+    torch.manual_seed(1)
+    net = TorchFeeder().to(DEV).eval()
+    imgs = torch.randn(2, 3, 96, 128, device=DEV)
+    with torch.no_grad():
+        low = net.lowres(imgs)
+        # spread the mask logits so that several classes win somewhere (at LOW resolution: both flows see the same values)
+        low["mask"] = (low["mask"] - low["mask"].mean(dim=(2, 3), keepdim=True)) * 8
+        full = {k: torch.nn.UpsamplingBilinear2d(scale_factor=4)(v) for k, v in low.items()}
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
+    a = {k: v.clone() for k, v in fp.pose_recover(full, inv_k, 32).items()}
+    b = fp.pose_recover(low, inv_k, 32, upsample=4)
+    assert a["class_ids"].shape[0] >= 1
+    for k in ("cat_mask", "labels", "class_ids", "sample_ids", "mask_sizes", "quaternion", "scales", "z"):
+        assert torch.equal(a[k], b[k]), k
