@@ -31,7 +31,7 @@ EXPORTS = (
     "fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances",
     "fpc_pack_masks", "fpc_pack_labels", "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances", "fpc_upsample_bilinear",
     "fpc_generate_hypothesis_vanishing_point", "fpc_voting_for_hypothesis_vanishing_point",
-    "fpc_pose_errors", "fpc_threshold_fraction",
+    "fpc_pose_errors", "fpc_threshold_fraction", "fpc_label_instances",
 )
 MASK_META = 8
 MASK_F32, MASK_U8 = 0, 1
@@ -92,6 +92,8 @@ def lib() -> ctypes.CDLL:
     L.fpc_bench_fp32_fma.argtypes = [_vp, _i, _i, _vp]
     L.fpc_bench_fp32_fma.restype = _i
     L.fpc_aggregate.argtypes = [ctypes.POINTER(RecoverArgs), _vp]
+    L.fpc_label_instances.argtypes = [ctypes.POINTER(RecoverArgs), _vp]
+    L.fpc_label_instances.restype = _i
     L.fpc_vote_dense.argtypes = [ctypes.POINTER(RecoverArgs), _vp, _vp, _i, _i, _vp, _ll, _ll, _ll, _ll, _i]
     L.fpc_materialize_instances.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]
     L.fpc_pack_masks.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp]

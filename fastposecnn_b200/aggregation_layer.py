@@ -122,12 +122,9 @@ class AggregationLayer(nn.Module):
         b, h, w = class_mask.shape
         dev = class_mask.device
         cat = (class_mask != 0).to(torch.int64).contiguous()
-        zeros = lambda c: torch.zeros((b, c, h, w), dtype=torch.float32, device=dev)  # noqa: E731
-        q, s, xy, z = zeros(4), zeros(3), zeros(2), torch.zeros((b, h, w), dtype=torch.float32, device=dev)
         cap = self.max_instances or max(1024, 128 * b)
         with torch.cuda.device(dev):
             a, bufs = _pipeline_args(b, h, w, 2, 1, cap, dev)
-            a.quaternion, a.scales, a.xy, a.z = q.data_ptr(), s.data_ptr(), xy.data_ptr(), z.data_ptr()
-            _lib.check(_lib.lib().fpc_aggregate(ctypes.byref(a), cat.data_ptr()))
+            _lib.check(_lib.lib().fpc_label_instances(ctypes.byref(a), cat.data_ptr()))
             n = _read_count(bufs, cap)
         return bufs["labels"], n

@@ -439,6 +439,18 @@ int fpc_aggregate(const fpc_recover_args *a, const int64_t *cat_mask) {
     return rc;
 }
 
+int fpc_label_instances(const fpc_recover_args *a, const int64_t *cat_mask) {
+    Workspace ws;
+    PathParams pp;
+    int rc = setup(a, ws, pp);
+    if (rc != FPC_OK) return rc;
+    if (!cat_mask || !a->labels) return fail(FPC_EINVAL, "NULL cat_mask / labels pointer");
+    cudaStream_t st = (cudaStream_t)a->stream;
+    rc = launch_label_and_tables(ws, pp, nullptr, reinterpret_cast<const long long *>(cat_mask), st);
+    if (rc == FPC_OK) rc = launch_relabel(ws, pp, a->labels, st);
+    return rc;
+}
+
 int fpc_vote_dense(const fpc_recover_args *a, const float *fmask, const int32_t *imask, int nplanes_per_src,
                    int match_base, const float *vertex, long long sN, long long sH, long long sW, long long s2, int refine) {
     Workspace ws;

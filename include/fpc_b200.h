@@ -203,6 +203,13 @@ FPC_API int fpc_pose_recover(const fpc_recover_args *args);
  * workspace); nothing votes.  Same workspace size as fpc_pose_recover. */
 FPC_API int fpc_aggregate(const fpc_recover_args *args, const int64_t *cat_mask);
 
+/* Labelling only: AggregationLayer.batchwise_break_segmentation_mask (lib/aggregation_layer.py:160-183, scipy / cupyx
+ * ndimage.label with the no-cross-image 4-connected structure of :43-59).  cat_mask [b,h,w] i64 (non-zero = foreground)
+ * -> args->labels [b,h,w] i32 (0 = background, k = k-th component in raster order of first pixels, image 0 first) and
+ * counters[FPC_CNT_INSTANCES] = number of components.  Uses args->{b,h,w,max_instances,max_rows,workspace,stream}; the
+ * head-map pointers are not read.  Same workspace size as fpc_pose_recover. */
+FPC_API int fpc_label_instances(const fpc_recover_args *args, const int64_t *cat_mask);
+
 /* ransac_voting_layer_v3 / ransac_voting_layer (lib/ransac_voting_gpu_layer/ransac_voting_gpu.py:518-607,
  * :11-98) on dense masks.  args->b is the number of voting problems (v3: instances; v1: images x
  * (class_num-1)), args->h/w the plane size.  Problem j votes with the pixels of
