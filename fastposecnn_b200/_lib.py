@@ -54,6 +54,7 @@ class RecoverArgs(ctypes.Structure):
         ("workspace", _vp), ("workspace_bytes", ctypes.c_size_t), ("stream", _vp),
         ("stage_events", ctypes.POINTER(_vp)), ("num_stage_events", ctypes.c_int32),
         ("upsample", ctypes.c_int32),
+        ("extra_out", _vp),
     ]
 
 

@@ -411,6 +411,7 @@ static int setup(const fpc_recover_args *a, Workspace &ws, PathParams &pp) {
     pp.arith = a->arith; pp.seed = a->seed; pp.idxs = a->idxs; pp.select_u = a->select_u;
     pp.refine = 1;
     pp.up = UpParams{0, a->h, a->w, 0.f, 0.f};
+    pp.extra = a->extra_out;
     return FPC_OK;
 }
 

@@ -59,6 +59,7 @@ struct PathParams {
     const float *select_u;       // [b,h,w] or nullptr
     int refine;                  // 1: inlier refinement (v3); 0: winning hypothesis as is (v1)
     UpParams up;                 // head-epilogue fusion: head maps are low resolution, x up.s bilinear on the fly
+    float *extra;                // [max_instances,2] (v4 residual variance, v5 confidence at 0.999) or nullptr
 };
 
 // Voting records as four SoA planes, instance-major, raster order inside an instance; every instance's range

@@ -552,6 +552,7 @@ __global__ void __launch_bounds__(FT) k_finalize(InstTables T, RowTables R, cons
     __shared__ double s_d[FT / 32][13];
     __shared__ int s_i[FT / 32][3];
     __shared__ float s_win[2];
+    __shared__ float s_ref[2];
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -669,6 +670,48 @@ __global__ void __launch_bounds__(FT) k_finalize(InstTables T, RowTables R, cons
             row[FPC_ROW_TN] = __int_as_float(tn);
             row[FPC_ROW_REFINE_INL] = __int_as_float(inl);
             row[FPC_ROW_BBOX] = __int_as_float((T.ymin[i] << 16) | (T.xmin[i] & 0xffff));
+            s_ref[0] = x;
+            s_ref[1] = y;
+        }
+        if (pp.extra) {
+            // ---- PVNet v4 / v5 extras: one more pass over the records with the refined point
+            __syncthreads();
+            const float rx = s_ref[0], ry = s_ref[1];
+            double ss = 0.0;
+            int nin = 0, nconf = 0;
+            for (int k4 = tid * 4; k4 < tn; k4 += FT * 4) {
+                const float4 X = *reinterpret_cast<const float4 *>(rec.x + rb + k4);
+                const float4 Y = *reinterpret_cast<const float4 *>(rec.y + rb + k4);
+                const float4 NX = *reinterpret_cast<const float4 *>(rec.nx + rb + k4);
+                const float4 NY = *reinterpret_cast<const float4 *>(rec.ny + rb + k4);
+                const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w};
+                const float nxs[4] = {NX.x, NX.y, NX.z, NX.w}, nys[4] = {NY.x, NY.y, NY.z, NY.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (k4 + j >= tn) continue;
+                    if (vote_exact<ARITH>(xs[j], ys[j], nxs[j], nys[j], wx, wy, pp.inlier_thresh)) {
+                        // residual of the inlier's line equation at the refined point (ransac_voting_gpu.py:757-758)
+                        const double nx = nys[j], ny = -(double)nxs[j];
+                        const double res = nx * ((double)rx - xs[j]) + ny * ((double)ry - ys[j]);
+                        ss += res * res;
+                        ++nin;
+                    }
+                    nconf += vote_exact<ARITH>(xs[j], ys[j], nxs[j], nys[j], rx, ry, 0.999f);   // :855-856
+                }
+            }
+            ss = warp_sum_d(ss);
+            nin = __reduce_add_sync(FULL, nin);
+            nconf = __reduce_add_sync(FULL, nconf);
+            __syncthreads();                       // s_d / s_i of the main pass were consumed by thread 0 above
+            if (lane == 0) { s_d[wv][0] = ss; s_i[wv][0] = nin; s_i[wv][1] = nconf; }
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                int a = 0, c = 0;
+                for (int wq = 0; wq < FT / 32; ++wq) { tot += s_d[wq][0]; a += s_i[wq][0]; c += s_i[wq][1]; }
+                pp.extra[2 * (size_t)i] = tn > 0 ? (float)(tot / (double)a) : 1.f;         // v4 skip value: ones (:696)
+                pp.extra[2 * (size_t)i + 1] = tn > 0 ? (float)c / (float)tn : 0.f;           // v5 skip value: zeros (:793)
+            }
         }
     }
 }

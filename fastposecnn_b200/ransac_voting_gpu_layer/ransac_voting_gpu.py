@@ -1,7 +1,8 @@
 """Drop-in for the PVNet drivers of lib/ransac_voting_gpu_layer/ransac_voting_gpu.py: ``ransac_voting_layer_v3``
 (:518-607, the one HoughVotingLayer calls), ``ransac_voting_layer`` (v1, :11-98), ``b_inv`` (:503-516) and, from the
 "next" rows, ``ransac_voting_layer_v2`` (:100), ``ransac_voting_hypothesis`` (:218), ``estimate_voting_distribution``
-(:263) and ``estimate_voting_distribution_with_mean`` (:333).  (``ransac_voting_vanish_point_layer`` :408 references an
+(:263), ``estimate_voting_distribution_with_mean`` (:333), ``ransac_voting_layer_v4`` (:678, + residual variance) and
+``ransac_voting_layer_v5`` (:771, + confidence).  (``ransac_voting_vanish_point_layer`` :408 references an
 undefined ``class_num`` and cannot run in the reference; its two kernels are mirrored in ``ransac_voting.py``.)
 
 Same positional/keyword signatures and result layouts.  Instead of a Python loop with ~40 small
@@ -45,6 +46,9 @@ def _vote(nprob, h, w, vn, fmask, imask, nplanes_per_src, match_base, vertex, ro
             hyp = torch.empty((nprob, round_hyp_num, 2), dtype=torch.float32, device=dev)
             votes = torch.empty((nprob, round_hyp_num), dtype=torch.int32, device=dev)
             a.hyp_out, a.vote_counts_out = hyp.data_ptr(), votes.data_ptr()
+            extra = torch.empty((nprob, 2), dtype=torch.float32, device=dev) if details is not None else None
+            if extra is not None:
+                a.extra_out = extra.data_ptr()
             keep = []
             if idxs is not None:
                 ix = idxs[:, :, vi, :].contiguous()
@@ -65,7 +69,8 @@ def _vote(nprob, h, w, vn, fmask, imask, nplanes_per_src, match_base, vertex, ro
             details.append({"hyp": hyp, "counts": votes, "win_idx": ti[:, _lib.ROW_WIN_IDX].clone(),
                             "win_counts": ti[:, _lib.ROW_WIN_COUNT].clone(), "tn": ti[:, _lib.ROW_TN].clone(),
                             "best_pts": table[:, _lib.ROW_HYP:_lib.ROW_HYP + 2].clone(),
-                            "refine_inliers": ti[:, _lib.ROW_REFINE_INL].clone()})
+                            "refine_inliers": ti[:, _lib.ROW_REFINE_INL].clone(),
+                            "residual_var": extra[:, 0], "confidence": extra[:, 1]})
     return out
 
 
@@ -157,6 +162,41 @@ def ransac_voting_layer_v2(mask, vertex, class_num, round_hyp_num, inlier_thresh
     out = _vote(b * k, h, w, vn, None, imask, k, 1, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num,
                 bool(refine_iter_num), idxs, su, details)
     return out.reshape(b, k, vn, 2)
+
+
+def _binary_mask_vote(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idxs, select_mask, select_u):
+    """v3's batched launch sequence with the per-instance details (winner, refinement, v4 / v5 extras) kept."""
+    mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
+    vertex = _lib.require_cuda(vertex, "vertex", torch.float32, contiguous=False)
+    b, h, w, vn, two = vertex.shape
+    if two != 2 or tuple(mask.shape) != (b, h, w):
+        raise RuntimeError(f"expected mask [b,h,w] and vertex [b,h,w,vn,2], got {tuple(mask.shape)}, {tuple(vertex.shape)}")
+    fmask = mask if (mask.dtype == torch.float32 and mask.is_contiguous()) else mask.to(torch.float32).contiguous()
+    su = _select_u(select_mask, select_u, (b, h, w), vertex.device)
+    det: list = []
+    pts = _vote(b, h, w, vn, fmask, None, 1, 0, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num, True, idxs, su, det)
+    return pts, det
+
+
+def ransac_voting_layer_v4(mask, vertex, round_hyp_num, inlier_thresh=0.99, confidence=0.999, max_iter=20, min_num=5,
+                           max_num=30000, *, idxs: Optional[torch.Tensor] = None, select_mask: Optional[torch.Tensor] = None,
+                           select_u: Optional[torch.Tensor] = None):
+    """ransac_voting_gpu.py:678-769 -- v3 plus the variance of the inlier rays' residuals about the refined point.
+
+    :return: ``[b,vn,2]`` refined points, ``[b,vn]`` variances (ones for instances with < ``min_num`` pixels)."""
+    pts, det = _binary_mask_vote(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idxs, select_mask, select_u)
+    return pts, torch.stack([d["residual_var"] for d in det], dim=1)
+
+
+def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                           max_num=100, *, idxs: Optional[torch.Tensor] = None, select_mask: Optional[torch.Tensor] = None,
+                           select_u: Optional[torch.Tensor] = None):
+    """ransac_voting_gpu.py:771-866 -- v3 plus a confidence: the fraction of the voters that vote for the refined point at
+    threshold 0.999.  Note the reference's default ``max_num=100``: larger instances are randomly sub-sampled.
+
+    :return: ``[b,vn,2]`` refined points, ``[b,vn]`` confidences (zeros for instances with < ``min_num`` pixels)."""
+    pts, det = _binary_mask_vote(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idxs, select_mask, select_u)
+    return pts, torch.stack([d["confidence"] for d in det], dim=1)
 
 
 def _class1_hypotheses(mask, vertex, hn, inlier_thresh, min_num, max_num, idxs, select_u):

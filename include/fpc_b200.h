@@ -187,6 +187,10 @@ typedef struct fpc_recover_args {
      * (nn.UpsamplingBilinear2d(scale_factor=S), align_corners=True; lib/pose_regressor.py:633-666) is evaluated on the
      * fly inside the arg-max and gather kernels -- the [b,67,h,w] head maps are never written or read. */
     int32_t upsample;
+    /* Optional [max_instances,2] f32, fpc_vote_dense / fpc_pose_recover: per instance (residual variance of the
+     * refinement inliers about the refined point, PVNet v4 ransac_voting_gpu.py:757-759; fraction of the voters that
+     * vote for the refined point at threshold 0.999, PVNet v5 :855-857).  One extra pass over the instance's records. */
+    float *extra_out;
 } fpc_recover_args;
 
 /* Workspace size for fpc_pose_recover with these sizes (only the size fields are read). */

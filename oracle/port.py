@@ -728,3 +728,66 @@ def calculate_aps(raw_data, metrics_threshold, metrics_operator):
             aps[key][class_id] = torch.sum(hits, dim=1) / values.shape[0]
         aps[key]["mean"] = torch.mean(torch.stack(list(aps[key].values())).float(), dim=0)
     return aps
+
+
+def _v3_with_extras(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idx_source, rv):
+    """Shared body of v4 (:678-769) and v5 (:771-866): per image the binary mask's winner, its inlier-weighted normal
+    equations, the residual variance about the refined point (v4) and the inlier ratio AT the refined point with the
+    hard-coded threshold 0.999 (v5).  Yields (points [vn,2], var [vn], conf [vn]) or None for a skipped image."""
+    b, h, w, vn, _ = vertex.shape
+    for bi in range(b):
+        cur = mask[bi].byte()
+        fg = torch.sum(cur)
+        if fg < min_num:
+            yield None
+            continue
+        if fg > max_num:
+            u = torch.zeros(cur.shape, dtype=torch.float32).uniform_(0, 1)
+            cur = cur * (u < (max_num / fg.float()))
+        sel = cur.bool()
+        coords = torch.nonzero(sel).float()[:, [1, 0]]
+        direct = vertex[bi].masked_select(sel.unsqueeze(2).unsqueeze(3)).view([coords.shape[0], vn, 2])
+        tn = coords.shape[0]
+        idxs = idx_source(bi, round_hyp_num, vn, tn).contiguous()
+        hyp, inl = _vote_round(rv, direct, coords, idxs, inlier_thresh)
+        win_counts, win_idx = torch.max(torch.sum(inl, 2), 0)
+        pts = hyp[win_idx, torch.arange(vn)]
+        pts = torch.where((win_counts.float() / tn > 0).unsqueeze(1), pts, torch.zeros_like(pts))
+        cur_inl = torch.zeros([1, vn, tn], dtype=torch.uint8)
+        rv.voting_for_hypothesis(direct, coords, pts.unsqueeze(0).contiguous(), cur_inl, inlier_thresh)
+        keep = cur_inl[0].float()                                               # [vn,tn]
+        normal = torch.stack((direct[:, :, 1], -direct[:, :, 0]), dim=2).permute(1, 0, 2) * keep.unsqueeze(2)   # [vn,tn,2]
+        rhs = torch.sum(normal * coords.unsqueeze(0), 2)                        # [vn,tn]
+        ata = torch.matmul(normal.permute(0, 2, 1), normal)
+        atb = torch.sum(normal * rhs.unsqueeze(2), 1)
+        refined = torch.matmul(b_inv(ata), atb.unsqueeze(2))                    # [vn,2,1]
+        residual = torch.matmul(normal, refined)[:, :, 0] - rhs
+        var = torch.sum(residual ** 2, 1) / torch.sum(keep, 1)
+        conf_inl = torch.zeros([1, vn, tn], dtype=torch.uint8)
+        rv.voting_for_hypothesis(direct, coords, refined[:, :, 0].unsqueeze(0).contiguous(), conf_inl, 0.999)
+        conf = torch.sum(conf_inl.int(), 2).float()[0] / tn
+        yield refined[:, :, 0], var, conf
+
+
+def ransac_voting_layer_v4(mask, vertex, round_hyp_num, inlier_thresh=0.99, confidence=0.999, max_iter=20, min_num=5,
+                           max_num=30000, *, idx_source: Optional[IdxSource] = None, kernels=None):
+    """ransac_voting_gpu.py:678-769 -> ``[b,vn,2]`` points, ``[b,vn]`` residual variances (zeros / ones when skipped)."""
+    vn = vertex.shape[3]
+    pts, var = [], []
+    for res in _v3_with_extras(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idx_source or seeded_idx_source(),
+                               kernels or native.ransac_voting):
+        pts.append(torch.zeros([1, vn, 2]) if res is None else res[0].unsqueeze(0))
+        var.append(torch.ones([1, vn]) if res is None else res[1].unsqueeze(0))
+    return torch.cat(pts), torch.cat(var)
+
+
+def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                           max_num=100, *, idx_source: Optional[IdxSource] = None, kernels=None):
+    """ransac_voting_gpu.py:771-866 -> ``[b,vn,2]`` points, ``[b,vn]`` confidences (zeros when skipped)."""
+    vn = vertex.shape[3]
+    pts, conf = [], []
+    for res in _v3_with_extras(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idx_source or seeded_idx_source(),
+                               kernels or native.ransac_voting):
+        pts.append(torch.zeros([1, vn, 2]) if res is None else res[0].unsqueeze(0))
+        conf.append(torch.zeros([1, vn]) if res is None else res[2].unsqueeze(0))
+    return torch.cat(pts), torch.cat(conf)

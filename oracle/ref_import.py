@@ -114,6 +114,22 @@ def fixed_idxs(idx_source, hn: int, vn: int = 1):
         torch.Tensor.random_ = original
 
 
+@contextmanager
+def legacy_uint8_masks():
+    """torch <= 1.x let ``masked_select`` take a uint8 mask (the reference's v4/v5/v6 build theirs with ``.byte()``,
+    ransac_voting_gpu.py:691,783); torch 2 insists on bool.  While active, uint8 masks are converted -- same selection."""
+    original = torch.Tensor.masked_select
+
+    def patched(self, mask):
+        return original(self, mask.bool() if mask.dtype == torch.uint8 else mask)
+
+    torch.Tensor.masked_select = patched
+    try:
+        yield
+    finally:
+        torch.Tensor.masked_select = original
+
+
 class _HP:
     """Anything with the attributes the path reads (config.py:80-82,93)."""
 

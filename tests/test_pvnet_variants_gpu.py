@@ -99,3 +99,35 @@ def test_distribution_estimators():
         idxs[i // rounds, (i % rounds) * 32:(i % rounds + 1) * 32] = t
     _, got_cov2 = estimate_voting_distribution_with_mean(mask.to(DEV), vertex.to(DEV), want_mean.to(DEV), idxs=idxs.to(DEV), **kw)
     assert helpers.rel_err(got_cov2.reshape(-1, 4), want_cov2.reshape(-1, 4)) <= 1e-3
+
+
+@pytest.mark.parametrize("vn", [1, 2])
+def test_v4_v5(vn):
+    from fastposecnn_b200.ransac_voting_gpu_layer.ransac_voting_gpu import ransac_voting_layer_v4, ransac_voting_layer_v5
+    from test_pvnet_variants_oracle import instance_scene
+    mask, vertex = instance_scene(vn)
+    hn = 40
+
+    def fixed(seed):
+        draw, log = recorded(seed)
+        return draw, log
+
+    draw, log = fixed(3)
+    want_pts, want_var = port.ransac_voting_layer_v4(mask, vertex, hn, idx_source=draw)
+    idxs = torch.zeros((mask.shape[0], hn, vn, 2), dtype=torch.int32)
+    for i, t in log:
+        idxs[i] = t
+    got_pts, got_var = ransac_voting_layer_v4(mask.to(DEV), vertex.to(DEV), hn, idxs=idxs.to(DEV))
+    assert got_pts.shape == want_pts.shape and got_var.shape == want_var.shape
+    assert helpers.rel_err(got_pts.reshape(-1, 2), want_pts.reshape(-1, 2)) <= helpers.REL_TOL
+    live = torch.isfinite(want_var)
+    assert torch.equal(torch.isfinite(got_var.cpu()), live)
+    assert float(((got_var.cpu() - want_var)[live].abs() / want_var[live].abs().clamp_min(1e-6)).max()) <= 1e-3
+    draw, log = fixed(5)
+    want_pts, want_conf = port.ransac_voting_layer_v5(mask, vertex, hn, max_num=30000, idx_source=draw)
+    for i, t in log:
+        idxs[i] = t
+    got_pts, got_conf = ransac_voting_layer_v5(mask.to(DEV), vertex.to(DEV), hn, max_num=30000, idxs=idxs.to(DEV))
+    assert helpers.rel_err(got_pts.reshape(-1, 2), want_pts.reshape(-1, 2)) <= helpers.REL_TOL
+    # the confidence counts votes at the refined point: a last-ulp difference of that point can flip a borderline pixel
+    assert float((got_conf.cpu() - want_conf).abs().max()) <= 2.0 / 600

@@ -56,3 +56,30 @@ def test_distribution_estimators_equal_reference():
     with ref_import.fixed_idxs(port.seeded_idx_source(7), 32):
         _, b_cov2 = ref.rvg.estimate_voting_distribution_with_mean(mask, vertex, b_mean, **kw)
     assert torch.equal(a_cov2, b_cov2)
+
+
+def instance_scene(vn=1):
+    frames = [[(30, 30, 14, 1)], [(64, 48, 22, 3)], [(100, 60, 1.0, 2)], []]
+    logits = syn.render_heads(frames, 96, 128, seed=7)
+    cat = port.class_compression(logits, 7)
+    vertex = cat["xy"].permute(0, 2, 3, 1).unsqueeze(3)
+    if vn > 1:
+        vertex = torch.cat([vertex, vertex.flip(-1) * torch.tensor([1.0, -1.0])], dim=3)
+    return (cat["mask"] != 0).float(), vertex.contiguous()
+
+
+@pytest.mark.parametrize("vn", [1, 2])
+def test_v4_v5_equal_reference(vn):
+    ref = ref_import.load()
+    mask, vertex = instance_scene(vn)
+    hn = 40
+    a_pts, a_var = port.ransac_voting_layer_v4(mask, vertex, hn, idx_source=port.seeded_idx_source(3))
+    with ref_import.fixed_idxs(port.seeded_idx_source(3), hn, vn), ref_import.legacy_uint8_masks():
+        b_pts, b_var = ref.rvg.ransac_voting_layer_v4(mask, vertex, hn)
+    assert torch.equal(a_pts, b_pts) and torch.equal(a_var, b_var)
+    assert torch.equal(a_var[3], torch.ones(vn)) and float(a_var[0, 0]) < 1.0
+    a_pts, a_conf = port.ransac_voting_layer_v5(mask, vertex, hn, max_num=30000, idx_source=port.seeded_idx_source(5))
+    with ref_import.fixed_idxs(port.seeded_idx_source(5), hn, vn), ref_import.legacy_uint8_masks():
+        b_pts, b_conf = ref.rvg.ransac_voting_layer_v5(mask, vertex, hn, max_num=30000)
+    assert torch.equal(a_pts, b_pts) and torch.equal(a_conf, b_conf)
+    assert torch.equal(a_conf[3], torch.zeros(vn)) and float(a_conf[:2, 0].min()) > 0.3
