@@ -598,6 +598,18 @@ def matching_section(dev, wl, logits, inv_k, hbm_peak, peak_src, iters=10):
 
     preds = fp.pose_recover(logits, inv_k, wl.hyps, materialize_dense=True)
     n = int(preds["class_ids"].shape[0])
+    # the drop-in voting drivers on the reference's dense per-instance layout (what HoughVotingLayer hands them), SURVEY 8f rank 3
+    from fastposecnn_b200.ransac_voting_gpu_layer import ransac_voting_gpu as rvg
+    vertex = preds["xy_mask"].permute(0, 2, 3, 1).unsqueeze(3)              # the reference's non-contiguous [N,h,w,1,2] view
+    drivers = {
+        "ransac_voting_layer_v3 (dense [N,h,w] masks + [N,h,w,1,2] vertex view)":
+            timed(lambda: rvg.ransac_voting_layer_v3(preds["instance_masks"], vertex, wl.hyps), n=5, warm=2),
+        "ransac_voting_layer_v4 (+ residual variance)":
+            timed(lambda: rvg.ransac_voting_layer_v4(preds["instance_masks"], vertex, wl.hyps), n=5, warm=2),
+        "ransac_voting_layer_v5 (+ confidence, max_num=30000)":
+            timed(lambda: rvg.ransac_voting_layer_v5(preds["instance_masks"], vertex, wl.hyps, max_num=30000), n=5, warm=2),
+    }
+    del vertex
     gts = {k: v.clone() for k, v in preds.items() if k not in ("labels", "cat_mask", "xy_mask")}
     gts["instance_masks"] = torch.roll(gts["instance_masks"], shifts=(3, -2), dims=(1, 2)).contiguous()
     gts["symmetric_ids"] = gts["class_ids"] % 2
@@ -637,6 +649,14 @@ def matching_section(dev, wl, logits, inv_k, hbm_peak, peak_src, iters=10):
             k += int((v > 0).sum())
         return k
     t_ref = timed(lambda: res.__setitem__("r", reference_style()), n=2, warm=1)
+    # evaluation maths on the matched pairs: one launch each
+    mt = res["d"]
+    evals = {
+        "get_quat_distance (360-rotation symmetry for odd classes)":
+            timed(lambda: fp.get_quat_distance(mt["quaternion"][0], mt["quaternion"][1], mt["symmetric_ids"])),
+        "get_3d_ious": timed(lambda: fp.get_3d_ious(mt["RT"][0], mt["RT"][1], mt["scales"][0], mt["scales"][1])),
+        "from_Ts_get_offset_error": timed(lambda: fp.from_Ts_get_offset_error(mt["T"][0], mt["T"][1])),
+    }
     pack_bytes = n * h * w * 4 + n * h * ((w + 31) // 32) * 4
     a = pack_bytes / (t_pack * 1e-3) / 1e9
     stack_bytes = 4 * n * h * w * 4          # read + write of the gt rows and of the matched prediction rows
@@ -648,6 +668,7 @@ def matching_section(dev, wl, logits, inv_k, hbm_peak, peak_src, iters=10):
         "speedup_vs_reference_algorithm_same_gpu": t_ref / t_dense,
         "kernel_ms": {"k_pack_masks_v4 (+meta init)": t_pack, "k_pack_labels (+memset, meta init)": t_lab, "k_mask_iou": t_iou,
                       "k_match_best + k_match_order (+memset)": t_pair},
+        "voting_drivers_ms": drivers, "evaluation_ms": evals,
         "roofline": {"bound": "hbm", "kernel": "k_pack_masks_v4", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                      "algorithmic_bytes": pack_bytes, "traffic": None, "peak_source": peak_src,
                      "note": "4 B/px read once + 1 bit/px written; the stacked [2,M,h,w] instance_masks output of the call "
