@@ -76,6 +76,58 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
             const int p = p0 + kx;
             const bool mem = kx < len;   // slots are contiguous runs
             float vx = 0.f, vy = 0.f;
+            // MODE 3 (low-resolution heads): the predicted class's 10 values of this pixel (q0..q3, s0..s2, z, dir_x, dir_y),
+            // each the x S bilinear interpolation of its low-res plane.  The 32 pixels of a warp iteration span <= 9 low-res
+            // columns for S >= 4, so the 2 x 16 taps of a plane are loaded ONCE by the warp (lane = row*16 + column) and
+            // handed to the pixels by shuffles: 1 load + 4 shuffles per channel instead of 4 loads and their address
+            // arithmetic.  That needs one class for the whole iteration; pixels of touching blobs of different classes (and
+            // S < 4) take the per-lane path.  Both paths feed identical operands to bilerp(): identical bits.
+            float lr[10];
+            int lr_cp = 0;
+            if (MODE == 3) {
+                lr_cp = mem ? (int)cls[p] : 0;
+                const LerpCoord LX = lerp_coord(min(x0 + kx, pp.w - 1), pp.up.sx, pp.up.wl);
+                const int wl = pp.up.wl;
+                const size_t lhw = (size_t)pp.up.hl * wl;
+                const unsigned members = __ballot_sync(FULL, mem);           // lane 0 is always a member
+                const int c_first = __shfl_sync(FULL, LX.i0, 0);
+                const int c_last = __shfl_sync(FULL, LX.i1, 31 - __clz(members));
+                const int cp0 = __shfl_sync(FULL, lr_cp, 0);
+                const bool uniform = __all_sync(FULL, !mem || lr_cp == cp0);
+                if (uniform && c_last - c_first < 16) {
+                    const int toff = ((lane >> 4) ? LY.i1 : LY.i0) * wl + min(c_first + (lane & 15), wl - 1);
+                    const int s00 = LX.i0 - c_first, s01 = LX.i1 - c_first;  // source lanes of this pixel's row-0 taps; +16: row 1
+                    const size_t kc = (size_t)img * K + (cp0 - 1);           // (image, predicted class) -> channel group
+                    const float *const planes[4] = {F.quaternion + 4 * kc * lhw, F.scales + 3 * kc * lhw, F.z + kc * lhw,
+                                                    F.xy + 2 * kc * lhw};
+                    int o = 0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int nch = g == 0 ? 4 : g == 1 ? 3 : g == 2 ? 1 : 2;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < nch) {
+                                const float t = __ldg(planes[g] + (size_t)c * lhw + toff);
+                                const float v00 = __shfl_sync(FULL, t, s00), v01 = __shfl_sync(FULL, t, s01);
+                                const float v10 = __shfl_sync(FULL, t, s00 + 16), v11 = __shfl_sync(FULL, t, s01 + 16);
+                                lr[o++] = bilerp(v00, v01, v10, v11, LX.w0, LX.w1, LY.w0, LY.w1);
+                            }
+                        }
+                    }
+                } else if (mem) {
+                    const int o00 = LY.i0 * wl + LX.i0, o01 = LY.i0 * wl + LX.i1, o10 = LY.i1 * wl + LX.i0, o11 = LY.i1 * wl + LX.i1;
+                    auto tap = [&](const float *__restrict__ plane) {
+                        return bilerp(__ldg(plane + o00), __ldg(plane + o01), __ldg(plane + o10), __ldg(plane + o11),
+                                      LX.w0, LX.w1, LY.w0, LY.w1);
+                    };
+                    const size_t kc = (size_t)img * K + (lr_cp - 1);
+                    const float *q = F.quaternion + 4 * kc * lhw, *sp = F.scales + 3 * kc * lhw, *v = F.xy + 2 * kc * lhw;
+                    lr[0] = tap(q); lr[1] = tap(q + lhw); lr[2] = tap(q + 2 * lhw); lr[3] = tap(q + 3 * lhw);
+                    lr[4] = tap(sp); lr[5] = tap(sp + lhw); lr[6] = tap(sp + 2 * lhw);
+                    lr[7] = tap(F.z + kc * lhw);
+                    lr[8] = tap(v); lr[9] = tap(v + lhw);
+                }
+            }
             if (mem) {
                 const size_t pix = (size_t)(pix0 + kx);
                 float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, zz = 0.f;
@@ -84,7 +136,7 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
                     vx = v[0];
                     vy = v[F.s2];
                 } else if (MODE == 0 || MODE == 3) {
-                    const int cp = (int)cls[p];
+                    const int cp = MODE == 3 ? lr_cp : (int)cls[p];
                     cmin = min(cmin, cp);
                     if (MODE == 0) {
                         const size_t koff = (size_t)(cp - 1) * hw;            // predicted class of THIS pixel (class_compress is per pixel)
@@ -96,22 +148,9 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
                         zz = __ldcs(F.z + (size_t)img * K * hw + koff + pix);
                         vx = __ldcs(v); vy = __ldcs(v + hw);
                     } else {
-                        const LerpCoord LX = lerp_coord(x0 + kx, pp.up.sx, pp.up.wl);
-                        const int wl = pp.up.wl;
-                        const size_t lhw = (size_t)pp.up.hl * wl;
-                        const int o00 = LY.i0 * wl + LX.i0, o01 = LY.i0 * wl + LX.i1, o10 = LY.i1 * wl + LX.i0, o11 = LY.i1 * wl + LX.i1;
-                        auto tap = [&](const float *__restrict__ plane) {
-                            return bilerp(__ldg(plane + o00), __ldg(plane + o01), __ldg(plane + o10), __ldg(plane + o11),
-                                          LX.w0, LX.w1, LY.w0, LY.w1);
-                        };
-                        const size_t kc = (size_t)img * K + (cp - 1);          // (image, predicted class) -> channel group
-                        const float *q = F.quaternion + 4 * kc * lhw;
-                        const float *s = F.scales + 3 * kc * lhw;
-                        const float *v = F.xy + 2 * kc * lhw;
-                        q0 = tap(q); q1 = tap(q + lhw); q2 = tap(q + 2 * lhw); q3 = tap(q + 3 * lhw);
-                        s0 = tap(s); s1 = tap(s + lhw); s2 = tap(s + 2 * lhw);
-                        zz = tap(F.z + kc * lhw);
-                        vx = tap(v); vy = tap(v + lhw);
+                        q0 = lr[0]; q1 = lr[1]; q2 = lr[2]; q3 = lr[3];
+                        s0 = lr[4]; s1 = lr[5]; s2 = lr[6]; zz = lr[7];
+                        vx = lr[8]; vy = lr[9];
                     }
                     // quaternion: only its masked mean is used (1e-4 budget) -> one reciprocal, four multiplies;
                     // direction: feeds the votes -> keep the reference's value / norm with IEEE sqrt and divide
