@@ -269,18 +269,22 @@ __global__ void __launch_bounds__(256) k_match_order(const long long *__restrict
 // Dense [m,h,w] f32 0/1 masks of the listed instances (row k: instance inst_of[k] of frame frame_of[k]) painted from the
 // label volume -- the matched predictions' masks, the only dense masks a label-volume prediction set ever needs.
 __global__ void __launch_bounds__(256) k_paint_instances(const int *__restrict__ labels, int b, long long hw, const long long *__restrict__ frame_of,
-                                                         const long long *__restrict__ inst_of, long long total4, float *__restrict__ out) {
-    const long long hw4 = hw >> 2;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
-        const long long k = t / hw4, q = t - k * hw4;
+                                                         const long long *__restrict__ inst_of, int m, float *__restrict__ out) {
+    const int hw4 = (int)(hw >> 2);
+    for (int k = blockIdx.y; k < m; k += gridDim.y) {                     // one output plane per blockIdx.y: no per-thread division
         const long long f = frame_of[k];
         const int want = (int)inst_of[k] + 1;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f >= 0 && f < b) {
-            const int4 L = __ldg(reinterpret_cast<const int4 *>(labels + f * hw) + q);
-            o = make_float4(L.x == want ? 1.f : 0.f, L.y == want ? 1.f : 0.f, L.z == want ? 1.f : 0.f, L.w == want ? 1.f : 0.f);
+        const bool live = f >= 0 && f < b;
+        const int4 *__restrict__ src = reinterpret_cast<const int4 *>(labels + (live ? f : 0) * hw);
+        float4 *__restrict__ dst = reinterpret_cast<float4 *>(out + (size_t)k * hw);
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < hw4; q += gridDim.x * blockDim.x) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const int4 L = __ldg(src + q);
+                o = make_float4(L.x == want ? 1.f : 0.f, L.y == want ? 1.f : 0.f, L.z == want ? 1.f : 0.f, L.w == want ? 1.f : 0.f);
+            }
+            __stcs(dst + q, o);
         }
-        __stcs(reinterpret_cast<float4 *>(out) + t, o);
     }
 }
 __global__ void __launch_bounds__(256) k_paint_instances_scalar(const int *__restrict__ labels, int b, long long hw, const long long *__restrict__ frame_of,
@@ -387,9 +391,10 @@ int fpc_paint_instances(const int32_t *labels, int b, int h, int w, const int64_
     const bool vec = hw % 4 == 0 && (uintptr_t)labels % 16 == 0 && (uintptr_t)out % 16 == 0;
     const long long items = vec ? total / 4 : total;
     const int grid = (int)std::min<long long>(ceil_div_ll(items, 256), (long long)sm_count() * 16);
-    if (vec)
-        k_paint_instances<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, b, hw, (const long long *)frame_of, (const long long *)inst_of, items, out);
-    else
+    if (vec) {
+        const dim3 g2((unsigned)std::min<long long>(ceil_div_ll(hw / 4, 256), 64), (unsigned)std::min(m, 65535));
+        k_paint_instances<<<g2, 256, 0, (cudaStream_t)stream>>>(labels, b, hw, (const long long *)frame_of, (const long long *)inst_of, m, out);
+    } else
         k_paint_instances_scalar<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, b, hw, (const long long *)frame_of, (const long long *)inst_of, items, out);
     FPC_LAUNCH_CHECK("k_paint_instances");
     return FPC_OK;
