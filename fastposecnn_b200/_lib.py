@@ -31,7 +31,7 @@ EXPORTS = (
     "fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances",
     "fpc_pack_masks", "fpc_pack_labels", "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances", "fpc_upsample_bilinear",
     "fpc_generate_hypothesis_vanishing_point", "fpc_voting_for_hypothesis_vanishing_point",
-    "fpc_pose_errors", "fpc_threshold_fraction", "fpc_label_instances",
+    "fpc_pose_errors", "fpc_threshold_fraction", "fpc_label_instances", "fpc_recover_args_size",
 )
 MASK_META = 8
 MASK_F32, MASK_U8 = 0, 1
@@ -72,6 +72,10 @@ def lib() -> ctypes.CDLL:
             "There is no CPU or PyTorch fallback for this path.")
     L = ctypes.CDLL(LIB_PATH)
     L.fpc_version.restype = _i
+    L.fpc_recover_args_size.restype = ctypes.c_size_t
+    if L.fpc_recover_args_size() != ctypes.sizeof(RecoverArgs):
+        raise RuntimeError(f"libfpc_b200.so was built with a different fpc_recover_args ({L.fpc_recover_args_size()} bytes) than "
+                           f"this binding declares ({ctypes.sizeof(RecoverArgs)}): rebuild with `make -C fastposecnn_b200/csrc`")
     L.fpc_last_error.restype = ctypes.c_char_p
     L.fpc_generate_hypothesis.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
     L.fpc_voting_for_hypothesis.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]

@@ -270,6 +270,7 @@ using namespace fpc;
 extern "C" {
 
 int fpc_version(void) { return FPC_VERSION; }
+size_t fpc_recover_args_size(void) { return sizeof(fpc_recover_args); }
 const char *fpc_last_error(void) { return err_buf(); }
 
 int fpc_generate_hypothesis(const float *direct, const float *coords, const int32_t *idxs, float *hypo_pts, int tn, int vn,

@@ -193,6 +193,9 @@ typedef struct fpc_recover_args {
     float *extra_out;
 } fpc_recover_args;
 
+/* sizeof(fpc_recover_args) as this library was compiled: lets a binding check its own struct definition. */
+FPC_API size_t fpc_recover_args_size(void);
+
 /* Workspace size for fpc_pose_recover with these sizes (only the size fields are read). */
 FPC_API size_t fpc_pose_recover_workspace_bytes(const fpc_recover_args *args);
 
