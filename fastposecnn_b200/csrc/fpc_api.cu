@@ -192,7 +192,7 @@ static size_t carve(Workspace &ws, void *base, long long P, long long rows_total
     ws.rec.y = c.take<float>((size_t)max_records);
     ws.rec.nx = c.take<float>((size_t)max_records);
     ws.rec.ny = c.take<float>((size_t)max_records);
-    ws.work = c.take<int4>(((size_t)max_records / VOTE_CHUNK + (size_t)max_instances + 1) * (size_t)vote_batches(hn));
+    ws.work = c.take<int4>(((size_t)max_records / vote_chunk_for(P) + (size_t)max_instances + 1) * (size_t)vote_batches(hn));
     if (own_hyp) ws.hyp = c.take<float2>((size_t)max_instances * hn);
     if (own_votes) ws.votes = c.take<int>((size_t)max_instances * hn);
     return (c.off + 255) & ~size_t(255);
@@ -411,6 +411,7 @@ static int setup(const fpc_recover_args *a, Workspace &ws, PathParams &pp) {
     pp.inlier_thresh = a->inlier_thresh; pp.min_num = a->min_num; pp.max_num = a->max_num;
     pp.arith = a->arith; pp.seed = a->seed; pp.idxs = a->idxs; pp.select_u = a->select_u;
     pp.refine = 1;
+    pp.vote_chunk = vote_chunk_for(P);
     pp.up = UpParams{0, a->h, a->w, 0.f, 0.f};
     pp.extra = a->extra_out;
     return FPC_OK;
@@ -435,7 +436,7 @@ int fpc_aggregate(const fpc_recover_args *a, const int64_t *cat_mask) {
     cudaStream_t st = (cudaStream_t)a->stream;
     rc = launch_label_and_tables(ws, pp, nullptr, reinterpret_cast<const long long *>(cat_mask), st);
     FieldSrc F{a->quaternion, a->scales, a->xy, a->z, 0, 0, 0, 0, 1};
-    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/1, /*want_records=*/false, VOTE_CHUNK, st);
+    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/1, /*want_records=*/false, pp.vote_chunk, st);
     if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, nullptr, a->pose_table, st);
     if (rc == FPC_OK && a->labels) rc = launch_relabel(ws, pp, a->labels, st);
     return rc;
@@ -466,7 +467,7 @@ int fpc_vote_dense(const fpc_recover_args *a, const float *fmask, const int32_t 
     cudaStream_t st = (cudaStream_t)a->stream;
     rc = launch_dense_problems(ws, pp, fmask, imask, nplanes_per_src, match_base, a->b, st);
     FieldSrc F{nullptr, nullptr, vertex, nullptr, sN, sH, sW, s2, nplanes_per_src};
-    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/2, /*want_records=*/true, VOTE_CHUNK, st);
+    if (rc == FPC_OK) rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/2, /*want_records=*/true, pp.vote_chunk, st);
     if (rc == FPC_OK) rc = launch_vote(ws, pp, ws.hyp, ws.votes, st);
     if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, nullptr, a->pose_table, st);
     return rc;
@@ -495,7 +496,7 @@ int fpc_pose_recover(const fpc_recover_args *a) {
     rc = launch_label_and_tables(ws, pp, a->mask_logits, nullptr, st);
     FieldSrc F{a->quaternion, a->scales, a->xy, a->z, 0, 0, 0, 0, 1};
     if (rc == FPC_OK)
-        rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/pp.up.s > 1 ? 3 : 0, /*want_records=*/true, VOTE_CHUNK, st);
+        rc = launch_rows_and_records(ws, pp, F, /*gather_mode=*/pp.up.s > 1 ? 3 : 0, /*want_records=*/true, pp.vote_chunk, st);
     if (rc == FPC_OK) rc = launch_vote(ws, pp, ws.hyp, ws.votes, st);
     if (rc == FPC_OK) rc = launch_finalize(ws, pp, ws.hyp, ws.votes, a->inv_intrinsics, a->pose_table, st);
     if (rc == FPC_OK && a->labels) rc = launch_relabel(ws, pp, a->labels, st);

@@ -58,6 +58,7 @@ struct PathParams {
     const int *idxs;             // [max_instances,hn,2] or nullptr
     const float *select_u;       // [b,h,w] or nullptr
     int refine;                  // 1: inlier refinement (v3); 0: winning hypothesis as is (v1)
+    int vote_chunk;              // pixels per vote work item for this problem size (vote_chunk_for)
     UpParams up;                 // head-epilogue fusion: head maps are low resolution, x up.s bilinear on the fly
     float *extra;                // [max_instances,2] (v4 residual variance, v5 confidence at 0.999) or nullptr
 };
@@ -85,7 +86,15 @@ struct Workspace {
 #ifndef FPC_VOTE_CHUNK
 #define FPC_VOTE_CHUNK 1024
 #endif
-constexpr int VOTE_CHUNK = FPC_VOTE_CHUNK;  // pixels per vote work item
+constexpr int VOTE_CHUNK = FPC_VOTE_CHUNK;  // pixels per vote work item (upper bound: shared-memory buffers have this size)
+// Small problems (a single frame, a few instances) would give the persistent vote kernel only a handful of work items;
+// they are cut into smaller chunks so that the votes still spread over the machine: P/2048 rounded down to a power of
+// two, clamped to [128, VOTE_CHUNK].  640x480: b = 1 -> 128, b = 4 -> 512, b >= 7 -> 1024.
+inline int vote_chunk_for(long long P) {
+    int c = VOTE_CHUNK;
+    while (c > 128 && (long long)c * 2048 > P) c >>= 1;
+    return c;
+}
 
 // fpc_aggregate.cu
 int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,

@@ -144,15 +144,16 @@ __global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__r
         if (idx >= total) {
             const int i = (int)(idx - total);
             const int tn = T.tn[i], w0 = T.workoff[i], px = T.pxoff[i];
-            const int chunks = (tn + VOTE_CHUNK - 1) / VOTE_CHUNK;
+            const int chunk = pp.vote_chunk;
+            const int chunks = (tn + chunk - 1) / chunk;
             for (int k = tn; k < ((tn + 15) & ~15); ++k) {            // padding records: can never be inliers
                 const size_t o = (size_t)px + k;
                 rec.x[o] = 1e18f; rec.y[o] = 1e18f; rec.nx[o] = 0.f; rec.ny[o] = 0.f;
             }
             for (int c = 0; c < chunks; ++c)
                 for (int b = 0; b < nb; ++b) {
-                    const int npx = min(VOTE_CHUNK, tn - c * VOTE_CHUNK), nh = min(1024, hn - b * 1024);
-                    work[w0 + c * nb + b] = make_int4(i, px + c * VOTE_CHUNK, npx | (nh << 16), b * 1024);
+                    const int npx = min(chunk, tn - c * chunk), nh = min(1024, hn - b * 1024);
+                    work[w0 + c * nb + b] = make_int4(i, px + c * chunk, npx | (nh << 16), b * 1024);
                 }
             continue;
         }
