@@ -114,3 +114,25 @@ def test_many_instances_random_blobs():
     assert torch.equal(pairs[:m, 0].cpu().long(), order) and torch.equal(pairs[:m, 1].cpu().long(), best[order])
     rows = torch.arange(gm.shape[0])[best >= 0]
     assert torch.equal(bi.cpu()[rows], want_iou[rows, best[rows]])
+
+
+def test_odd_image_size_label_volume_path():
+    """70x101 frames: h*w is not a multiple of 4 (scalar paint kernel), w is not a multiple of 32 (ragged last bit-plane word)."""
+    import fastposecnn_b200 as fp
+    frames, h, w = helpers.scenes()["odd_width"]
+    logits = syn.render_heads(frames, h, w, seed=4)
+    inv_k = torch.inverse(syn.camera_intrinsics())
+    sparse = fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32)
+    dense = {k: v.clone() for k, v in fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32,
+                                                      materialize_dense=True).items() if k not in ("labels", "xy_mask")}
+    gts = {k: v.clone() for k, v in dense.items() if k != "cat_mask"}
+    gts["instance_masks"] = torch.roll(gts["instance_masks"], shifts=(1, 2), dims=(1, 2)).contiguous()
+    gts["symmetric_ids"] = gts["class_ids"] % 2
+    a = fp.batchwise_find_matches({k: v for k, v in sparse.items()}, gts)
+    b = fp.batchwise_find_matches(dense, gts)
+    want = port.batchwise_find_matches({k: v.cpu() for k, v in dense.items()}, {k: v.cpu() for k, v in gts.items()})
+    assert a is not None and want is not None
+    for k in ("sample_ids", "class_ids", "symmetric_ids", "instance_masks", "quaternion", "scales", "z"):
+        assert torch.equal(a[k], b[k]) and torch.equal(b[k].cpu(), want[k]), k
+    want_iou = port.batchwise_get_2d_iou(gts["instance_masks"].cpu(), dense["instance_masks"].cpu())
+    assert torch.equal(fp.batchwise_get_2d_iou(gts["instance_masks"], dense["instance_masks"]).cpu(), want_iou)
