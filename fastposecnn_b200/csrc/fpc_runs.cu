@@ -330,6 +330,60 @@ __global__ void __launch_bounds__(256) k_emit_runs(const uint8_t *__restrict__ c
     if (p + 4 >= P) RT.rowrun[P / w] = tile_base[gridDim.x];   // sentinel: total number of runs
 }
 
+// The same for w % 16 == 0 (and spans that are multiples of 16): one thread owns 16 pixels = one 16-byte load; its
+// foreground / run-start / run-end masks come from byte compares and shifts instead of a per-pixel loop, and only set bits
+// are visited when writing.  64 threads per 1024-pixel tile; ~13x fewer instructions per pixel than the 4-pixel kernel.
+__device__ __forceinline__ unsigned nonzero_bytes4(unsigned q) {
+    // 0xFF per non-zero byte -> one bit per byte (bits land on 24..27: no carries between the partial products)
+    return ((__vcmpne4(q, 0u) & 0x01010101u) * 0x01020408u) >> 24;
+}
+__global__ void __launch_bounds__(64) k_emit_runs16(const uint8_t *__restrict__ cls, const int *__restrict__ tile_base, RunTables RT,
+                                                    int w, int P, int span, long long cap) {
+    __shared__ int s_w[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = (blockIdx.x * 64 + threadIdx.x) * 16;          // P is a multiple of 16
+    const int smask = span - 1;
+    unsigned fg = 0, st = 0, en = 0;
+    if (p < P) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(cls + p);
+        fg = nonzero_bytes4(v.x) | (nonzero_bytes4(v.y) << 4) | (nonzero_bytes4(v.z) << 8) | (nonzero_bytes4(v.w) << 12);
+    }
+    const int x0 = p < P ? p - (p / w) * w : 1;                  // the 16 pixels lie in one image row (w % 16 == 0)
+    if (fg) {
+        const bool left_cut = x0 == 0 || (p & smask) == 0;                      // row start or span start: a new run begins
+        const bool right_cut = x0 + 16 == w || ((p + 16) & smask) == 0;
+        const unsigned prev = ((fg & 1u) && !left_cut && cls[p - 1]) ? 1u : 0u;
+        const unsigned next = ((fg & 0x8000u) && !right_cut && cls[p + 16]) ? 0x8000u : 0u;
+        st = fg & ~((fg << 1) | prev) & 0xFFFFu;
+        en = fg & ~((fg >> 1) | next);
+    }
+    if (!__syncthreads_or(fg)) {                                 // all-background tile: only the row index needs the base
+        if (p < P) {
+            if (x0 == 0) RT.rowrun[p / w] = tile_base[blockIdx.x];
+            if (p + 16 >= P) RT.rowrun[P / w] = tile_base[gridDim.x];
+        }
+        return;
+    }
+    const int mine = __popc(st);
+    const int inc = warp_incl_scan(mine, lane);
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (p >= P) return;
+    int before = tile_base[blockIdx.x] + inc - mine + (wid ? s_w[0] : 0);     // run starts before my first pixel
+    if (x0 == 0) RT.rowrun[p / w] = before;                      // first run at or after the start of this image row
+    unsigned both = st | en;
+    while (both) {
+        const int j = __ffs(both) - 1;
+        both &= both - 1;
+        if ((st >> j) & 1u) {
+            if (before < cap) { RT.start[before] = p + j; RT.parent[before] = before; }
+            ++before;
+        }
+        if (((en >> j) & 1u) && before - 1 < cap) RT.end[before - 1] = p + j;
+    }
+    if (p + 16 >= P) RT.rowrun[P / w] = tile_base[gridDim.x];    // sentinel: total number of runs
+}
+
 // =============================================================================================
 // 4. union-find over runs (roots = smallest run id = the run holding the component's first pixel)
 // =============================================================================================
@@ -566,7 +620,10 @@ static int launch_run_tables(const Workspace &ws, const PathParams &pp, int span
     const long long cap = pp.max_rows;
     k_scan_tiles<<<1, 1024, 0, st>>>(ws.tile_roots, ntiles, ws.counters, FPC_CNT_ROWS, cap, FPC_FLAG_ROWS, 1);
     FPC_LAUNCH_CHECK("k_scan_tiles");
-    k_emit_runs<<<ntiles, 256, 0, st>>>(ws.cls, ws.tile_roots, ws.RT, pp.w, P, span, cap);
+    if (pp.w % 16 == 0 && span % 16 == 0 && (reinterpret_cast<uintptr_t>(ws.cls) & 15) == 0)
+        k_emit_runs16<<<ntiles, 64, 0, st>>>(ws.cls, ws.tile_roots, ws.RT, pp.w, P, span, cap);
+    else
+        k_emit_runs<<<ntiles, 256, 0, st>>>(ws.cls, ws.tile_roots, ws.RT, pp.w, P, span, cap);
     FPC_LAUNCH_CHECK("k_emit_runs");
     const int rgrid = sm_count() * 8;
     const int rtiles = ceil_div(std::min<long long>(cap, (long long)P), TILE);
