@@ -368,8 +368,9 @@ def batchwise_get_2d_iou(masks1: torch.Tensor, masks2: torch.Tensor) -> torch.Te
     ``logical_and`` / ``logical_or`` as int64; here the same integers come from one integer matrix
     product (|A and B|) and inclusion-exclusion (|A or B| = |A| + |B| - |A and B|).  int64 / int64 is torch's true
     division: both sides converted to float32, IEEE divide, 0/0 = NaN."""
-    a = (masks1 != 0).reshape(masks1.shape[0], -1).to(torch.int64)
-    b = (masks2 != 0).reshape(masks2.shape[0], -1).to(torch.int64)
+    hw = masks1.shape[-2] * masks1.shape[-1]
+    a = (masks1 != 0).reshape(masks1.shape[0], hw).to(torch.int64)
+    b = (masks2 != 0).reshape(masks2.shape[0], hw).to(torch.int64)
     inter = a @ b.t()
     union = a.sum(dim=1, keepdim=True) + b.sum(dim=1).unsqueeze(0) - inter
     return inter / union
