@@ -657,6 +657,19 @@ def matching_section(dev, wl, logits, inv_k, hbm_peak, peak_src, iters=10):
         "get_3d_ious": timed(lambda: fp.get_3d_ious(mt["RT"][0], mt["RT"][1], mt["scales"][0], mt["scales"][1])),
         "from_Ts_get_offset_error": timed(lambda: fp.from_Ts_get_offset_error(mt["T"][0], mt["T"][1])),
     }
+    # training support (second half): forward + backward of class_compression -> AggregationLayer on this batch
+    import types
+    layer = fp.AggregationLayer(types.SimpleNamespace(HV_NUM_OF_HYPOTHESES=wl.hyps), wl.num_classes, max_instances=max(1024, 2 * n))
+    train_in = {k: (v.detach().clone().requires_grad_(True) if k != "mask" else v) for k, v in logits.items()}
+
+    def train_step():
+        for k, v in train_in.items():
+            if k != "mask":
+                v.grad = None
+        agg_t = layer(fp.class_compression(train_in, wl.num_classes))
+        (agg_t["quaternion"].sum() + agg_t["scales"].sum() + agg_t["z"].sum()).backward()
+    t_train = timed(train_step, n=3, warm=1)
+    del layer, train_in
     pack_bytes = n * h * w * 4 + n * h * ((w + 31) // 32) * 4
     a = pack_bytes / (t_pack * 1e-3) / 1e9
     stack_bytes = 4 * n * h * w * 4          # read + write of the gt rows and of the matched prediction rows
@@ -669,6 +682,7 @@ def matching_section(dev, wl, logits, inv_k, hbm_peak, peak_src, iters=10):
         "kernel_ms": {"k_pack_masks_v4 (+meta init)": t_pack, "k_pack_labels (+memset, meta init)": t_lab, "k_mask_iou": t_iou,
                       "k_match_best + k_match_order (+memset)": t_pair},
         "voting_drivers_ms": drivers, "evaluation_ms": evals,
+        "training_forward_backward_ms": {"class_compression + AggregationLayer, losses on q / scales / z": t_train},
         "roofline": {"bound": "hbm", "kernel": "k_pack_masks_v4", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                      "algorithmic_bytes": pack_bytes, "traffic": None, "peak_source": peak_src,
                      "note": "4 B/px read once + 1 bit/px written; the stacked [2,M,h,w] instance_masks output of the call "

@@ -103,17 +103,36 @@ class AggregationLayer(nn.Module):
             raise RuntimeError("AggregationLayer: cat_data tensors have inconsistent shapes")
         dev = cat_mask.device
         cap = self.max_instances or max(1024, 128 * b)
-        with torch.cuda.device(dev):
-            a, bufs = _pipeline_args(b, h, w, int(self.classes), 1, cap, dev)
-            a.quaternion, a.scales, a.xy, a.z = q.data_ptr(), s.data_ptr(), xy.data_ptr(), z.data_ptr()
-            _lib.check(_lib.lib().fpc_aggregate(ctypes.byref(a), cat_mask.data_ptr()))
-            n = _read_count(bufs, cap)
-        table = bufs["table_full"][1:]
-        full = table_to_agg(table, n)
-        agg = {k: full[k] for k in ("class_ids", "sample_ids", "quaternion", "scales", "z")}
-        agg["instance_masks"] = materialize_instance_masks(bufs["labels"], table, n)
-        agg["xy"] = materialize_xy_mask(bufs["labels"], table, xy, n)
-        return agg
+
+        def run():
+            with torch.cuda.device(dev):
+                a, bufs = _pipeline_args(b, h, w, int(self.classes), 1, cap, dev)
+                a.quaternion, a.scales, a.xy, a.z = q.data_ptr(), s.data_ptr(), xy.data_ptr(), z.data_ptr()
+                extra = torch.zeros((cap, 4), dtype=f32, device=dev)
+                a.extra_out = extra.data_ptr()
+                _lib.check(_lib.lib().fpc_aggregate(ctypes.byref(a), cat_mask.data_ptr()))
+                n = _read_count(bufs, cap)
+            table = bufs["table_full"][1:]
+            full = table_to_agg(table, n)
+            agg = {k: full[k] for k in ("class_ids", "sample_ids", "quaternion", "scales", "z")}
+            agg["instance_masks"] = materialize_instance_masks(bufs["labels"], table, n)
+            agg["xy"] = materialize_xy_mask(bufs["labels"], table, xy, n)
+            return agg, bufs["labels"], full["mask_sizes"].to(torch.int32), extra[:n, 2].clone()
+
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (q, s, xy, z)):
+            # training: the masked means (and the masked xy) stay differentiable w.r.t. the class-compressed fields
+            from .autograd import AggregateFn
+            holder = {}
+
+            def run_and_keep():
+                res = run()
+                holder["agg"] = res[0]
+                return res
+            q_o, s_o, z_o, xy_o = AggregateFn.apply(run_and_keep, q, s, xy, z)
+            agg = dict(holder["agg"])
+            agg.update({"quaternion": q_o, "scales": s_o, "z": z_o, "xy": xy_o})
+            return agg
+        return run()[0]
 
     def batchwise_break_segmentation_mask(self, class_mask: torch.Tensor):
         """lib/aggregation_layer.py:160-183: 4-connected labelling of a [b,h,w] foreground volume, labels in

@@ -1,0 +1,83 @@
+"""Training support: ``torch.autograd.Function`` shells around the forward kernels, with hand-written backward kernels
+(``csrc/fpc_backward.cu``).  The reference trains its aggregated losses (lib/loss.py:155-545) through plain torch ops; with
+these, ``class_compress`` / ``class_compression`` and ``AggregationLayer.forward`` of the drop-in stay differentiable with
+respect to the regression head maps (quaternion, scales, xy, z).  The mask head is trained by its own pixel-wise losses
+(lib/loss.py:26-101); the arg-max that selects classes has no gradient in the reference either."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class ClassCompressFn(torch.autograd.Function):
+    """(quaternion, scales, xy, z raw head maps) -> class-compressed fields; ``run`` does the forward launch."""
+
+    @staticmethod
+    def forward(ctx, run, num_of_classes, quat, scales, xy, z):
+        out = run()
+        cat = out["mask"] if "mask" in out else out["_cat_mask"]
+        ctx.save_for_backward(cat, quat, xy)
+        ctx.num_of_classes = num_of_classes
+        ctx.shapes = (quat.shape, scales.shape, xy.shape, z.shape)
+        ctx.mark_non_differentiable(cat)
+        return out["quaternion"], out["scales"], out["xy"], out["z"], cat
+
+    @staticmethod
+    def backward(ctx, g_q, g_s, g_xy, g_z, _g_cat):
+        cat, quat, xy = ctx.saved_tensors
+        b, h, w = cat.shape
+        dev = cat.device
+        f32 = torch.float32
+
+        def prep(g):
+            return None if g is None else g.to(f32).contiguous()
+        g_q, g_s, g_xy, g_z = prep(g_q), prep(g_s), prep(g_xy), prep(g_z)
+        d = [torch.empty(s, dtype=f32, device=dev) for s in ctx.shapes]
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fpc_class_compress_backward(
+                cat.data_ptr(), quat.data_ptr(), xy.data_ptr(), _lib.ptr(g_q), _lib.ptr(g_s), _lib.ptr(g_xy), _lib.ptr(g_z),
+                d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), b, ctx.num_of_classes, h, w,
+                _lib.current_stream(dev)))
+        return None, None, d[0], d[1], d[2], d[3]
+
+
+class AggregateFn(torch.autograd.Function):
+    """Class-compressed fields -> per-instance (quaternion, scales, z) and the masked dense xy; ``run`` does the forward
+    launches and returns (agg dict, labels [b,h,w] i32, pixel counts [n] i32, |mean quaternion| [n])."""
+
+    @staticmethod
+    def forward(ctx, run, q, s, xy, z):
+        agg, labels, counts, qnorm = run()
+        ctx.save_for_backward(labels, counts, qnorm, agg["quaternion"], agg["z"])
+        ctx.shape = tuple(labels.shape)
+        ctx.extra = {k: v for k, v in agg.items() if k not in ("quaternion", "scales", "z", "xy")}
+        return agg["quaternion"], agg["scales"], agg["z"], agg["xy"]
+
+    @staticmethod
+    def backward(ctx, g_q, g_s, g_z, g_xy):
+        labels, counts, qnorm, q_hat, z_val = ctx.saved_tensors
+        b, h, w = ctx.shape
+        dev, f32 = labels.device, torch.float32
+        n = int(counts.shape[0])
+        inv_c = (1.0 / counts.to(f32).clamp_min(1)).unsqueeze(1)
+        G = torch.zeros((n, 8), dtype=f32, device=dev)
+        if g_q is not None:
+            g = g_q.to(f32)
+            proj = (g - q_hat * (q_hat * g).sum(dim=1, keepdim=True)) / qnorm.unsqueeze(1).clamp_min(1e-30)
+            G[:, 0:4] = torch.where(qnorm.unsqueeze(1) != 0, proj, g) * inv_c       # zero-norm guard of normalize(): divide by 1
+        if g_s is not None:
+            G[:, 4:7] = g_s.to(f32) * inv_c
+        if g_z is not None:
+            G[:, 7:8] = g_z.to(f32).reshape(n, 1) * z_val.reshape(n, 1) * inv_c    # z = exp(mean)
+        g_xy = None if g_xy is None else g_xy.to(f32).contiguous()
+        d_q = torch.empty((b, 4, h, w), dtype=f32, device=dev)
+        d_s = torch.empty((b, 3, h, w), dtype=f32, device=dev)
+        d_xy = torch.empty((b, 2, h, w), dtype=f32, device=dev)
+        d_z = torch.empty((b, h, w), dtype=f32, device=dev)
+        G = G.contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fpc_aggregate_backward(labels.data_ptr(), G.data_ptr(), _lib.ptr(g_xy), n, d_q.data_ptr(),
+                                                         d_s.data_ptr(), d_xy.data_ptr(), d_z.data_ptr(), b, h, w,
+                                                         _lib.current_stream(dev)))
+        return None, d_q, d_s, d_xy, d_z

@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(FT) k_finalize(InstTables T, RowTables R, cons
     __shared__ double s_d[FT / 32][13];
     __shared__ int s_i[FT / 32][3];
     __shared__ float s_win[2];
-    __shared__ float s_ref[2];
+    __shared__ float s_ref[3];
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -673,6 +673,7 @@ __global__ void __launch_bounds__(FT) k_finalize(InstTables T, RowTables R, cons
             row[FPC_ROW_BBOX] = __int_as_float((T.ymin[i] << 16) | (T.xmin[i] & 0xffff));
             s_ref[0] = x;
             s_ref[1] = y;
+            s_ref[2] = qn;
         }
         if (pp.extra) {
             // ---- PVNet v4 / v5 extras: one more pass over the records with the refined point
@@ -710,8 +711,10 @@ __global__ void __launch_bounds__(FT) k_finalize(InstTables T, RowTables R, cons
                 double tot = 0.0;
                 int a = 0, c = 0;
                 for (int wq = 0; wq < FT / 32; ++wq) { tot += s_d[wq][0]; a += s_i[wq][0]; c += s_i[wq][1]; }
-                pp.extra[2 * (size_t)i] = tn > 0 ? (float)(tot / (double)a) : 1.f;         // v4 skip value: ones (:696)
-                pp.extra[2 * (size_t)i + 1] = tn > 0 ? (float)c / (float)tn : 0.f;           // v5 skip value: zeros (:793)
+                pp.extra[4 * (size_t)i] = tn > 0 ? (float)(tot / (double)a) : 1.f;         // v4 skip value: ones (:696)
+                pp.extra[4 * (size_t)i + 1] = tn > 0 ? (float)c / (float)tn : 0.f;           // v5 skip value: zeros (:793)
+                pp.extra[4 * (size_t)i + 2] = s_ref[2];                                      // |mean quaternion| before normalisation
+                pp.extra[4 * (size_t)i + 3] = 0.f;
             }
         }
     }

@@ -49,19 +49,34 @@ def _compress(num_of_classes: int, mask_logits, cat_mask, logits) -> th.Categori
         cat_mask = _lib.require_cuda(cat_mask, "cat_mask", torch.int64)
         if tuple(cat_mask.shape) != (b, h, w):
             raise RuntimeError(f"cat_mask must be [{b},{h},{w}]")
-    q_out = torch.empty((b, 4, h, w), dtype=f32, device=dev)
-    s_out = torch.empty((b, 3, h, w), dtype=f32, device=dev)
-    xy_out = torch.empty((b, 2, h, w), dtype=f32, device=dev)
-    z_out = torch.empty((b, h, w), dtype=f32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().fpc_class_compress(
-            _lib.ptr(mask_logits) if cat_mask is None else None, _lib.ptr(cat_mask),
-            quat.data_ptr(), scales.data_ptr(), xy.data_ptr(), z.data_ptr(),
-            _lib.ptr(cat_out), q_out.data_ptr(), s_out.data_ptr(), xy_out.data_ptr(), z_out.data_ptr(),
-            b, num_of_classes, h, w, _lib.current_stream(dev)))
-    out = {"quaternion": q_out, "scales": s_out, "xy": xy_out, "z": z_out}
-    if cat_out is not None:
-        out["mask"] = cat_out
+    def run():
+        q_out = torch.empty((b, 4, h, w), dtype=f32, device=dev)
+        s_out = torch.empty((b, 3, h, w), dtype=f32, device=dev)
+        xy_out = torch.empty((b, 2, h, w), dtype=f32, device=dev)
+        z_out = torch.empty((b, h, w), dtype=f32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fpc_class_compress(
+                _lib.ptr(mask_logits) if cat_mask is None else None, _lib.ptr(cat_mask),
+                quat.data_ptr(), scales.data_ptr(), xy.data_ptr(), z.data_ptr(),
+                _lib.ptr(cat_out), q_out.data_ptr(), s_out.data_ptr(), xy_out.data_ptr(), z_out.data_ptr(),
+                b, num_of_classes, h, w, _lib.current_stream(dev)))
+        res = {"quaternion": q_out, "scales": s_out, "xy": xy_out, "z": z_out}
+        if cat_out is not None:
+            res["mask"] = cat_out
+        else:
+            res["_cat_mask"] = cat_mask
+        return res
+
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (quat, scales, xy, z)):
+        # training: keep the graph (backward = fpc_class_compress_backward)
+        from .autograd import ClassCompressFn
+        q_o, s_o, xy_o, z_o, cat_o = ClassCompressFn.apply(run, num_of_classes, quat, scales, xy, z)
+        out = {"quaternion": q_o, "scales": s_o, "xy": xy_o, "z": z_o}
+        if cat_out is not None:
+            out["mask"] = cat_o
+        return out
+    out = run()
+    out.pop("_cat_mask", None)
     return out
 
 

@@ -46,7 +46,7 @@ def _vote(nprob, h, w, vn, fmask, imask, nplanes_per_src, match_base, vertex, ro
             hyp = torch.empty((nprob, round_hyp_num, 2), dtype=torch.float32, device=dev)
             votes = torch.empty((nprob, round_hyp_num), dtype=torch.int32, device=dev)
             a.hyp_out, a.vote_counts_out = hyp.data_ptr(), votes.data_ptr()
-            extra = torch.empty((nprob, 2), dtype=torch.float32, device=dev) if details is not None else None
+            extra = torch.empty((nprob, 4), dtype=torch.float32, device=dev) if details is not None else None
             if extra is not None:
                 a.extra_out = extra.data_ptr()
             keep = []

@@ -187,9 +187,10 @@ typedef struct fpc_recover_args {
      * (nn.UpsamplingBilinear2d(scale_factor=S), align_corners=True; lib/pose_regressor.py:633-666) is evaluated on the
      * fly inside the arg-max and gather kernels -- the [b,67,h,w] head maps are never written or read. */
     int32_t upsample;
-    /* Optional [max_instances,2] f32, fpc_vote_dense / fpc_pose_recover: per instance (residual variance of the
-     * refinement inliers about the refined point, PVNet v4 ransac_voting_gpu.py:757-759; fraction of the voters that
-     * vote for the refined point at threshold 0.999, PVNet v5 :855-857).  One extra pass over the instance's records. */
+    /* Optional [max_instances,4] f32: per instance (residual variance of the refinement inliers about the refined point,
+     * PVNet v4 ransac_voting_gpu.py:757-759; fraction of the voters that vote for the refined point at threshold 0.999,
+     * PVNet v5 :855-857; norm of the mean quaternion before its normalisation, needed by the backward of the aggregation;
+     * 0).  One extra pass over the instance's records. */
     float *extra_out;
 } fpc_recover_args;
 
@@ -295,6 +296,25 @@ FPC_API int fpc_pose_errors(const float *q_gt, const float *q_pred, const int64_
  * value < thresholds[t] (op 0, torch.less) or value > thresholds[t] (op 1, torch.greater). */
 FPC_API int fpc_threshold_fraction(const double *values, int n, const double *thresholds, int num_thresholds, int op, float *out,
                                    void *stream);
+
+/* ---- training support: backward of the two differentiable steps at the head of the path --------------------------
+ * (the reference trains its aggregated losses, lib/loss.py:155-545, through these torch ops)
+ *
+ * class_compress (lib/gpu_tensor_funcs.py:52-99).  g_* = gradients of the class-compressed fields ([b,4|3|2,h,w], z
+ * [b,h,w]; any may be NULL); d_* = gradients of the raw head maps ([b,4K|3K|2K|K,h,w], zero-filled here, then the
+ * predicted class's channels of foreground pixels are written; q / xy go through the Jacobian of their L2 normalisation,
+ * for which the raw `quaternion` / `xy` head maps are read). */
+FPC_API int fpc_class_compress_backward(const int64_t *cat_mask, const float *quaternion, const float *xy, const float *g_q,
+                                        const float *g_s, const float *g_xy, const float *g_z, float *d_quaternion,
+                                        float *d_scales, float *d_xy, float *d_z, int b, int num_classes, int h, int w,
+                                        void *stream);
+
+/* AggregationLayer.forward (lib/aggregation_layer.py:125-156).  labels [b,h,w] i32 from the forward call; inst_grads [n,8] =
+ * per-instance gradient of (q0..q3, s0..s2, z) w.r.t. ONE member pixel (the caller folds in 1/count, exp and the
+ * normalisation Jacobian: n small vectors); g_xy_dense [n,2,h,w] = gradient of the masked xy output or NULL.  Writes every
+ * element of d_q [b,4,h,w], d_s [b,3,h,w], d_xy [b,2,h,w], d_z [b,h,w] (zeros on background). */
+FPC_API int fpc_aggregate_backward(const int32_t *labels, const float *inst_grads, const float *g_xy_dense, int n, float *d_q,
+                                   float *d_s, float *d_xy, float *d_z, int b, int h, int w, void *stream);
 
 /* Number of kernels fpc_pose_recover launches per call (for launch accounting). */
 FPC_API int fpc_pose_recover_num_launches(void);

@@ -1,0 +1,86 @@
+"""GPU: training support.  Gradients through the drop-in class_compress / class_compression and AggregationLayer.forward
+against torch autograd through the oracle restatements of the reference's torch ops (oracle/port.py: the same ops the
+reference differentiates), for random upstream gradients: <= 1e-4 relative per tensor."""
+import types
+
+import pytest
+import torch
+
+import helpers
+from helpers import port, syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+KEYS = ("quaternion", "scales", "xy", "z")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def scene(seed=3):
+    frames = [[(30, 30, 14, 1), (90, 40, 18, 3), (60, 75, 12, 6)], [(40, 50, 20, 2), (52 + 20, 50, 12, 5)], []]   # two touching blobs in frame 1
+    return syn.render_heads(frames, 96, 128, seed=seed)
+
+
+def test_class_compress_backward():
+    import fastposecnn_b200 as fp
+    logits = scene()
+    g = torch.Generator().manual_seed(0)
+    # oracle: autograd through the reference's ops on the CPU
+    ref_in = {k: v.clone().requires_grad_(k in KEYS) for k, v in logits.items()}
+    ref_out = port.class_compression(ref_in, 7)
+    ups = {k: torch.randn(ref_out[k].shape, generator=g) for k in KEYS}
+    sum((ref_out[k] * ups[k]).sum() for k in KEYS).backward()
+    # drop-in on the GPU
+    gpu_in = {k: v.to(DEV).requires_grad_(k in KEYS) for k, v in logits.items()}
+    out = fp.class_compression(gpu_in, 7)
+    assert torch.equal(out["mask"].cpu(), ref_out["mask"]) and not out["mask"].requires_grad
+    for k in KEYS:
+        assert out[k].requires_grad and rel(out[k], ref_out[k]) <= 1e-6
+    sum((out[k] * ups[k].to(DEV)).sum() for k in KEYS).backward()
+    for k in KEYS:
+        assert gpu_in[k].grad is not None and gpu_in[k].grad.shape == logits[k].shape
+        assert rel(gpu_in[k].grad, ref_in[k].grad) <= helpers.REL_TOL, k
+        # only the predicted class's channels of foreground pixels receive gradient
+        assert int((gpu_in[k].grad != 0).sum()) <= int((ref_out["mask"] != 0).sum()) * out[k].shape[1] if out[k].dim() == 4 else True
+    # explicit cat_mask variant (gtf.class_compress) and partial upstream gradients (only scales used)
+    gpu_in2 = {k: v.to(DEV).requires_grad_(k in KEYS) for k, v in logits.items()}
+    out2 = fp.class_compress(7, out["mask"], gpu_in2)
+    (out2["scales"] * ups["scales"].to(DEV)).sum().backward()
+    assert rel(gpu_in2["scales"].grad, ref_in["scales"].grad) <= helpers.REL_TOL
+    assert gpu_in2["quaternion"].grad is None or float(gpu_in2["quaternion"].grad.abs().max()) == 0.0
+
+
+def test_aggregation_backward_chain():
+    """class_compression -> AggregationLayer, gradients all the way back to the raw head maps."""
+    import fastposecnn_b200 as fp
+    logits = scene(seed=5)
+    g = torch.Generator().manual_seed(1)
+    ref_in = {k: v.clone().requires_grad_(k in KEYS) for k, v in logits.items()}
+    ref_agg = port.aggregate(port.class_compression(ref_in, 7))
+    n = ref_agg["class_ids"].shape[0]
+    ups = {k: torch.randn(ref_agg[k].shape, generator=g) for k in KEYS}
+    sum((ref_agg[k] * ups[k]).sum() for k in KEYS).backward()
+
+    gpu_in = {k: v.to(DEV).requires_grad_(k in KEYS) for k, v in logits.items()}
+    layer = fp.AggregationLayer(types.SimpleNamespace(HV_NUM_OF_HYPOTHESES=32), 7)
+    agg = layer(fp.class_compression(gpu_in, 7))
+    assert agg["class_ids"].shape[0] == n and torch.equal(agg["class_ids"].cpu(), ref_agg["class_ids"].long())
+    assert torch.equal(agg["instance_masks"].cpu(), ref_agg["instance_masks"])
+    for k in KEYS:
+        assert agg[k].requires_grad and rel(agg[k], ref_agg[k]) <= helpers.REL_TOL, k
+    sum((agg[k] * ups[k].to(DEV)).sum() for k in KEYS).backward()
+    for k in KEYS:
+        assert rel(gpu_in[k].grad, ref_in[k].grad) <= helpers.REL_TOL, k
+
+
+def test_no_graph_without_requires_grad():
+    import fastposecnn_b200 as fp
+    logits = {k: v.to(DEV) for k, v in scene().items()}
+    out = fp.class_compression(logits, 7)
+    assert all(not out[k].requires_grad for k in KEYS)
+    with torch.no_grad():
+        gin = {k: v.clone().requires_grad_(k in KEYS) for k, v in logits.items()}
+        assert not fp.class_compression(gin, 7)["quaternion"].requires_grad
