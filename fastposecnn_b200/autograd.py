@@ -81,3 +81,52 @@ class AggregateFn(torch.autograd.Function):
                                                          d_s.data_ptr(), d_xy.data_ptr(), d_z.data_ptr(), b, h, w,
                                                          _lib.current_stream(dev)))
         return None, d_q, d_s, d_xy, d_z
+
+
+class PoseRecoverFn(torch.autograd.Function):
+    """The fused path as one differentiable node: raw head maps -> per-instance (quaternion, scales, z).  Backward = the two
+    kernels above chained (instance gradient -> class-compressed fields -> predicted class's channels of the raw maps).  The
+    voted centre ``xy`` (and T / RT, which depend on it) is returned without a gradient: the RANSAC refinement is not
+    differentiated here."""
+
+    @staticmethod
+    def forward(ctx, run, num_of_classes, quat, scales, z):
+        agg, labels, cat_u8, counts, qnorm = run()
+        ctx.save_for_backward(labels, cat_u8, counts, qnorm, agg["quaternion"], agg["z"], quat)
+        ctx.num_of_classes = num_of_classes
+        ctx.shapes = (quat.shape, scales.shape, z.shape)
+        return agg["quaternion"], agg["scales"], agg["z"]
+
+    @staticmethod
+    def backward(ctx, g_q, g_s, g_z):
+        labels, cat_u8, counts, qnorm, q_hat, z_val, quat = ctx.saved_tensors
+        b, h, w = labels.shape
+        dev, f32 = labels.device, torch.float32
+        n = int(counts.shape[0])
+        inv_c = (1.0 / counts.to(f32).clamp_min(1)).unsqueeze(1)
+        G = torch.zeros((n, 8), dtype=f32, device=dev)
+        if g_q is not None:
+            g = g_q.to(f32)
+            proj = (g - q_hat * (q_hat * g).sum(dim=1, keepdim=True)) / qnorm.unsqueeze(1).clamp_min(1e-30)
+            G[:, 0:4] = torch.where(qnorm.unsqueeze(1) != 0, proj, g) * inv_c
+        if g_s is not None:
+            G[:, 4:7] = g_s.to(f32) * inv_c
+        if g_z is not None:
+            G[:, 7:8] = g_z.to(f32).reshape(n, 1) * z_val.reshape(n, 1) * inv_c
+        c_q = torch.empty((b, 4, h, w), dtype=f32, device=dev)
+        c_s = torch.empty((b, 3, h, w), dtype=f32, device=dev)
+        c_xy = torch.empty((b, 2, h, w), dtype=f32, device=dev)
+        c_z = torch.empty((b, h, w), dtype=f32, device=dev)
+        d_q, d_s, d_z = (torch.empty(sh, dtype=f32, device=dev) for sh in ctx.shapes)
+        K = ctx.num_of_classes - 1
+        d_xy = torch.empty((b, 2 * K, h, w), dtype=f32, device=dev)
+        cat = cat_u8.to(torch.int64)
+        L, st = _lib.lib(), _lib.current_stream(dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.fpc_aggregate_backward(labels.data_ptr(), G.contiguous().data_ptr(), None, n, c_q.data_ptr(), c_s.data_ptr(),
+                                                c_xy.data_ptr(), c_z.data_ptr(), b, h, w, st))
+            # the fused forward normalises each pixel's quaternion before averaging: same Jacobian as class_compress
+            _lib.check(L.fpc_class_compress_backward(cat.data_ptr(), quat.data_ptr(), None, c_q.data_ptr(), c_s.data_ptr(), None,
+                                                     c_z.data_ptr(), d_q.data_ptr(), d_s.data_ptr(), d_xy.data_ptr(), d_z.data_ptr(),
+                                                     b, ctx.num_of_classes, h, w, st))
+        return None, None, d_q, d_s, d_z

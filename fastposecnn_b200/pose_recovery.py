@@ -61,6 +61,7 @@ class PoseRecoveryEngine:
         self._fetch_event = None
         self._graph = None
         self._idxs_keepalive = None
+        self.extra_out = None          # optional [max_instances,4] f32 (fpc_recover_args.extra_out), set by callers that need it
 
     def _base_args(self) -> RecoverArgs:
         a = RecoverArgs()
@@ -117,6 +118,8 @@ class PoseRecoveryEngine:
         if self.labels is not None:
             a.labels = self.labels.data_ptr()
         a.hyp_out, a.vote_counts_out = self.hyp.data_ptr(), self.votes.data_ptr()
+        if self.extra_out is not None:
+            a.extra_out = self.extra_out.data_ptr()
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
         a.stream = _lib.current_stream(self.device)
         if stage_events is not None:
@@ -302,9 +305,31 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
     # head maps may also be PINNED HOST tensors (read in place over PCIe); the device then comes from inv_intrinsics
     device = mask.device if mask.is_cuda else inv_intrinsics.device
     eng = get_engine(b, h, w, C, hn, device, want_labels=True, upsample=upsample, **engine_kw)
-    eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
-    n = eng.fetch_count()
-    agg = eng.table_to_agg(n)
+    heads = [logits[k] for k in ("quaternion", "scales", "z")]
+    if torch.is_grad_enabled() and upsample == 1 and any(t.requires_grad for t in heads):
+        # training: quaternion / scales / z of the result stay differentiable w.r.t. their head maps (autograd.PoseRecoverFn);
+        # each call gets its own tables so that the saved tensors survive later calls
+        from .autograd import PoseRecoverFn
+        holder = {}
+
+        def run():
+            extra = torch.zeros((eng.max_instances, 4), dtype=torch.float32, device=device)
+            eng.extra_out = extra
+            try:
+                eng.launch({k: v.detach() for k, v in logits.items()}, inv_intrinsics, idxs=idxs, select_u=select_u)
+            finally:
+                eng.extra_out = None
+            n_ = eng.fetch_count()
+            agg_ = {k: v.clone() for k, v in eng.table_to_agg(n_).items()}
+            holder["agg"], holder["n"] = agg_, n_
+            return agg_, eng.labels.clone(), eng.cat_mask_u8.clone(), agg_["mask_sizes"].to(torch.int32), extra[:n_, 2].clone()
+        q_o, s_o, z_o = PoseRecoverFn.apply(run, C, *heads)
+        agg, n = holder["agg"], holder["n"]
+        agg.update({"quaternion": q_o, "scales": s_o, "z": z_o})
+    else:
+        eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
+        n = eng.fetch_count()
+        agg = eng.table_to_agg(n)
     agg["cat_mask"] = eng.cat_mask_u8
     agg["labels"] = eng.labels
     if materialize_dense:

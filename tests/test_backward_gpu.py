@@ -84,3 +84,29 @@ def test_no_graph_without_requires_grad():
     with torch.no_grad():
         gin = {k: v.clone().requires_grad_(k in KEYS) for k, v in logits.items()}
         assert not fp.class_compression(gin, 7)["quaternion"].requires_grad
+
+
+def test_fused_path_backward():
+    """pose_recover as one differentiable node: gradients of (quaternion, scales, z) w.r.t. their raw head maps against
+    autograd through the oracle chain class_compression -> aggregate."""
+    import fastposecnn_b200 as fp
+    logits = scene(seed=7)
+    g = torch.Generator().manual_seed(2)
+    keys = ("quaternion", "scales", "z")
+    ref_in = {k: v.clone().requires_grad_(k in keys) for k, v in logits.items()}
+    ref_agg = port.aggregate(port.class_compression(ref_in, 7))
+    ups = {k: torch.randn(ref_agg[k].shape, generator=g) for k in keys}
+    sum((ref_agg[k] * ups[k]).sum() for k in keys).backward()
+    gpu_in = {k: v.to(DEV).requires_grad_(k in keys) for k, v in logits.items()}
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
+    out = fp.pose_recover(gpu_in, inv_k, 32)
+    assert out["quaternion"].requires_grad and not out["xy"].requires_grad
+    for k in keys:
+        assert rel(out[k], ref_agg[k]) <= helpers.REL_TOL, k
+    sum((out[k] * ups[k].to(DEV)).sum() for k in keys).backward()
+    for k in keys:
+        # the fused forward normalises pixel quaternions with rsqrt (1e-4 budget), so does its gradient
+        assert rel(gpu_in[k].grad, ref_in[k].grad) <= 2 * helpers.REL_TOL, k
+    # a second call must not disturb the first call's saved tensors
+    out2 = fp.pose_recover(gpu_in, inv_k, 32)
+    assert torch.equal(out2["class_ids"], out["class_ids"])
