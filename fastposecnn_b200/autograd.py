@@ -130,3 +130,37 @@ class PoseRecoverFn(torch.autograd.Function):
                                                      c_z.data_ptr(), d_q.data_ptr(), d_s.data_ptr(), d_xy.data_ptr(), d_z.data_ptr(),
                                                      b, ctx.num_of_classes, h, w, st))
         return None, None, d_q, d_s, d_z
+
+
+class RansacV3Fn(torch.autograd.Function):
+    """``ransac_voting_layer_v3`` differentiable w.r.t. ``vertex``: the refinement solve over the winner's inliers
+    (ransac_voting_gpu.py:584-598) is differentiated with the inlier set held constant, as autograd does in the reference
+    (the set enters there as a 0/1 weight).  ``run`` does the forward and returns (points [n,vn,2], per-keypoint details)."""
+
+    @staticmethod
+    def forward(ctx, run, fmask, vertex, inlier_thresh, arith):
+        pts, det = run()
+        ctx.save_for_backward(fmask, vertex, pts.detach(), torch.stack([d["best_pts"] for d in det], dim=1),
+                              torch.stack([d["tn"] for d in det], dim=1).to(torch.int32))
+        ctx.inlier_thresh, ctx.arith = float(inlier_thresh), int(arith)
+        return pts
+
+    @staticmethod
+    def backward(ctx, g_pts):
+        fmask, vertex, pts, win, tn = ctx.saved_tensors
+        n, h, w, vn, _ = vertex.shape
+        dev, f32 = vertex.device, torch.float32
+        grad = torch.empty((n, h, w, vn, 2), dtype=f32, device=dev)
+        tmp = torch.empty((n, h, w, 2), dtype=f32, device=dev)
+        g_pts = g_pts.to(f32)
+        for vi in range(vn):
+            v = vertex[..., vi, :]
+            sN, sH, sW, s2 = v.stride()
+            wp, rp, gx = win[:, vi].contiguous(), pts[:, vi].contiguous(), g_pts[:, vi].contiguous()
+            live = (tn[:, vi] > 0).to(torch.int32).contiguous()
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().fpc_vote_refine_backward(fmask.data_ptr(), v.data_ptr(), sN, sH, sW, s2, wp.data_ptr(),
+                                                               rp.data_ptr(), gx.data_ptr(), live.data_ptr(), ctx.inlier_thresh, n, h, w,
+                                                               ctx.arith, tmp.data_ptr(), _lib.current_stream(dev)))
+            grad[..., vi, :] = tmp
+        return None, None, grad, None, None

@@ -4,7 +4,7 @@
 //   * class_compress  (lib/gpu_tensor_funcs.py:52-99): per pixel the predicted class's channels, q / xy L2-normalised;
 //   * AggregationLayer (lib/aggregation_layer.py:125-156): masked means per instance (exp for z, normalise for q), masked xy.
 // Both are per-pixel scatters: HBM-bound, every gradient element written exactly once.
-#include "fpc_common.cuh"
+#include "fpc_internal.cuh"
 
 namespace fpc {
 namespace {
@@ -144,6 +144,17 @@ int fpc_aggregate_backward(const int32_t *labels, const float *inst_grads, const
                                                                            h * w, (int)P);
     FPC_LAUNCH_CHECK("k_aggregate_backward");
     return FPC_OK;
+}
+
+int fpc_vote_refine_backward(const float *fmask, const float *vertex, long long sN, long long sH, long long sW, long long s2,
+                             const float *win_pts, const float *refined, const float *g_x, const int32_t *live, float inlier_thresh,
+                             int n, int h, int w, int arith, float *d_vertex, void *stream) {
+    if (n < 0 || h <= 0 || w <= 0) return fail(FPC_EINVAL, "bad size");
+    if (n == 0) return FPC_OK;
+    if (!fmask || !vertex || !win_pts || !refined || !g_x || !live || !d_vertex) return fail(FPC_EINVAL, "NULL pointer");
+    if (arith != FPC_ARITH_IEEE && arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", arith);
+    return launch_vote_refine_backward(fmask, vertex, sN, sH, sW, s2, win_pts, refined, g_x, live, inlier_thresh, n, h, w, arith,
+                                       d_vertex, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -732,6 +732,80 @@ __global__ void __launch_bounds__(128) k_get_rt(const float *__restrict__ q, con
 }
 
 // =============================================================================================
+// Training support: backward of the refinement solve (ransac_voting_gpu.py:584-598) w.r.t. the direction field.
+// x* = A^-1 b with A = sum n n^T, b = sum n (n . c) over the winner's inliers (n = (dir_y, -dir_x)); the inlier set is a
+// constant of the differentiation, exactly as in the reference where it enters as a 0/1 weight.  For an upstream
+// gradient g on x*:  u = A^+ g,  r = c - x*,  dL/dn = (n . r) u + r (n . u),  dL/d dir = (-dn_y, dn_x).
+// Block per instance, two passes over its [h,w] plane; every element of d_vertex is written (zeros off the inlier set).
+// =============================================================================================
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_vote_refine_backward(const float *__restrict__ fmask, const float *__restrict__ vertex,
+                                                              long long sN, long long sH, long long sW, long long s2,
+                                                              const float *__restrict__ win_pts, const float *__restrict__ refined,
+                                                              const float *__restrict__ g_x, const int *__restrict__ live, float thresh,
+                                                              int h, int w, float *__restrict__ d_vertex) {
+    __shared__ double s_a[8][3];
+    __shared__ double s_u[2];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int hw = h * w;
+    const float wx = win_pts[2 * i], wy = win_pts[2 * i + 1];
+    const bool on = live[i] != 0;
+    const float *mk = fmask + (size_t)i * hw;
+    const float *vt = vertex + (long long)i * sN;
+    double a00 = 0, a01 = 0, a11 = 0;
+    if (on)
+        for (int p = tid; p < hw; p += 256) {
+            if (mk[p] == 0.f) continue;
+            const int y = p / w, x = p - y * w;
+            const float dx = vt[(long long)y * sH + (long long)x * sW], dy = vt[(long long)y * sH + (long long)x * sW + s2];
+            if (!vote_exact<ARITH>((float)x, (float)y, dx, dy, wx, wy, thresh)) continue;
+            const double nx = dy, ny = -(double)dx;
+            a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;
+        }
+    a00 = warp_sum_d(a00); a01 = warp_sum_d(a01); a11 = warp_sum_d(a11);
+    if (lane == 0) { s_a[wv][0] = a00; s_a[wv][1] = a01; s_a[wv][2] = a11; }
+    __syncthreads();
+    if (tid == 0) {
+        double t0 = 0, t1 = 0, t2 = 0, ux = 0, uy = 0;
+        for (int k = 0; k < 8; ++k) { t0 += s_a[k][0]; t1 += s_a[k][1]; t2 += s_a[k][2]; }
+        if (on) solve_sym2_pinv(t0, t1, t2, (double)g_x[2 * i], (double)g_x[2 * i + 1], ux, uy);
+        s_u[0] = ux;
+        s_u[1] = uy;
+    }
+    __syncthreads();
+    const double ux = s_u[0], uy = s_u[1];
+    const double rx0 = refined[2 * i], ry0 = refined[2 * i + 1];
+    float2 *out = reinterpret_cast<float2 *>(d_vertex) + (size_t)i * hw;
+    for (int p = tid; p < hw; p += 256) {
+        float2 g = make_float2(0.f, 0.f);
+        if (on && mk[p] != 0.f) {
+            const int y = p / w, x = p - y * w;
+            const float dx = vt[(long long)y * sH + (long long)x * sW], dy = vt[(long long)y * sH + (long long)x * sW + s2];
+            if (vote_exact<ARITH>((float)x, (float)y, dx, dy, wx, wy, thresh)) {
+                const double nx = dy, ny = -(double)dx;
+                const double rx = (double)x - rx0, ry = (double)y - ry0;
+                const double nr = nx * rx + ny * ry, nu = nx * ux + ny * uy;
+                const double gnx = nr * ux + rx * nu, gny = nr * uy + ry * nu;
+                g = make_float2((float)(-gny), (float)gnx);
+            }
+        }
+        out[p] = g;
+    }
+}
+
+int launch_vote_refine_backward(const float *fmask, const float *vertex, long long sN, long long sH, long long sW, long long s2,
+                                const float *win_pts, const float *refined, const float *g_x, const int *live, float thresh, int n,
+                                int h, int w, int arith, float *d_vertex, cudaStream_t st) {
+    if (n == 0) return FPC_OK;
+    if (arith == FPC_ARITH_IEEE)
+        k_vote_refine_backward<FPC_ARITH_IEEE><<<n, 256, 0, st>>>(fmask, vertex, sN, sH, sW, s2, win_pts, refined, g_x, live, thresh, h, w, d_vertex);
+    else
+        k_vote_refine_backward<FPC_ARITH_NVCC_FMA><<<n, 256, 0, st>>>(fmask, vertex, sN, sH, sW, s2, win_pts, refined, g_x, live, thresh, h, w, d_vertex);
+    FPC_LAUNCH_CHECK("k_vote_refine_backward");
+    return FPC_OK;
+}
+
+// =============================================================================================
 // host-side launchers
 // =============================================================================================
 int launch_generate_hypothesis(const float *direct, const float *coords, const int *idxs, float *hypo, int tn, int vn,

@@ -106,6 +106,19 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
         raise RuntimeError(f"expected mask [b,h,w] and vertex [b,h,w,vn,2], got {tuple(mask.shape)}, {tuple(vertex.shape)}")
     fmask = mask if (mask.dtype == torch.float32 and mask.is_contiguous()) else mask.to(torch.float32).contiguous()
     su = _select_u(select_mask, select_u, (b, h, w), vertex.device)
+    if torch.is_grad_enabled() and vertex.requires_grad and b > 0:
+        # training: the refined centres stay differentiable w.r.t. the direction field (autograd.RansacV3Fn)
+        from ..autograd import RansacV3Fn
+        if su is not None or bool((fmask.flatten(1) != 0).sum(dim=1).max() > max_num):
+            raise NotImplementedError("ransac_voting_layer_v3 backward: instances sub-sampled to max_num are not differentiable here")
+
+        def run():
+            det = details if details is not None else []
+            first = len(det)
+            pts = _vote(b, h, w, vn, fmask, None, 1, 0, vertex.detach(), int(round_hyp_num), inlier_thresh, min_num, max_num, True,
+                        idxs, None, det, arith)
+            return pts, det[first:]
+        return RansacV3Fn.apply(run, fmask, vertex, inlier_thresh, _lib.ARITH_IEEE if arith is None else int(arith))
     return _vote(b, h, w, vn, fmask, None, 1, 0, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num, True,
                  idxs, su, details, arith)
 

@@ -316,6 +316,16 @@ FPC_API int fpc_class_compress_backward(const int64_t *cat_mask, const float *qu
 FPC_API int fpc_aggregate_backward(const int32_t *labels, const float *inst_grads, const float *g_xy_dense, int n, float *d_q,
                                    float *d_s, float *d_xy, float *d_z, int b, int h, int w, void *stream);
 
+/* Backward of the refinement solve of ransac_voting_layer_v3 (ransac_voting_gpu.py:584-598) w.r.t. the direction field.
+ * fmask [n,h,w] f32 and vertex (element strides sN, sH, sW, s2 as in fpc_vote_dense) are the forward inputs; win_pts [n,2]
+ * the winning hypotheses (they define the inlier set, a constant of the differentiation as in the reference), refined [n,2]
+ * the forward result, g_x [n,2] its gradient, live [n] i32 = 0 for instances the forward skipped (< min_num pixels).
+ * d_vertex [n,h,w,2] contiguous: every element written (zeros off the inlier set). */
+FPC_API int fpc_vote_refine_backward(const float *fmask, const float *vertex, long long sN, long long sH, long long sW,
+                                     long long s2, const float *win_pts, const float *refined, const float *g_x,
+                                     const int32_t *live, float inlier_thresh, int n, int h, int w, int arith, float *d_vertex,
+                                     void *stream);
+
 /* Number of kernels fpc_pose_recover launches per call (for launch accounting). */
 FPC_API int fpc_pose_recover_num_launches(void);
 

@@ -110,3 +110,58 @@ def test_fused_path_backward():
     # a second call must not disturb the first call's saved tensors
     out2 = fp.pose_recover(gpu_in, inv_k, 32)
     assert torch.equal(out2["class_ids"], out["class_ids"])
+
+
+@pytest.mark.parametrize("vn", [1, 2])
+def test_voting_refinement_backward(vn):
+    """ransac_voting_layer_v3: gradient of the refined centres w.r.t. the direction field against autograd through the
+    oracle driver (same fixed pixel pairs, same inlier sets)."""
+    from fastposecnn_b200 import ransac_voting_layer_v3
+    frames = [[(30, 30, 14, 1)], [(64, 48, 22, 3)], [(100, 60, 1.0, 2)], []]
+    logits = syn.render_heads(frames, 96, 128, seed=7)
+    cat = port.class_compression(logits, 7)
+    mask = (cat["mask"] != 0).float()
+    vertex = cat["xy"].permute(0, 2, 3, 1).unsqueeze(3)
+    if vn > 1:
+        vertex = torch.cat([vertex, vertex.flip(-1) * torch.tensor([1.0, -1.0])], dim=3)
+    vertex = vertex.contiguous()
+    hn = 40
+    log = []
+    src = port.seeded_idx_source(3)
+
+    def draw(i, hn_, vn_, tn):
+        t = src(i, hn_, vn_, tn)
+        log.append((i, t))
+        return t
+    ref_v = vertex.clone().requires_grad_(True)
+    ref_pts = port.ransac_voting_layer_v3(mask, ref_v, hn, idx_source=draw)
+    up = torch.randn(ref_pts.shape, generator=torch.Generator().manual_seed(4))
+    (ref_pts * up).sum().backward()
+    idxs = torch.zeros((mask.shape[0], hn, vn, 2), dtype=torch.int32)
+    for i, t in log:
+        idxs[i] = t
+    gpu_v = vertex.to(DEV).requires_grad_(True)
+    pts = ransac_voting_layer_v3(mask.to(DEV), gpu_v, hn, idxs=idxs.to(DEV))
+    assert pts.requires_grad and helpers.rel_err(pts.reshape(-1, 2), ref_pts.detach().reshape(-1, 2)) <= helpers.REL_TOL
+    (pts * up.to(DEV)).sum().backward()
+    assert gpu_v.grad.shape == vertex.shape
+    assert rel(gpu_v.grad, ref_v.grad) <= 1e-3
+    # gradient only on inlier pixels of live instances: nothing outside the masks, nothing for the 5-pixel / empty frames' background
+    assert float(gpu_v.grad[mask.to(DEV) == 0].abs().max()) == 0.0
+    assert float(gpu_v.grad[3].abs().max()) == 0.0
+
+
+def test_full_chain_to_the_xy_head():
+    """class_compression -> AggregationLayer -> HoughVotingLayer: a loss on the voted centres reaches the raw xy head map."""
+    import fastposecnn_b200 as fp
+    logits = {k: v.to(DEV) for k, v in scene(seed=9).items()}
+    logits["xy"].requires_grad_(True)
+    hp = types.SimpleNamespace(HV_NUM_OF_HYPOTHESES=32)
+    agg = fp.HoughVotingLayer(hp)(fp.AggregationLayer(hp, 7)(fp.class_compression(logits, 7)))
+    assert agg["xy"].shape[1:] == (2,) and agg["xy"].requires_grad
+    target = agg["xy"].detach() + 1.0
+    ((agg["xy"] - target) ** 2).sum().backward()
+    g = logits["xy"].grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+    fg = fp.class_compression({k: v.detach() for k, v in logits.items()}, 7)["mask"] != 0
+    assert float(g.permute(0, 2, 3, 1)[~fg].abs().max()) == 0.0          # background pixels carry no gradient
