@@ -10,7 +10,7 @@ from oracle import native
 masks_st = st.integers(0, 2 ** 31 - 1).map(lambda s: np.random.default_rng(s))
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(rng=masks_st, n1=st.integers(0, 5), n2=st.integers(0, 5), h=st.integers(1, 9), w=st.integers(1, 40))
 def test_iou_matrix_is_the_pairwise_definition(rng, n1, n2, h, w):
     a = torch.from_numpy((rng.random((n1, h, w)) > 0.5).astype(np.float32))
@@ -23,7 +23,7 @@ def test_iou_matrix_is_the_pairwise_definition(rng, n1, n2, h, w):
             assert torch.equal(got[i, j], want) or (torch.isnan(got[i, j]) and torch.isnan(want))
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(rng=masks_st, ng=st.integers(1, 8), np_=st.integers(0, 8))
 def test_pairing_rule(rng, ng, np_):
     gc = torch.from_numpy(rng.integers(1, 4, ng))
@@ -43,7 +43,7 @@ def test_pairing_rule(rng, ng, np_):
     assert order.tolist() == sorted(kept, key=lambda i: (int(gc[i]), i))
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(hl=st.integers(2, 12), wl=st.integers(2, 12), scale=st.integers(1, 5), a=st.floats(-2, 2), b=st.floats(-2, 2), c=st.floats(-5, 5))
 def test_upsampling_reproduces_affine_planes_and_corners(hl, wl, scale, a, b, c):
     ys, xs = torch.meshgrid(torch.arange(hl, dtype=torch.float32), torch.arange(wl, dtype=torch.float32), indexing="ij")
@@ -60,7 +60,7 @@ def test_upsampling_reproduces_affine_planes_and_corners(hl, wl, scale, a, b, c)
     assert float(up.min()) >= float(plane.min()) - 1e-5 and float(up.max()) <= float(plane.max()) + 1e-5
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(rng=masks_st, b=st.integers(1, 3), h=st.integers(1, 12), w=st.integers(1, 16))
 def test_labels_are_raster_ordered_and_never_cross_images(rng, b, h, w):
     fg = torch.from_numpy(rng.random((b, h, w)) > 0.55)
