@@ -164,3 +164,30 @@ class RansacV3Fn(torch.autograd.Function):
                                                                ctx.arith, tmp.data_ptr(), _lib.current_stream(dev)))
             grad[..., vi, :] = tmp
         return None, None, grad, None, None
+
+
+class GetRTFn(torch.autograd.Function):
+    """``batchwise_get_RT`` differentiable w.r.t. (q, xys, exp_zs); ``run`` does the forward launch."""
+
+    @staticmethod
+    def forward(ctx, run, q, xys, exp_zs, inv_k):
+        R, T, RT = run()
+        ctx.save_for_backward(q, xys, exp_zs, inv_k)
+        return R, T, RT
+
+    @staticmethod
+    def backward(ctx, g_R, g_T, g_RT):
+        q, xys, exp_zs, inv_k = ctx.saved_tensors
+        n, dev, f32 = q.shape[0], q.device, torch.float32
+
+        def prep(g):
+            return None if g is None else g.to(f32).contiguous()
+        g_R, g_T, g_RT = prep(g_R), prep(g_T), prep(g_RT)
+        d_q = torch.empty((n, 4), dtype=f32, device=dev)
+        d_xy = torch.empty((n, 2), dtype=f32, device=dev)
+        d_z = torch.empty(exp_zs.shape, dtype=f32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fpc_get_rt_backward(q.data_ptr(), xys.data_ptr(), exp_zs.data_ptr(), inv_k.data_ptr(), _lib.ptr(g_R),
+                                                      _lib.ptr(g_T), _lib.ptr(g_RT), n, d_q.data_ptr(), d_xy.data_ptr(), d_z.data_ptr(),
+                                                      _lib.current_stream(dev)))
+        return None, d_q, d_xy, d_z, None

@@ -104,6 +104,63 @@ __global__ void __launch_bounds__(256) k_aggregate_backward(const int *__restric
     d_xy[((size_t)bi * 2 + 1) * HW + pix] = gy;
 }
 
+// Backward of batchwise_get_RT (lib/gpu_tensor_funcs.py:204-235 with quats_2_rotation_matrix :306-326), thread per instance.
+// Forward in closed form: qn = q/|q| = (a,b,c,d), R = M(a,b,c,d)^T, t = K^-1 (x zz, y zz, zz) with zz = z/1000,
+// RT = [[R, -R t], [0 0 0 1]].
+__global__ void __launch_bounds__(128) k_get_rt_backward(const float *__restrict__ q_in, const float *__restrict__ xy, const float *__restrict__ z_in,
+                                                         const float *__restrict__ inv_k, const float *__restrict__ gR,
+                                                         const float *__restrict__ gT, const float *__restrict__ gRT, int n,
+                                                         float *__restrict__ d_q, float *__restrict__ d_xy, float *__restrict__ d_z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double q0 = q_in[4 * i], q1 = q_in[4 * i + 1], q2 = q_in[4 * i + 2], q3 = q_in[4 * i + 3];
+    const double nq = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), sn = nq > 0.0 ? nq : 1.0;
+    const double a = q0 / sn, b = q1 / sn, c = q2 / sn, d = q3 / sn;
+    const double x = xy[2 * i], y = xy[2 * i + 1], zz = (double)z_in[i] / 1000.0;
+    double k[9];
+    for (int j = 0; j < 9; ++j) k[j] = inv_k[j];
+    const double h[3] = {x * zz, y * zz, zz};
+    double t[3];
+    for (int r = 0; r < 3; ++r) t[r] = k[3 * r] * h[0] + k[3 * r + 1] * h[1] + k[3 * r + 2] * h[2];
+    double m[3][3];
+    m[0][0] = a * a - b * b - c * c + d * d; m[0][1] = 2 * (a * b + c * d); m[0][2] = 2 * (a * c - b * d);
+    m[1][0] = 2 * (a * b - c * d); m[1][1] = -a * a + b * b - c * c + d * d; m[1][2] = 2 * (b * c + a * d);
+    m[2][0] = 2 * (a * c + b * d); m[2][1] = 2 * (b * c - a * d); m[2][2] = -a * a - b * b + c * c + d * d;
+    // upstream gradients gathered on R (= M^T) and t
+    double GR[3][3], gcol[3], gt[3];
+    for (int r = 0; r < 3; ++r) {
+        gcol[r] = gRT ? (double)gRT[16 * i + 4 * r + 3] : 0.0;
+        for (int cc = 0; cc < 3; ++cc)
+            GR[r][cc] = (gR ? (double)gR[9 * i + 3 * r + cc] : 0.0) + (gRT ? (double)gRT[16 * i + 4 * r + cc] : 0.0) - gcol[r] * t[cc];
+    }
+    for (int cc = 0; cc < 3; ++cc) {
+        double acc = gT ? (double)gT[3 * i + cc] : 0.0;
+        for (int r = 0; r < 3; ++r) acc -= m[cc][r] * gcol[r];          // -(R^T gcol)_cc, R^T = M
+        gt[cc] = acc;
+    }
+    double gh[3];
+    for (int cc = 0; cc < 3; ++cc) gh[cc] = k[cc] * gt[0] + k[3 + cc] * gt[1] + k[6 + cc] * gt[2];   // K^-T gt
+    d_xy[2 * i] = (float)(gh[0] * zz);
+    d_xy[2 * i + 1] = (float)(gh[1] * zz);
+    d_z[i] = (float)((gh[0] * x + gh[1] * y + gh[2]) / 1000.0);
+    double G[3][3];                                                        // gradient on M: G = GR^T
+    for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) G[r][cc] = GR[cc][r];
+    const double ga = 2 * (a * G[0][0] + b * G[0][1] + c * G[0][2] + b * G[1][0] - a * G[1][1] + d * G[1][2] + c * G[2][0] - d * G[2][1] - a * G[2][2]);
+    const double gb = 2 * (-b * G[0][0] + a * G[0][1] - d * G[0][2] + a * G[1][0] + b * G[1][1] + c * G[1][2] + d * G[2][0] + c * G[2][1] - b * G[2][2]);
+    const double gc = 2 * (-c * G[0][0] + d * G[0][1] + a * G[0][2] - d * G[1][0] - c * G[1][1] + b * G[1][2] + a * G[2][0] + b * G[2][1] + c * G[2][2]);
+    const double gd = 2 * (d * G[0][0] + c * G[0][1] - b * G[0][2] - c * G[1][0] + d * G[1][1] + a * G[1][2] + b * G[2][0] - a * G[2][1] + d * G[2][2]);
+    if (nq > 0.0) {
+        const double dot = a * ga + b * gb + c * gc + d * gd;
+        d_q[4 * i] = (float)((ga - a * dot) / nq);
+        d_q[4 * i + 1] = (float)((gb - b * dot) / nq);
+        d_q[4 * i + 2] = (float)((gc - c * dot) / nq);
+        d_q[4 * i + 3] = (float)((gd - d * dot) / nq);
+    } else {
+        d_q[4 * i] = (float)ga; d_q[4 * i + 1] = (float)gb; d_q[4 * i + 2] = (float)gc; d_q[4 * i + 3] = (float)gd;
+    }
+}
+
 }  // namespace
 }  // namespace fpc
 
@@ -143,6 +200,16 @@ int fpc_aggregate_backward(const int32_t *labels, const float *inst_grads, const
     k_aggregate_backward<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(labels, inst_grads, g_xy_dense, n, d_q, d_s, d_xy, d_z,
                                                                            h * w, (int)P);
     FPC_LAUNCH_CHECK("k_aggregate_backward");
+    return FPC_OK;
+}
+
+int fpc_get_rt_backward(const float *q, const float *xy, const float *z, const float *inv_k, const float *g_R, const float *g_T,
+                        const float *g_RT, int n, float *d_q, float *d_xy, float *d_z, void *stream) {
+    if (n < 0) return fail(FPC_EINVAL, "negative size");
+    if (n == 0) return FPC_OK;
+    if (!q || !xy || !z || !inv_k || !d_q || !d_xy || !d_z) return fail(FPC_EINVAL, "NULL pointer");
+    k_get_rt_backward<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(q, xy, z, inv_k, g_R, g_T, g_RT, n, d_q, d_xy, d_z);
+    FPC_LAUNCH_CHECK("k_get_rt_backward");
     return FPC_OK;
 }
 

@@ -102,13 +102,19 @@ def batchwise_get_RT(q: torch.Tensor, xys: torch.Tensor, exp_zs: torch.Tensor, i
     n = q.shape[0]
     if tuple(q.shape) != (n, 4) or tuple(xys.shape) != (n, 2) or exp_zs.numel() != n or tuple(inv_k.shape) != (3, 3):
         raise RuntimeError("batchwise_get_RT: expected q [n,4], xys [n,2], exp_zs [n,1], inv_intrinsics [3,3]")
-    R = torch.empty((n, 3, 3), dtype=f32, device=q.device)
-    T = torch.empty((n, 3), dtype=f32, device=q.device)
-    RT = torch.empty((n, 4, 4), dtype=f32, device=q.device)
-    with torch.cuda.device(q.device):
-        _lib.check(_lib.lib().fpc_get_rt(q.data_ptr(), xys.data_ptr(), exp_zs.data_ptr(), inv_k.data_ptr(),
-                                         R.data_ptr(), T.data_ptr(), RT.data_ptr(), n, _lib.current_stream(q.device)))
-    return R, T, RT
+    def run():
+        R = torch.empty((n, 3, 3), dtype=f32, device=q.device)
+        T = torch.empty((n, 3), dtype=f32, device=q.device)
+        RT = torch.empty((n, 4, 4), dtype=f32, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(_lib.lib().fpc_get_rt(q.data_ptr(), xys.data_ptr(), exp_zs.data_ptr(), inv_k.data_ptr(),
+                                             R.data_ptr(), T.data_ptr(), RT.data_ptr(), n, _lib.current_stream(q.device)))
+        return R, T, RT
+
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (q, xys, exp_zs)):
+        from .autograd import GetRTFn
+        return GetRTFn.apply(run, q, xys, exp_zs, inv_k)
+    return run()
 
 
 def samplewise_get_RT(agg_data: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor):

@@ -316,6 +316,11 @@ FPC_API int fpc_class_compress_backward(const int64_t *cat_mask, const float *qu
 FPC_API int fpc_aggregate_backward(const int32_t *labels, const float *inst_grads, const float *g_xy_dense, int n, float *d_q,
                                    float *d_s, float *d_xy, float *d_z, int b, int h, int w, void *stream);
 
+/* Backward of fpc_get_rt (lib/gpu_tensor_funcs.py:204-235, 306-326): gradients g_R [n,3,3], g_T [n,3], g_RT [n,4,4] (any may
+ * be NULL) -> d_q [n,4], d_xy [n,2], d_z [n]. */
+FPC_API int fpc_get_rt_backward(const float *q, const float *xy, const float *z, const float *inv_k, const float *g_R,
+                                const float *g_T, const float *g_RT, int n, float *d_q, float *d_xy, float *d_z, void *stream);
+
 /* Backward of the refinement solve of ransac_voting_layer_v3 (ransac_voting_gpu.py:584-598) w.r.t. the direction field.
  * fmask [n,h,w] f32 and vertex (element strides sN, sH, sW, s2 as in fpc_vote_dense) are the forward inputs; win_pts [n,2]
  * the winning hypotheses (they define the inlier set, a constant of the differentiation as in the reference), refined [n,2]

@@ -165,3 +165,31 @@ def test_full_chain_to_the_xy_head():
     assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
     fg = fp.class_compression({k: v.detach() for k, v in logits.items()}, 7)["mask"] != 0
     assert float(g.permute(0, 2, 3, 1)[~fg].abs().max()) == 0.0          # background pixels carry no gradient
+
+
+def test_get_rt_backward():
+    """batchwise_get_RT: gradients of (R, T, RT) w.r.t. (q, xy, z) against autograd through the oracle (two torch.inverse)."""
+    import fastposecnn_b200 as fp
+    g = torch.Generator().manual_seed(5)
+    n = 40
+    q = torch.randn(n, 4, generator=g) * 1.7                      # not normalised: the normalisation is part of the function
+    xy = torch.rand(n, 2, generator=g) * torch.tensor([640.0, 480.0])
+    z = 700 + 600 * torch.rand(n, 1, generator=g)
+    inv_k = torch.inverse(syn.camera_intrinsics())
+    ups = [torch.randn(n, 3, 3, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 4, 4, generator=g)]
+    ref = [t.clone().requires_grad_(True) for t in (q, xy, z)]
+    outs = port.batchwise_get_RT(*ref, inv_k)
+    sum((o * u).sum() for o, u in zip(outs, ups)).backward()
+    gpu = [t.to(DEV).requires_grad_(True) for t in (q, xy, z)]
+    R, T, RT = fp.batchwise_get_RT(*gpu, inv_k.to(DEV))
+    assert R.requires_grad and rel(RT, outs[2]) <= helpers.REL_TOL
+    sum((o * u.to(DEV)).sum() for o, u in zip((R, T, RT), ups)).backward()
+    for a, b, name in zip(gpu, ref, ("q", "xy", "z")):
+        assert a.grad.shape == b.grad.shape and rel(a.grad, b.grad) <= 1e-3, name
+    # only one output used upstream
+    gpu2 = [t.to(DEV).requires_grad_(True) for t in (q, xy, z)]
+    fp.batchwise_get_RT(*gpu2, inv_k.to(DEV))[1].sum().backward()
+    ref2 = [t.clone().requires_grad_(True) for t in (q, xy, z)]
+    port.batchwise_get_RT(*ref2, inv_k)[1].sum().backward()
+    assert rel(gpu2[1].grad, ref2[1].grad) <= 1e-4 and rel(gpu2[2].grad, ref2[2].grad) <= 1e-4
+    assert float(gpu2[0].grad.abs().max()) == 0.0
