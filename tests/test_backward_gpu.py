@@ -193,3 +193,41 @@ def test_get_rt_backward():
     port.batchwise_get_RT(*ref2, inv_k)[1].sum().backward()
     assert rel(gpu2[1].grad, ref2[1].grad) <= 1e-4 and rel(gpu2[2].grad, ref2[2].grad) <= 1e-4
     assert float(gpu2[0].grad.abs().max()) == 0.0
+
+
+def test_whole_drop_in_chain_gradients_vs_reference_chain():
+    """Capstone: class_compression -> AggregationLayer -> HoughVotingLayer -> samplewise_get_RT with a loss on every
+    differentiable output (quaternion, scales, z, voted xy, R, T, RT); gradients w.r.t. all four raw regression head maps
+    against autograd through the oracle's restatement of the same chain, on the same fixed pixel pairs."""
+    import fastposecnn_b200 as fp
+    logits = scene(seed=11)
+    hn = 32
+    inv_k = torch.inverse(syn.camera_intrinsics())
+    keys = ("quaternion", "scales", "z", "xy", "R", "T", "RT")
+    ref_in = {k: v.clone().requires_grad_(k in KEYS) for k, v in logits.items()}
+    log = []
+    src = port.seeded_idx_source(8)
+
+    def draw(i, hn_, vn_, tn):
+        t = src(i, hn_, vn_, tn)
+        log.append((i, t))
+        return t
+    _, ref = port.pose_recover(ref_in, inv_k, hn, idx_source=draw)
+    n = ref["class_ids"].shape[0]
+    g = torch.Generator().manual_seed(9)
+    ups = {k: torch.randn(ref[k].shape, generator=g) * (0.01 if k in ("xy", "T", "RT") else 1.0) for k in keys}
+    sum((ref[k] * ups[k]).sum() for k in keys).backward()
+
+    idxs = torch.zeros((n, hn, 1, 2), dtype=torch.int32)
+    for i, t in log:
+        idxs[i] = t
+    gpu_in = {k: v.to(DEV).requires_grad_(k in KEYS) for k, v in logits.items()}
+    hp = types.SimpleNamespace(HV_NUM_OF_HYPOTHESES=hn)
+    agg = fp.AggregationLayer(hp, 7)(fp.class_compression(gpu_in, 7))
+    agg = fp.HoughVotingLayer(hp)(agg, idxs=idxs.to(DEV))
+    agg = fp.samplewise_get_RT(agg, inv_k.to(DEV))
+    for k in keys:
+        assert agg[k].requires_grad and rel(agg[k], ref[k]) <= helpers.REL_TOL, k
+    sum((agg[k] * ups[k].to(DEV)).sum() for k in keys).backward()
+    for k in KEYS:
+        assert rel(gpu_in[k].grad, ref_in[k].grad) <= 2e-3, k
