@@ -326,6 +326,10 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
         q_o, s_o, z_o = PoseRecoverFn.apply(run, C, *heads)
         agg, n = holder["agg"], holder["n"]
         agg.update({"quaternion": q_o, "scales": s_o, "z": z_o})
+        # R / T / RT through the differentiable batchwise_get_RT, so that rotation / translation losses reach q and z
+        # (the voted centre xy enters as a constant here)
+        from .gpu_tensor_funcs import batchwise_get_RT
+        agg["R"], agg["T"], agg["RT"] = batchwise_get_RT(q_o, agg["xy"], z_o, inv_intrinsics)
     else:
         eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
         n = eng.fetch_count()

@@ -103,10 +103,16 @@ def test_fused_path_backward():
     assert out["quaternion"].requires_grad and not out["xy"].requires_grad
     for k in keys:
         assert rel(out[k], ref_agg[k]) <= helpers.REL_TOL, k
-    sum((out[k] * ups[k].to(DEV)).sum() for k in keys).backward()
+    sum((out[k] * ups[k].to(DEV)).sum() for k in keys).backward(retain_graph=True)
     for k in keys:
         # the fused forward normalises pixel quaternions with rsqrt (1e-4 budget), so does its gradient
         assert rel(gpu_in[k].grad, ref_in[k].grad) <= 2 * helpers.REL_TOL, k
+    # rotation / transformation outputs are differentiable through q and z as well
+    assert out["R"].requires_grad and out["RT"].requires_grad
+    for k in keys:
+        gpu_in[k].grad = None
+    (out["R"].sum() + out["T"].sum()).backward()
+    assert float(gpu_in["quaternion"].grad.abs().max()) > 0 and float(gpu_in["z"].grad.abs().max()) > 0
     # a second call must not disturb the first call's saved tensors
     out2 = fp.pose_recover(gpu_in, inv_k, 32)
     assert torch.equal(out2["class_ids"], out["class_ids"])
