@@ -31,7 +31,7 @@ EXPORTS = (
     "fpc_aggregate", "fpc_vote_dense", "fpc_materialize_instances",
     "fpc_pack_masks", "fpc_pack_labels", "fpc_mask_iou", "fpc_match_instances", "fpc_paint_instances", "fpc_upsample_bilinear",
     "fpc_generate_hypothesis_vanishing_point", "fpc_voting_for_hypothesis_vanishing_point",
-    "fpc_pose_errors", "fpc_threshold_fraction", "fpc_label_instances", "fpc_recover_args_size", "fpc_class_compress_backward", "fpc_aggregate_backward", "fpc_vote_refine_backward", "fpc_get_rt_backward",
+    "fpc_pose_errors", "fpc_threshold_fraction", "fpc_label_instances", "fpc_recover_args_size", "fpc_class_compress_backward", "fpc_aggregate_backward", "fpc_vote_refine_backward", "fpc_get_rt_backward", "fpc_pose_recover_xy_backward",
 )
 MASK_META = 8
 MASK_F32, MASK_U8 = 0, 1
@@ -90,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.fpc_vote_refine_backward.argtypes = [_vp, _vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]
     L.fpc_get_rt_backward.argtypes = [_vp] * 7 + [_i] + [_vp] * 4
     L.fpc_get_rt_backward.restype = _i
+    L.fpc_pose_recover_xy_backward.argtypes = [_vp] * 8 + [_f, _i, _i, _i, _i, _i, _i, _vp, _vp]
+    L.fpc_pose_recover_xy_backward.restype = _i
     L.fpc_class_compress_backward.restype = L.fpc_aggregate_backward.restype = L.fpc_vote_refine_backward.restype = _i
     L.fpc_normalize.argtypes = [_vp, _vp, _ll, _i, _ll, _vp]
     L.fpc_class_compress.argtypes = [_vp] * 11 + [_i, _i, _i, _i, _vp]

@@ -84,25 +84,26 @@ class AggregateFn(torch.autograd.Function):
 
 
 class PoseRecoverFn(torch.autograd.Function):
-    """The fused path as one differentiable node: raw head maps -> per-instance (quaternion, scales, z).  Backward = the two
-    kernels above chained (instance gradient -> class-compressed fields -> predicted class's channels of the raw maps).  The
-    voted centre ``xy`` (and T / RT, which depend on it) is returned without a gradient: the RANSAC refinement is not
-    differentiated here."""
+    """The fused path as one differentiable node: raw head maps -> per-instance (quaternion, scales, z, voted centre xy).
+    Backward = the kernels above chained: instance gradient -> class-compressed fields -> predicted class's channels of the
+    raw maps for q / scales / z; the refinement-solve backward on the label volume for xy (inlier set held constant)."""
 
     @staticmethod
-    def forward(ctx, run, num_of_classes, quat, scales, z):
+    def forward(ctx, run, num_of_classes, inlier_thresh, arith, quat, scales, z, xy_head):
         agg, labels, cat_u8, counts, qnorm = run()
-        ctx.save_for_backward(labels, cat_u8, counts, qnorm, agg["quaternion"], agg["z"], quat)
-        ctx.num_of_classes = num_of_classes
+        ctx.save_for_backward(labels, cat_u8, counts, qnorm, agg["quaternion"], agg["z"], quat, xy_head, agg["xy"], agg["win_hypothesis"],
+                              agg["tn"].to(torch.int32), agg["sample_ids"].to(torch.int32))
+        ctx.num_of_classes, ctx.inlier_thresh, ctx.arith = num_of_classes, float(inlier_thresh), int(arith)
         ctx.shapes = (quat.shape, scales.shape, z.shape)
-        return agg["quaternion"], agg["scales"], agg["z"]
+        return agg["quaternion"], agg["scales"], agg["z"], agg["xy"]
 
     @staticmethod
-    def backward(ctx, g_q, g_s, g_z):
-        labels, cat_u8, counts, qnorm, q_hat, z_val, quat = ctx.saved_tensors
+    def backward(ctx, g_q, g_s, g_z, g_xy):
+        labels, cat_u8, counts, qnorm, q_hat, z_val, quat, xy_head, refined, win, tn, frame_of = ctx.saved_tensors
         b, h, w = labels.shape
         dev, f32 = labels.device, torch.float32
         n = int(counts.shape[0])
+        L, st = _lib.lib(), _lib.current_stream(dev)
         inv_c = (1.0 / counts.to(f32).clamp_min(1)).unsqueeze(1)
         G = torch.zeros((n, 8), dtype=f32, device=dev)
         if g_q is not None:
@@ -119,17 +120,23 @@ class PoseRecoverFn(torch.autograd.Function):
         c_z = torch.empty((b, h, w), dtype=f32, device=dev)
         d_q, d_s, d_z = (torch.empty(sh, dtype=f32, device=dev) for sh in ctx.shapes)
         K = ctx.num_of_classes - 1
+        d_xy_unused = torch.empty((b, 2 * K, h, w), dtype=f32, device=dev)
         d_xy = torch.empty((b, 2 * K, h, w), dtype=f32, device=dev)
         cat = cat_u8.to(torch.int64)
-        L, st = _lib.lib(), _lib.current_stream(dev)
+        gx = torch.zeros((n, 2), dtype=f32, device=dev) if g_xy is None else g_xy.to(f32).contiguous()
+        live = (tn > 0).to(torch.int32).contiguous()
         with torch.cuda.device(dev):
             _lib.check(L.fpc_aggregate_backward(labels.data_ptr(), G.contiguous().data_ptr(), None, n, c_q.data_ptr(), c_s.data_ptr(),
                                                 c_xy.data_ptr(), c_z.data_ptr(), b, h, w, st))
             # the fused forward normalises each pixel's quaternion before averaging: same Jacobian as class_compress
             _lib.check(L.fpc_class_compress_backward(cat.data_ptr(), quat.data_ptr(), None, c_q.data_ptr(), c_s.data_ptr(), None,
-                                                     c_z.data_ptr(), d_q.data_ptr(), d_s.data_ptr(), d_xy.data_ptr(), d_z.data_ptr(),
-                                                     b, ctx.num_of_classes, h, w, st))
-        return None, None, d_q, d_s, d_z
+                                                     c_z.data_ptr(), d_q.data_ptr(), d_s.data_ptr(), d_xy_unused.data_ptr(),
+                                                     d_z.data_ptr(), b, ctx.num_of_classes, h, w, st))
+            _lib.check(L.fpc_pose_recover_xy_backward(labels.data_ptr(), cat_u8.data_ptr(), xy_head.data_ptr(), frame_of.data_ptr(),
+                                                      win.contiguous().data_ptr(), refined.contiguous().data_ptr(), gx.data_ptr(),
+                                                      live.data_ptr(), ctx.inlier_thresh, n, b, ctx.num_of_classes, h, w, ctx.arith,
+                                                      d_xy.data_ptr(), st))
+        return None, None, None, None, d_q, d_s, d_z, d_xy
 
 
 class RansacV3Fn(torch.autograd.Function):

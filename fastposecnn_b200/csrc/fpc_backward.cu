@@ -224,4 +224,18 @@ int fpc_vote_refine_backward(const float *fmask, const float *vertex, long long 
                                        d_vertex, (cudaStream_t)stream);
 }
 
+int fpc_pose_recover_xy_backward(const int32_t *labels, const uint8_t *cat_mask_u8, const float *xy_head, const int32_t *frame_of,
+                                 const float *win_pts, const float *refined, const float *g_x, const int32_t *live, float inlier_thresh,
+                                 int n, int b, int num_classes, int h, int w, int arith, float *d_xy_head, void *stream) {
+    if (n < 0 || b <= 0 || h <= 0 || w <= 0 || num_classes < 2) return fail(FPC_EINVAL, "bad size");
+    if (!labels || !cat_mask_u8 || !xy_head || !d_xy_head) return fail(FPC_EINVAL, "NULL pointer");
+    if (arith != FPC_ARITH_IEEE && arith != FPC_ARITH_NVCC_FMA) return fail(FPC_EINVAL, "bad arith mode %d", arith);
+    cudaStream_t st = (cudaStream_t)stream;
+    FPC_CUDA_TRY(cudaMemsetAsync(d_xy_head, 0, (size_t)b * 2 * (num_classes - 1) * h * w * sizeof(float), st));
+    if (n == 0) return FPC_OK;
+    if (!frame_of || !win_pts || !refined || !g_x || !live) return fail(FPC_EINVAL, "NULL pointer");
+    return launch_vote_refine_backward_labels(labels, cat_mask_u8, xy_head, frame_of, win_pts, refined, g_x, live, inlier_thresh, n,
+                                              num_classes - 1, h, w, arith, d_xy_head, st);
+}
+
 }  // extern "C"

@@ -120,6 +120,9 @@ int launch_voting_for_hypothesis_vp(const float *direct, const float *coords, co
 int launch_vote_refine_backward(const float *fmask, const float *vertex, long long sN, long long sH, long long sW, long long s2,
                                 const float *win_pts, const float *refined, const float *g_x, const int *live, float thresh, int n,
                                 int h, int w, int arith, float *d_vertex, cudaStream_t st);
+int launch_vote_refine_backward_labels(const int *labels, const uint8_t *cls, const float *xy_head, const int *frame_of,
+                                       const float *win_pts, const float *refined, const float *g_x, const int *live, float thresh,
+                                       int n, int K, int h, int w, int arith, float *d_xy_head, cudaStream_t st);
 void set_vote_packed(int v);
 int vote_batches(int hn);
 int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st);

@@ -793,6 +793,94 @@ __global__ void __launch_bounds__(256) k_vote_refine_backward(const float *__res
     }
 }
 
+// The same for the fused path: membership from the label volume, direction = the predicted class's raw xy channels
+// L2-normalised exactly as the gather kernel does (IEEE sqrt / divide), gradient pushed back through that normalisation
+// into the raw head map (pre-zeroed).  Block per instance, two passes over its frame.
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_vote_refine_backward_labels(const int *__restrict__ labels, const uint8_t *__restrict__ cls,
+                                                                     const float *__restrict__ xy_head, const int *__restrict__ frame_of,
+                                                                     const float *__restrict__ win_pts, const float *__restrict__ refined,
+                                                                     const float *__restrict__ g_x, const int *__restrict__ live,
+                                                                     float thresh, int K, int h, int w, float *__restrict__ d_xy_head) {
+    __shared__ double s_a[8][3];
+    __shared__ double s_u[2];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int hw = h * w, want = i + 1;
+    const int img = frame_of[i];
+    const bool on = live[i] != 0;
+    const float wx = win_pts[2 * i], wy = win_pts[2 * i + 1];
+    const int *lab = labels + (size_t)img * hw;
+    const uint8_t *cl = cls + (size_t)img * hw;
+    const float *head = xy_head + (size_t)img * 2 * K * hw;
+    float *dhead = d_xy_head + (size_t)img * 2 * K * hw;
+    auto direction = [&](int p, float &rx, float &ry, float &nrm, float &dx, float &dy, size_t &off) {
+        off = (size_t)2 * ((int)cl[p] - 1) * hw + p;
+        rx = head[off];
+        ry = head[off + hw];
+        nrm = __fsqrt_rn(rx * rx + ry * ry);
+        dx = rx; dy = ry;
+        if (nrm != 0.f) { dx = __fdiv_rn(rx, nrm); dy = __fdiv_rn(ry, nrm); }
+    };
+    double a00 = 0, a01 = 0, a11 = 0;
+    if (on)
+        for (int p = tid; p < hw; p += 256) {
+            if (lab[p] != want) continue;
+            float rx, ry, nrm, dx, dy;
+            size_t off;
+            direction(p, rx, ry, nrm, dx, dy, off);
+            const int y = p / w, x = p - y * w;
+            if (!vote_exact<ARITH>((float)x, (float)y, dx, dy, wx, wy, thresh)) continue;
+            const double nx = dy, ny = -(double)dx;
+            a00 += nx * nx; a01 += nx * ny; a11 += ny * ny;
+        }
+    a00 = warp_sum_d(a00); a01 = warp_sum_d(a01); a11 = warp_sum_d(a11);
+    if (lane == 0) { s_a[wv][0] = a00; s_a[wv][1] = a01; s_a[wv][2] = a11; }
+    __syncthreads();
+    if (tid == 0) {
+        double t0 = 0, t1 = 0, t2 = 0, ux = 0, uy = 0;
+        for (int k = 0; k < 8; ++k) { t0 += s_a[k][0]; t1 += s_a[k][1]; t2 += s_a[k][2]; }
+        if (on) solve_sym2_pinv(t0, t1, t2, (double)g_x[2 * i], (double)g_x[2 * i + 1], ux, uy);
+        s_u[0] = ux;
+        s_u[1] = uy;
+    }
+    __syncthreads();
+    if (!on) return;
+    const double ux = s_u[0], uy = s_u[1];
+    const double rx0 = refined[2 * i], ry0 = refined[2 * i + 1];
+    for (int p = tid; p < hw; p += 256) {
+        if (lab[p] != want) continue;
+        float rx, ry, nrm, dx, dy;
+        size_t off;
+        direction(p, rx, ry, nrm, dx, dy, off);
+        const int y = p / w, x = p - y * w;
+        if (!vote_exact<ARITH>((float)x, (float)y, dx, dy, wx, wy, thresh)) continue;
+        const double nx = dy, ny = -(double)dx;
+        const double qx = (double)x - rx0, qy = (double)y - ry0;
+        const double nr = nx * qx + ny * qy, nu = nx * ux + ny * uy;
+        const double gnx = nr * ux + qx * nu, gny = nr * uy + qy * nu;
+        double gdx = -gny, gdy = gnx;                                   // gradient on the unit direction
+        if (nrm != 0.f) {                                               // ... back through dir = raw / |raw|
+            const double dot = dx * gdx + dy * gdy;
+            gdx = (gdx - dx * dot) / nrm;
+            gdy = (gdy - dy * dot) / nrm;
+        }
+        dhead[off] = (float)gdx;
+        dhead[off + hw] = (float)gdy;
+    }
+}
+
+int launch_vote_refine_backward_labels(const int *labels, const uint8_t *cls, const float *xy_head, const int *frame_of,
+                                       const float *win_pts, const float *refined, const float *g_x, const int *live, float thresh,
+                                       int n, int K, int h, int w, int arith, float *d_xy_head, cudaStream_t st) {
+    if (n == 0) return FPC_OK;
+    if (arith == FPC_ARITH_IEEE)
+        k_vote_refine_backward_labels<FPC_ARITH_IEEE><<<n, 256, 0, st>>>(labels, cls, xy_head, frame_of, win_pts, refined, g_x, live, thresh, K, h, w, d_xy_head);
+    else
+        k_vote_refine_backward_labels<FPC_ARITH_NVCC_FMA><<<n, 256, 0, st>>>(labels, cls, xy_head, frame_of, win_pts, refined, g_x, live, thresh, K, h, w, d_xy_head);
+    FPC_LAUNCH_CHECK("k_vote_refine_backward_labels");
+    return FPC_OK;
+}
+
 int launch_vote_refine_backward(const float *fmask, const float *vertex, long long sN, long long sH, long long sW, long long s2,
                                 const float *win_pts, const float *refined, const float *g_x, const int *live, float thresh, int n,
                                 int h, int w, int arith, float *d_vertex, cudaStream_t st) {

@@ -305,7 +305,7 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
     # head maps may also be PINNED HOST tensors (read in place over PCIe); the device then comes from inv_intrinsics
     device = mask.device if mask.is_cuda else inv_intrinsics.device
     eng = get_engine(b, h, w, C, hn, device, want_labels=True, upsample=upsample, **engine_kw)
-    heads = [logits[k] for k in ("quaternion", "scales", "z")]
+    heads = [logits[k] for k in ("quaternion", "scales", "z", "xy")]
     if torch.is_grad_enabled() and upsample == 1 and any(t.requires_grad for t in heads):
         # training: quaternion / scales / z of the result stay differentiable w.r.t. their head maps (autograd.PoseRecoverFn);
         # each call gets its own tables so that the saved tensors survive later calls
@@ -321,15 +321,17 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
                 eng.extra_out = None
             n_ = eng.fetch_count()
             agg_ = {k: v.clone() for k, v in eng.table_to_agg(n_).items()}
+            if n_ and int(agg_["mask_sizes"].max()) > eng.max_num:
+                raise NotImplementedError("pose_recover backward: an instance was sub-sampled to max_num voters, which is not "
+                                          "differentiable here; raise max_num")
             holder["agg"], holder["n"] = agg_, n_
             return agg_, eng.labels.clone(), eng.cat_mask_u8.clone(), agg_["mask_sizes"].to(torch.int32), extra[:n_, 2].clone()
-        q_o, s_o, z_o = PoseRecoverFn.apply(run, C, *heads)
+        q_o, s_o, z_o, xy_o = PoseRecoverFn.apply(run, C, eng.inlier_thresh, eng.arith, *heads)
         agg, n = holder["agg"], holder["n"]
-        agg.update({"quaternion": q_o, "scales": s_o, "z": z_o})
-        # R / T / RT through the differentiable batchwise_get_RT, so that rotation / translation losses reach q and z
-        # (the voted centre xy enters as a constant here)
+        agg.update({"quaternion": q_o, "scales": s_o, "z": z_o, "xy": xy_o})
+        # R / T / RT through the differentiable batchwise_get_RT: rotation / translation losses reach q, z and the xy head
         from .gpu_tensor_funcs import batchwise_get_RT
-        agg["R"], agg["T"], agg["RT"] = batchwise_get_RT(q_o, agg["xy"], z_o, inv_intrinsics)
+        agg["R"], agg["T"], agg["RT"] = batchwise_get_RT(q_o, xy_o, z_o, inv_intrinsics)
     else:
         eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
         n = eng.fetch_count()

@@ -331,6 +331,14 @@ FPC_API int fpc_vote_refine_backward(const float *fmask, const float *vertex, lo
                                      const int32_t *live, float inlier_thresh, int n, int h, int w, int arith, float *d_vertex,
                                      void *stream);
 
+/* The same for the fused path (fpc_pose_recover): membership from the label volume [b,h,w], direction = the predicted
+ * class's raw xy channels of xy_head [b,2K,h,w] normalised as the forward does; frame_of [n] = frame of each instance.
+ * d_xy_head [b,2K,h,w] is zero-filled here, then the inlier pixels receive the gradient pushed through that normalisation. */
+FPC_API int fpc_pose_recover_xy_backward(const int32_t *labels, const uint8_t *cat_mask_u8, const float *xy_head,
+                                         const int32_t *frame_of, const float *win_pts, const float *refined, const float *g_x,
+                                         const int32_t *live, float inlier_thresh, int n, int b, int num_classes, int h, int w,
+                                         int arith, float *d_xy_head, void *stream);
+
 /* Number of kernels fpc_pose_recover launches per call (for launch accounting). */
 FPC_API int fpc_pose_recover_num_launches(void);
 

@@ -100,7 +100,7 @@ def test_fused_path_backward():
     gpu_in = {k: v.to(DEV).requires_grad_(k in keys) for k, v in logits.items()}
     inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
     out = fp.pose_recover(gpu_in, inv_k, 32)
-    assert out["quaternion"].requires_grad and not out["xy"].requires_grad
+    assert out["quaternion"].requires_grad
     for k in keys:
         assert rel(out[k], ref_agg[k]) <= helpers.REL_TOL, k
     sum((out[k] * ups[k].to(DEV)).sum() for k in keys).backward(retain_graph=True)
@@ -237,3 +237,26 @@ def test_whole_drop_in_chain_gradients_vs_reference_chain():
     sum((agg[k] * ups[k].to(DEV)).sum() for k in keys).backward()
     for k in KEYS:
         assert rel(gpu_in[k].grad, ref_in[k].grad) <= 2e-3, k
+
+
+def test_fused_path_xy_backward_equals_drop_in_chain():
+    """The fused path's gradient of the voted centres w.r.t. the raw xy head against the drop-in chain's (itself checked
+    against autograd through the oracle): same pixel pairs -> same winners, same inlier sets."""
+    import fastposecnn_b200 as fp
+    base = scene(seed=13)
+    hn = 32
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
+    hp = types.SimpleNamespace(HV_NUM_OF_HYPOTHESES=hn)
+    a_in = {k: v.to(DEV).requires_grad_(k == "xy") for k, v in base.items()}
+    agg = fp.AggregationLayer(hp, 7)(fp.class_compression(a_in, 7))
+    n = agg["class_ids"].shape[0]
+    idxs = syn.presampled_idxs(agg["instance_masks"].sum(dim=(1, 2)).long().cpu().tolist(), hn, seed=21)
+    agg = fp.samplewise_get_RT(fp.HoughVotingLayer(hp)(agg, idxs=idxs.to(DEV)), inv_k)
+    up = torch.randn(n, 2, generator=torch.Generator().manual_seed(6)).to(DEV)
+    upT = torch.randn(n, 3, generator=torch.Generator().manual_seed(7)).to(DEV)
+    ((agg["xy"] * up).sum() + (agg["T"] * upT).sum()).backward()
+    b_in = {k: v.to(DEV).requires_grad_(k == "xy") for k, v in base.items()}
+    out = fp.pose_recover(b_in, inv_k, hn, idxs=idxs.reshape(n, hn, 2).to(DEV))
+    assert out["xy"].requires_grad and helpers.rel_err(out["xy"], agg["xy"].detach()) <= helpers.REL_TOL
+    ((out["xy"] * up).sum() + (out["T"] * upT).sum()).backward()
+    assert rel(b_in["xy"].grad, a_in["xy"].grad) <= 1e-3
