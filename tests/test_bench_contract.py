@@ -55,7 +55,7 @@ def test_eight_gpu_line_scales():
 
 
 def test_bench_cli_help_lists_the_contract_flags():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in out.stdout
