@@ -81,11 +81,12 @@ def test_lowres_equals_full_resolution_path_on_upsampled_maps():
         assert torch.equal(a[k], b[k]), k
 
 
-def test_reference_head_modules_feed_the_fused_path():
+def test_reference_head_modules_feed_the_fused_path(monkeypatch):
     """lowres_logits() runs only the 1x1 convolutions of SegmentationHead-shaped modules; the fused path on that equals the
     reference flow conv -> up-sample -> xyz split -> path."""
     import fastposecnn_b200 as fp
     torch.manual_seed(0)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)        # fp32 convolutions: the CPU flow is the yardstick
     b, cin, hl, wl, scale, C = 2, 16, 24, 32, 4, 7
     K = C - 1
 
