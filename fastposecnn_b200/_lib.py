@@ -82,7 +82,7 @@ def lib() -> ctypes.CDLL:
     L.fpc_generate_hypothesis_vanishing_point.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
     L.fpc_voting_for_hypothesis_vanishing_point.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]
     L.fpc_generate_hypothesis_vanishing_point.restype = L.fpc_voting_for_hypothesis_vanishing_point.restype = _i
-    L.fpc_pose_errors.argtypes = [_vp] * 10 + [_i] + [_vp] * 5
+    L.fpc_pose_errors.argtypes = [_vp] * 10 + [_i] + [_vp] * 6
     L.fpc_threshold_fraction.argtypes = [_vp, _i, _vp, _i, _i, _vp, _vp]
     L.fpc_pose_errors.restype = L.fpc_threshold_fraction.restype = _i
     L.fpc_class_compress_backward.argtypes = [_vp] * 11 + [_i, _i, _i, _i, _vp]

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(128) k_pose_errors(const float *__restrict__ q
                                                      const float *__restrict__ s0, const float *__restrict__ s1,
                                                      const float *__restrict__ t0, const float *__restrict__ t1, int m,
                                                      float *__restrict__ raw_deg, double *__restrict__ sym_deg,
-                                                     float *__restrict__ iou3d, float *__restrict__ offset) {
+                                                     float *__restrict__ iou3d, float *__restrict__ offset,
+                                                     float *__restrict__ centers) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= m) return;
     if (q0 && q1) {
@@ -135,6 +136,15 @@ __global__ void __launch_bounds__(128) k_pose_errors(const float *__restrict__ q
         if (lo < 0.0) inter = 0.0;
         iou3d[i] = (float)(inter / (v1 + v2 - inter));
     }
+    if (centers) {
+        // world position of the camera-frame origin under each RT: inverse(RT) @ (0,0,0,1), de-homogenised
+        // (from_RTs_get_T_offset_errors, lib/gpu_tensor_funcs.py:569-609)
+        double inv[4][4];
+        inverse4(rt0 + 16 * i, inv);
+        for (int k = 0; k < 3; ++k) centers[6 * i + k] = (float)(inv[k][3] / inv[3][3]);
+        inverse4(rt1 + 16 * i, inv);
+        for (int k = 0; k < 3; ++k) centers[6 * i + 3 + k] = (float)(inv[k][3] / inv[3][3]);
+    }
     if (offset) {
         const float dx = t0[3 * i] - t1[3 * i], dy = t0[3 * i + 1] - t1[3 * i + 1], dz = t0[3 * i + 2] - t1[3 * i + 2];
         offset[i] = sqrtf(dx * dx + dy * dy + dz * dz) * 10.f;
@@ -172,18 +182,19 @@ extern "C" {
 int fpc_pose_errors(const float *q_gt, const float *q_pred, const int64_t *symmetric_ids, const double *sym_rotations,
                     const float *rt_gt, const float *rt_pred, const float *scales_gt, const float *scales_pred, const float *t_gt,
                     const float *t_pred, int m, float *raw_degrees, double *sym_degrees, float *iou_3d, float *offset_error,
-                    void *stream) {
+                    float *world_centers, void *stream) {
     if (m < 0) return fail(FPC_EINVAL, "negative size");
     if (m == 0) return FPC_OK;
     if ((raw_degrees || sym_degrees) && (!q_gt || !q_pred)) return fail(FPC_EINVAL, "quaternions missing");
     if (sym_degrees && !sym_rotations) return fail(FPC_EINVAL, "symmetry rotation table missing");
     if (iou_3d && (!rt_gt || !rt_pred || !scales_gt || !scales_pred)) return fail(FPC_EINVAL, "RT / scales missing");
+    if (world_centers && (!rt_gt || !rt_pred)) return fail(FPC_EINVAL, "RT missing");
     if (offset_error && (!t_gt || !t_pred)) return fail(FPC_EINVAL, "translations missing");
     const bool quats = raw_degrees || sym_degrees;
     k_pose_errors<<<ceil_div(m, 4), 128, 0, (cudaStream_t)stream>>>(quats ? q_gt : nullptr, quats ? q_pred : nullptr,
                                                                    (const long long *)symmetric_ids, sym_rotations, rt_gt, rt_pred,
                                                                    scales_gt, scales_pred, t_gt, t_pred, m, raw_degrees, sym_degrees,
-                                                                   iou_3d, offset_error);
+                                                                   iou_3d, offset_error, world_centers);
     FPC_LAUNCH_CHECK("k_pose_errors");
     return FPC_OK;
 }

@@ -164,7 +164,8 @@ def _symmetry_rotations(device) -> torch.Tensor:
     return _SYM_ROTATIONS[key]
 
 
-def _pose_errors(q0=None, q1=None, symmetric_ids=None, rts=None, scales=None, ts=None, want_raw=False, want_sym=False):
+def _pose_errors(q0=None, q1=None, symmetric_ids=None, rts=None, scales=None, ts=None, want_raw=False, want_sym=False,
+                 want_centers=False):
     f32 = torch.float32
     ref = q0 if q0 is not None else (rts[0] if rts is not None else ts[0])
     dev, m = ref.device, int(ref.shape[0])
@@ -187,14 +188,18 @@ def _pose_errors(q0=None, q1=None, symmetric_ids=None, rts=None, scales=None, ts
             out["raw"] = torch.empty((m,), dtype=f32, device=dev)
     if rts is not None:
         args[4], args[5] = chk(rts[0], "RTs_1", (4, 4)), chk(rts[1], "RTs_2", (4, 4))
-        args[6], args[7] = chk(scales[0], "scales_1", (3,)), chk(scales[1], "scales_2", (3,))
-        out["iou"] = torch.empty((m,), dtype=f32, device=dev)
+        if scales is not None:
+            args[6], args[7] = chk(scales[0], "scales_1", (3,)), chk(scales[1], "scales_2", (3,))
+            out["iou"] = torch.empty((m,), dtype=f32, device=dev)
+        if want_centers:
+            out["centers"] = torch.empty((m, 6), dtype=f32, device=dev)
     if ts is not None:
         args[8], args[9] = chk(ts[0], "gt_Ts", (3,)), chk(ts[1], "pred_Ts", (3,))
         out["offset"] = torch.empty((m,), dtype=f32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().fpc_pose_errors(*[_lib.ptr(a) for a in args], m, _lib.ptr(out.get("raw")), _lib.ptr(out.get("sym")),
-                                              _lib.ptr(out.get("iou")), _lib.ptr(out.get("offset")), _lib.current_stream(dev)))
+                                              _lib.ptr(out.get("iou")), _lib.ptr(out.get("offset")), _lib.ptr(out.get("centers")),
+                                              _lib.current_stream(dev)))
     return out
 
 
@@ -246,6 +251,16 @@ def from_Ts_get_offset_error(gt_Ts, pred_Ts) -> torch.Tensor:
     if gt_Ts.shape[0] == 0:
         return torch.zeros((0,), dtype=torch.float32, device=gt_Ts.device)
     return _pose_errors(ts=(gt_Ts, pred_Ts))["offset"]
+
+
+def from_RTs_get_T_offset_errors(gt_RTs, pred_RTs) -> torch.Tensor:
+    """lib/gpu_tensor_funcs.py:569-609 -- the camera-frame origin mapped to world coordinates by inverse(RT), ground truth
+    against prediction.  As in the reference the distance is taken over ALL pairs at once (``get_offset_error_from_centroid``
+    sums the squared differences of the whole [n,3] arrays), so the result is ONE number (times 10), not one per pair."""
+    if gt_RTs.shape[0] == 0:
+        return torch.stack([])                      # the reference's torch.stack([]) raises here too
+    c = _pose_errors(rts=(gt_RTs, pred_RTs), want_centers=True)["centers"]
+    return torch.sqrt(torch.sum(torch.pow(c[:, :3] - c[:, 3:], 2))) * 10
 
 
 def calculate_aps(raw_data, metrics_threshold, metrics_operator):

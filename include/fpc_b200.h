@@ -286,11 +286,13 @@ FPC_API int fpc_paint_instances(const int32_t *labels, int b, int h, int w, cons
  * get_symmetric_quat_distance (sym_degrees [m] f64: min over the 360 rotations sym_rotations [360,4] f64 about y; NaN for
  * pairs whose symmetric_ids entry is 0; symmetric_ids NULL = every pair), :503-547 get_3d_ious (iou_3d [m] f32, with the
  * reference's reduction over the coordinate axis kept) and :565-567 from_Ts_get_offset_error (offset_error [m] f32).
+ * world_centers [m,6] f32 = inverse(RT) @ (0,0,0,1) de-homogenised, for the ground truth then the prediction: the two
+ * points from_RTs_get_T_offset_errors (:569-609) compares.
  * Any output may be NULL (then its inputs may be NULL too).  q [m,4], RT [m,4,4], scales [m,3], T [m,3], row-major. */
 FPC_API int fpc_pose_errors(const float *q_gt, const float *q_pred, const int64_t *symmetric_ids, const double *sym_rotations,
                             const float *rt_gt, const float *rt_pred, const float *scales_gt, const float *scales_pred,
                             const float *t_gt, const float *t_pred, int m, float *raw_degrees, double *sym_degrees, float *iou_3d,
-                            float *offset_error, void *stream);
+                            float *offset_error, float *world_centers, void *stream);
 
 /* lib/gpu_tensor_funcs.py:611-652 calculate_aps for one (metric, class): out[t] = fraction of the non-NaN values with
  * value < thresholds[t] (op 0, torch.less) or value > thresholds[t] (op 1, torch.greater). */

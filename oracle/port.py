@@ -792,3 +792,45 @@ def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
         pts.append(torch.zeros([1, vn, 2]) if res is None else res[0].unsqueeze(0))
         conf.append(torch.zeros([1, vn]) if res is None else res[2].unsqueeze(0))
     return torch.cat(pts), torch.cat(conf)
+
+
+def from_RTs_get_T_offset_errors(gt_rts, pred_rts) -> torch.Tensor:
+    """gpu_tensor_funcs.py:569-609: the camera-frame origin mapped through inverse(RT) for both sides; the reference then
+    takes ONE Euclidean norm over the whole [n,3] difference (:557-559 sums every element), times 10."""
+    def centres(rts):
+        out = []
+        for rt in rts:
+            w = torch.inverse(rt) @ torch.tensor([[0.0], [0.0], [0.0], [1.0]], dtype=rt.dtype)
+            out.append((w[:-1] / w[-1]).flatten())
+        return torch.stack(out)
+    diff = centres(gt_rts) - centres(pred_rts)
+    return torch.sqrt(torch.sum(torch.pow(diff, 2))) * 10
+
+
+def metric_values(matches_seq, kind: str, threshold=None) -> torch.Tensor:
+    """lib/metrics.py restated as a fold over a sequence of matched-pair dicts.  ``kind``: degree_ap / iou_ap / offset_ap
+    (:11-50, 91-133, 176-219: passed / seen * 100) or degree_error / iou_accuracy / offset_error (:52-89, 135-174, 221-260:
+    value = (value + batch mean) / 2 from 0)."""
+    correct, total, running = torch.tensor(0), torch.tensor(0), torch.tensor(0)
+    for m in matches_seq:
+        if m is None:
+            continue
+        if kind.startswith("degree") and "quaternion" in m:
+            v = get_quat_distance(m["quaternion"][0], m["quaternion"][1], m["symmetric_ids"])
+            passed = v < threshold if threshold is not None else None
+        elif kind.startswith("iou") and "RT" in m:
+            v = get_3d_ious(m["RT"][0], m["RT"][1], m["scales"][0], m["scales"][1])
+            passed = v > threshold if threshold is not None else None
+            v = v * 100
+        elif kind == "offset_ap" and "RT" in m:
+            v = from_Ts_get_offset_error(m["T"][0], m["T"][1])
+            passed = v < threshold
+        elif kind == "offset_error" and "RT" in m:
+            v, passed = from_RTs_get_T_offset_errors(m["RT"][0], m["RT"][1]), None
+        else:
+            continue
+        if kind.endswith("_ap"):
+            correct, total = correct + torch.sum(passed.int()), total + passed.shape[0]
+        else:
+            running = (running + torch.mean(v)) / 2
+    return (correct.float() / total.float()) * 100 if kind.endswith("_ap") else running

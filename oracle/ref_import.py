@@ -41,7 +41,7 @@ _loaded = None
 
 
 def load():
-    """Returns a namespace with the reference modules: gtf, agg, hv, rvg, mg (matching)."""
+    """Returns a namespace with the reference modules: gtf, agg, hv, rvg, mg (matching), metrics."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -86,6 +86,17 @@ def load():
     ns.hv = importlib.import_module("hough_voting")
     ns.agg = importlib.import_module("aggregation_layer")
     ns.mg = importlib.import_module("matching")
+    # lib/metrics.py subclasses pl.metrics.Metric (pytorch-lightning is not installed): a base with the two things it uses
+    pl = stub("pytorch_lightning")
+
+    class _Metric:
+        def __init__(self, *a, **k):
+            pass
+
+        def add_state(self, name, default, dist_reduce_fx=None):
+            setattr(self, name, default)
+    pl.metrics = types.SimpleNamespace(Metric=_Metric)
+    ns.metrics = importlib.import_module("metrics")
     _loaded = ns
     return ns
 
