@@ -148,7 +148,7 @@ def run_b200(args):
     from fastposecnn_b200 import _lib
     from fastposecnn_b200 import synthetic as syn
     from fastposecnn_b200.pose_recovery import PoseRecoveryEngine, PoseRecoveryPipeline
-    from fastposecnn_b200.sharding import OverlappedGather, gather_pose_tables
+    from fastposecnn_b200.sharding import OverlappedGather
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -2,7 +2,6 @@
 from __future__ import annotations
 
 import ctypes
-from typing import Dict
 
 import torch
 import torch.nn as nn

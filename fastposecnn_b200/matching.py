@@ -17,7 +17,7 @@ pairings are bit-identical.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict
 
 import torch
 

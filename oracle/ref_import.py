@@ -23,7 +23,6 @@ import importlib
 import os
 import sys
 import types
-from collections import deque
 from contextlib import contextmanager
 
 import torch
