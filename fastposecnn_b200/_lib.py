@@ -126,6 +126,48 @@ def lib() -> ctypes.CDLL:
     return L
 
 
+class CapacityError(RuntimeError):
+    """A capacity-sized table overflowed (FPC_FLAG_*).  Carries the counters the kernels reported so that callers with
+    default capacities can grow their buffers and retry (the reference accepts any instance count,
+    lib/aggregation_layer.py:87-118)."""
+
+    def __init__(self, message: str, flags: int, instances: int, rows: int, records: int):
+        super().__init__(message)
+        self.flags, self.instances, self.rows, self.records = flags, instances, rows, records
+
+    def grown(self, max_instances: int, max_rows: int, max_records: int, P: int, h: int):
+        """Capacities for the retry: at least what the counters ask for, at least double what overflowed."""
+        if self.flags & FLAG_INSTANCES:
+            max_instances = max(self.instances + 16, 2 * max_instances)
+            max_rows = max(max_rows, min(P, max_instances * h))
+            max_records = max(max_records, P + 16 * max_instances)
+        if self.flags & FLAG_ROWS:
+            max_rows = min(max(P, 1), max(self.rows + 16, 2 * max_rows))
+        if self.flags & FLAG_RECORDS:
+            max_records = max(self.records + 16, 2 * max_records)
+        return int(max_instances), int(max_rows), int(max_records)
+
+
+def capacity_error(c, max_instances, max_rows, max_records) -> CapacityError:
+    flags = int(c[CNT_FLAGS])
+    what = [n for bit, n in ((FLAG_INSTANCES, f"instances ({int(c[CNT_INSTANCES])} > max_instances={max_instances})"),
+                             (FLAG_ROWS, f"rows ({int(c[CNT_ROWS])} > max_rows={max_rows})"),
+                             (FLAG_RECORDS, f"records ({int(c[CNT_RECORDS])} > max_records={max_records})")) if flags & bit]
+    return CapacityError("libfpc_b200 error -3 (FPC_ECAPACITY): capacity exceeded for " + ", ".join(what), flags,
+                         int(c[CNT_INSTANCES]), int(c[CNT_ROWS]), int(c[CNT_RECORDS]))
+
+
+_seed_counter = 0
+
+
+def fresh_seed() -> int:
+    """Seed of one call's on-device pixel-pair sampling when the caller fixed none: torch's seed mixed with a call counter, so
+    every call (and every keypoint) draws new pairs like the reference's ``random_`` (ransac_voting_gpu.py:552)."""
+    global _seed_counter
+    _seed_counter += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
 def check(rc: int) -> None:
     if rc != FPC_OK:
         msg = lib().fpc_last_error().decode("utf-8", "replace")

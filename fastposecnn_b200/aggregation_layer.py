@@ -17,11 +17,12 @@ def _pipeline_args(b, h, w, num_classes, hn, max_instances, dev, **kw):
     P = b * h * w
     a.b, a.h, a.w, a.num_classes, a.hn = b, h, w, num_classes, hn
     a.max_instances = max_instances
-    a.max_records = max(P, 1) + 16 * max_instances
-    a.max_rows = max(min(P, max_instances * h), 1)
+    a.max_records = kw.get("max_records") or max(P, 1) + 16 * max_instances
+    a.max_rows = kw.get("max_rows") or max(min(P, max_instances * h), 1)
     a.inlier_thresh = kw.get("inlier_thresh", 0.999)
     a.min_num, a.max_num = kw.get("min_num", 5), kw.get("max_num", 30000)
-    a.arith, a.seed = kw.get("arith", _lib.ARITH_IEEE), kw.get("seed", 1234)
+    seed = kw.get("seed")
+    a.arith, a.seed = kw.get("arith", _lib.ARITH_IEEE), (_lib.fresh_seed() if seed is None else int(seed))
     L = _lib.lib()
     nbytes = L.fpc_pose_recover_workspace_bytes(ctypes.byref(a))
     if nbytes == 0:
@@ -36,16 +37,31 @@ def _pipeline_args(b, h, w, num_classes, hn, max_instances, dev, **kw):
     a.counters = bufs["table_full"].data_ptr()
     a.labels = bufs["labels"].data_ptr()
     a.stream = _lib.current_stream(dev)
+    bufs["caps"] = (int(a.max_instances), int(a.max_rows), int(a.max_records), P, h)
     return a, bufs
+
+
+def grow_and_retry(call, max_instances, fixed: bool):
+    """``call(max_instances, max_rows, max_records)`` with default table capacities; on overflow (CapacityError) the tables
+    grow to what the kernels' counters ask for and the call is repeated -- the reference accepts any instance count
+    (lib/aggregation_layer.py:87-118).  ``fixed``: the caller chose the capacity, overflow is an error."""
+    caps = (max_instances, None, None)
+    for attempt in range(5):
+        try:
+            return call(*caps)
+        except _lib.CapacityError as e:
+            if fixed or attempt == 4:
+                raise
+            caps = e.grown_caps
 
 
 def _read_count(bufs, max_instances) -> int:
     c = bufs["table_full"][0, :_lib.NUM_COUNTERS].view(torch.int32).cpu()
-    flags = int(c[_lib.CNT_FLAGS])
-    if flags:
-        raise RuntimeError(f"libfpc_b200 error -3 (FPC_ECAPACITY): capacity exceeded (flags={flags}, instances="
-                           f"{int(c[_lib.CNT_INSTANCES])}, max_instances={max_instances}, rows={int(c[_lib.CNT_ROWS])}, "
-                           f"records={int(c[_lib.CNT_RECORDS])})")
+    if int(c[_lib.CNT_FLAGS]):
+        mi, mr, mrec, P, h = bufs["caps"]
+        err = _lib.capacity_error(c, mi, mr, mrec)
+        err.grown_caps = err.grown(mi, mr, mrec, P, h)
+        raise err
     return int(c[_lib.CNT_INSTANCES])
 
 
@@ -101,11 +117,12 @@ class AggregationLayer(nn.Module):
                 or tuple(z.shape) != (b, h, w):
             raise RuntimeError("AggregationLayer: cat_data tensors have inconsistent shapes")
         dev = cat_mask.device
-        cap = self.max_instances or max(1024, 128 * b)
-
         def run():
+            return grow_and_retry(run_with, self.max_instances or max(1024, 128 * b), fixed=self.max_instances is not None)
+
+        def run_with(cap, max_rows, max_records):
             with torch.cuda.device(dev):
-                a, bufs = _pipeline_args(b, h, w, int(self.classes), 1, cap, dev)
+                a, bufs = _pipeline_args(b, h, w, int(self.classes), 1, cap, dev, max_rows=max_rows, max_records=max_records)
                 a.quaternion, a.scales, a.xy, a.z = q.data_ptr(), s.data_ptr(), xy.data_ptr(), z.data_ptr()
                 extra = torch.zeros((cap, 4), dtype=f32, device=dev)
                 a.extra_out = extra.data_ptr()
@@ -140,9 +157,9 @@ class AggregationLayer(nn.Module):
         b, h, w = class_mask.shape
         dev = class_mask.device
         cat = (class_mask != 0).to(torch.int64).contiguous()
-        cap = self.max_instances or max(1024, 128 * b)
-        with torch.cuda.device(dev):
-            a, bufs = _pipeline_args(b, h, w, 2, 1, cap, dev)
-            _lib.check(_lib.lib().fpc_label_instances(ctypes.byref(a), cat.data_ptr()))
-            n = _read_count(bufs, cap)
-        return bufs["labels"], n
+        def label_with(cap, max_rows, max_records):
+            with torch.cuda.device(dev):
+                a, bufs = _pipeline_args(b, h, w, 2, 1, cap, dev, max_rows=max_rows, max_records=max_records)
+                _lib.check(_lib.lib().fpc_label_instances(ctypes.byref(a), cat.data_ptr()))
+                return bufs["labels"], _read_count(bufs, cap)
+        return grow_and_retry(label_with, self.max_instances or max(1024, 128 * b), fixed=self.max_instances is not None)

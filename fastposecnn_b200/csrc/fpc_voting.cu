@@ -187,24 +187,38 @@ __global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__r
 // done by the copy engine: one thread arms an mbarrier and issues five bulk copies (cp.async.bulk: the four
 // SoA record planes x, y, dir_x, dir_y of the chunk and the hypotheses of the batch) for the NEXT item while
 // all warps vote on the current one.  Every lane keeps VQ hypotheses in registers and walks the pixels with
-// broadcast LDS.128 loads (4 pixels per load), two pixels per packed f32x2 instruction (FFMA2/FMUL2/FADD2).
+// broadcast LDS.128 loads (4 pixels per load), two pixels per packed f32x2 instruction (FFMA2).
 // No inlier matrix is ever written (the reference materialises hn*tn bytes and re-reads them,
 // ransac_voting_gpu.py:562-566).
 //
-// Exactness.  The reference decides   cos = dot(d,n) / (|n| |d|) > t   in rounded binary32 ops; its rounded
-// cosine is within (7 + 1/t) u of the true one (u = 2^-24).  The fast test works in tangent form, which is far
-// better conditioned next to cos = 1:  with U = d.n and W = d x n,   cos > c  <=>  U > 0 and |W| < T(c) U,
-// T(c) = sqrt(1 - c^2) / c.  Two thresholds tau_hi < tau_lo bracket the reference's uncertainty plus our own
-// rounding (derivation in DESIGN.md):   |W| - tau_hi U < 0  -> certainly an inlier;   |W| - tau_lo U >= 0 ->
-// certainly not.  Votes in between (about one in 10^4) are queued in shared memory and settled afterwards by
-// all lanes in parallel with the reference expression itself (explicitly rounded intrinsics), as are all votes
-// of hypotheses within 1e-3 of a pixel-lattice point (where |d| may fall under the reference's 1e-6 guard).
-// Both sign bits of every vote are collected with funnel shifts, so the hot loop has no branch.
+// Exactness.  The reference decides   cos = dot(d,n) / (|n| |d|) > t,  d = fl(h - c),  in rounded binary32 ops; its
+// rounded cosine is within (8 + 1/t) u of the cosine of the exact d = h - c (u = 2^-24; one u of that is fl(h - c)).
+// The fast test works in tangent form, far better conditioned next to cos = 1:  with U = d.n and W = d x n,
+//   cos > c  <=>  U > 0 and |W| < T(c) U,   T(c) = sqrt(1 - c^2) / c.
+// FIVE fused multiply-adds per vote.  Every block first re-expresses the chunk it staged in instance-local
+// coordinates (origin o = centre of the instance's bounding box, h' = h - o, c' = c - o exact for pixel coordinates):
+// the direction n is scaled by a power of two (exact) so that |n| <= 1, and the pixel planes (x, y) are overwritten by
+//   pu = -(c'.n),  pw = -(c' x n)        so that        U = fma(h'x, nx, fma(h'y, ny, pu)),
+//                                                        W = fma(h'x, ny, fma(-h'y, nx, pw)),   s = fma(U, -tau, |W|)
+// with tau = T(t) (middle of the reference's uncertainty interval).  sign(s) is the fast answer, collected with one
+// funnel shift per vote.  The absolute error of U and W is <= 8u (|h'x| + |h'y| + Rx + Ry) =: E (Rx, Ry = half extents of
+// the bounding box), so the answer is certain as soon as
+//   |s| >= delta(h) = 1.01 [ max(T_lo - tau, tau - T_hi) (|d|max + E) + (1 + T_lo) E ],   |d|max = |h'| + |(Rx, Ry)|,
+// T_hi = T(t (1 + eps)), T_lo = T(t (1 - eps)), eps = 1.25 (9 + 1/t) u  (derivation in DESIGN.md).  The hot loop only
+// tracks  m = min |s|  over a 16-pixel round (one 3-input FMNMX per two votes); a round with m < delta (about one
+// vote in 10^4 lands there) is re-examined by the whole warp, its uncertain votes are removed from the fast count and
+// queued in shared memory, and the queue is settled afterwards by all lanes in parallel with the reference
+// expression itself (explicitly rounded intrinsics, original operands re-read from the record planes).  Hypotheses
+// within 1e-3 of a pixel-lattice point (where |d| may fall under the reference's 1e-6 guard), non-finite or absurdly
+// far hypotheses have ALL their votes settled that way; pixels whose direction the reference's |n| < 1e-6 guard skips
+// are given pw = 1e30 (never an inlier), pixels with an absurd |n| get n = 0, pw = 0 (s = 0: always uncertain).
 constexpr int VT = 256;            // threads per block
 constexpr int VQ = 4;              // hypotheses per lane
 constexpr int VHB = 1024;          // hypotheses per batch (8 groups of 32 lanes x VQ)
-constexpr int VROUND = 16;         // pixels per sign-collection round (2 bits per vote in a 32-bit word)
+constexpr int VROUND = 16;         // pixels per sign-collection round
 constexpr int VQCAP = 2048;        // deferred exact-vote queue entries
+constexpr float V_FAR = 1e12f;     // |h'x| + |h'y| beyond this (or NaN): the hypothesis is voted exactly
+constexpr float V_NEVER = 1e30f;   // pw of a pixel that can never be an inlier
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
@@ -213,19 +227,14 @@ __device__ __forceinline__ u64 pk2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ void unpk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-    u64 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-    u64 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     u64 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {   // FMNMX3 (sm_100)
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
 
@@ -257,12 +266,15 @@ __device__ __forceinline__ bool near_lattice(float x, float y) {
     return fabsf(x - rintf(x)) < 1e-3f && fabsf(y - rintf(y)) < 1e-3f;
 }
 
+// After the prepare pass: pu[] = -(c'.n), pw[] = -(c' x n), nx[] / ny[] = the power-of-two scaled direction.
 struct __align__(128) VoteBuf {
-    float cx[VOTE_CHUNK], cy[VOTE_CHUNK], nx[VOTE_CHUNK], ny[VOTE_CHUNK];
+    float pu[VOTE_CHUNK], pw[VOTE_CHUNK], nx[VOTE_CHUNK], ny[VOTE_CHUNK];
     float2 hyp[VHB];
 };
 struct VoteItem {
-    int wi, i, hb, nh, npx, exact;
+    int wi, i, hb, nh, npx, src;
+    float ox, oy;          // origin of the instance-local frame (centre of the bounding box, integer valued)
+    float rsum, rdiag;     // Rx + Ry and |(Rx, Ry)| of the box half extents (bounds on |c'x| + |c'y| and |c'|)
 };
 struct __align__(128) VoteSmem {
     VoteBuf buf[2];
@@ -273,42 +285,49 @@ struct __align__(128) VoteSmem {
     int qn[2], nex[2];
 };
 
-// one vote on the fast path (tangent form): appends sign(r_hi), sign(r_lo) to acc
-__device__ __forceinline__ void vote_fast(float hx, float hy, float cx, float cy, float nx, float ny, float ntau_hi,
-                                          float ntau_lo, unsigned &acc) {
-    const float dx = hx - cx, dy = hy - cy;
-    const float u = fmaf(dy, ny, dx * nx);
-    const float w = fmaf(dy, nx, -(dx * ny));
-    const float rhi = fmaf(u, ntau_hi, fabsf(w));
-    const float rlo = fmaf(u, ntau_lo, fabsf(w));
-    acc = __funnelshift_l(__float_as_uint(rhi), acc, 1);
-    acc = __funnelshift_l(__float_as_uint(rlo), acc, 1);
-}
-// two pixels (a, b) against one hypothesis, packed f32x2 arithmetic; nny2 = -dir_y of the two pixels
-__device__ __forceinline__ void vote_fast2(u64 hx2, u64 hy2, u64 cx2, u64 cy2, u64 nx2, u64 ny2, u64 nny2, u64 ntau_hi2,
-                                           u64 ntau_lo2, unsigned &acc) {
-    const u64 dx = sub2(hx2, cx2), dy = sub2(hy2, cy2);
-    const u64 u = fma2(dy, ny2, mul2(dx, nx2));
-    const u64 w = fma2(dy, nx2, mul2(dx, nny2));
-    float wa, wb;
-    unpk2(w, wa, wb);
-    const u64 aw = pk2(fabsf(wa), fabsf(wb));
-    const u64 rhi = fma2(u, ntau_hi2, aw), rlo = fma2(u, ntau_lo2, aw);
-    float hia, hib, loa, lob;
-    unpk2(rhi, hia, hib);
-    unpk2(rlo, loa, lob);
-    acc = __funnelshift_l(__float_as_uint(hia), acc, 1);
-    acc = __funnelshift_l(__float_as_uint(loa), acc, 1);
-    acc = __funnelshift_l(__float_as_uint(hib), acc, 1);
-    acc = __funnelshift_l(__float_as_uint(lob), acc, 1);
-}
-
 struct VoteConsts {
-    float ntau_hi, ntau_lo;   // -tau_hi, -tau_lo
-    int all_exact;            // thresh <= 0 or otherwise outside the fast test's domain: settle every vote exactly
+    float ntau;               // -tau
+    float half_w;             // max(T_lo - tau, tau - T_hi), rounded up
+    float one_plus_tlo;       // 1 + T_lo, rounded up
+    int all_exact;            // thresh outside the fast test's domain: settle every vote exactly
     int nb;                   // hypothesis batches per (instance, chunk)
     int hyp_bulk;             // hypotheses can be bulk-copied (hn even -> 16-byte aligned batches)
 };
+
+// s of one vote, scalar twin of vote_pair below: the SAME five roundings in the same order.
+__device__ __forceinline__ float vote_s(float hx, float hy, float nx, float ny, float pu, float pw, float ntau) {
+    const float U = __fmaf_rn(hx, nx, __fmaf_rn(hy, ny, pu));
+    const float W = __fmaf_rn(hx, ny, __fmaf_rn(-hy, nx, pw));
+    return __fmaf_rn(U, ntau, fabsf(W));
+}
+// one hypothesis against two pixels (packed f32x2 lanes): appends the two sign bits to acc, folds |s| into m
+template <bool PACKED>
+__device__ __forceinline__ void vote_pair(float hx, float hy, float nxa, float nxb, float nya, float nyb, float pua, float pub,
+                                          float pwa, float pwb, float ntau, unsigned &acc, float &m) {
+    float sa, sb;
+    if (PACKED) {
+        const u64 hx2 = pk2(hx, hx), hy2 = pk2(hy, hy), nhy2 = pk2(-hy, -hy);
+        const u64 nx2 = pk2(nxa, nxb), ny2 = pk2(nya, nyb);
+        const u64 U = fma2(hx2, nx2, fma2(hy2, ny2, pk2(pua, pub)));
+        const u64 W = fma2(hx2, ny2, fma2(nhy2, nx2, pk2(pwa, pwb)));
+        float wa, wb;
+        unpk2(W, wa, wb);
+        unpk2(fma2(U, pk2(ntau, ntau), pk2(fabsf(wa), fabsf(wb))), sa, sb);
+    } else {
+        sa = vote_s(hx, hy, nxa, nya, pua, pwa, ntau);
+        sb = vote_s(hx, hy, nxb, nyb, pub, pwb, ntau);
+    }
+    acc = __funnelshift_l(__float_as_uint(sa), acc, 1);
+    acc = __funnelshift_l(__float_as_uint(sb), acc, 1);
+    m = min3(m, fabsf(sa), fabsf(sb));
+}
+// |s| >= band_delta(h') : the sign of s is certainly the reference's answer (see the comment above)
+__device__ __forceinline__ float band_delta(float hx, float hy, float rsum, float rdiag, const VoteConsts &vc) {
+    const float a = fabsf(hx) + fabsf(hy);
+    if (!(a < V_FAR)) return 0.f;                       // voted exactly, never on the fast path
+    const float E = 4.8e-7f * (a + rsum);               // 8 u (|h'x| + |h'y| + Rx + Ry), rounded up
+    return 1.01f * (vc.half_w * (1.0002f * (a + rdiag) + E) + vc.one_plus_tlo * E);
+}
 
 template <int ARITH, bool PACKED>
 __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ counters, PathParams pp, RecPlanes rec,
@@ -326,23 +345,31 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
     auto fetch = [&](int b, int wi) {
         VoteItem it;
         it.wi = wi;
-        it.i = it.hb = it.nh = it.npx = it.exact = 0;
+        it.i = it.hb = it.nh = it.npx = it.src = 0;
+        it.ox = it.oy = it.rsum = it.rdiag = 0.f;
         if (wi < W) {
             const int4 d = work[wi];
             it.i = d.x;
+            it.src = d.y;
             it.npx = d.z & 0xffff;
             it.nh = d.z >> 16;
             it.hb = d.w;
             const uint32_t pbytes = (uint32_t)((it.npx + 3) & ~3) * 4u;
             const uint32_t hbytes = vc.hyp_bulk ? (uint32_t)it.nh * 8u : 0u;
             const size_t src = (size_t)d.y;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this buffer are done
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this buffer are done
             mbar_expect_tx(&sm.bar[b], 4u * pbytes + hbytes);
-            bulk_g2s(sm.buf[b].cx, rec.x + src, pbytes, &sm.bar[b]);
-            bulk_g2s(sm.buf[b].cy, rec.y + src, pbytes, &sm.bar[b]);
+            bulk_g2s(sm.buf[b].pu, rec.x + src, pbytes, &sm.bar[b]);
+            bulk_g2s(sm.buf[b].pw, rec.y + src, pbytes, &sm.bar[b]);
             bulk_g2s(sm.buf[b].nx, rec.nx + src, pbytes, &sm.bar[b]);
             bulk_g2s(sm.buf[b].ny, rec.ny + src, pbytes, &sm.bar[b]);
             if (hbytes) bulk_g2s(sm.buf[b].hyp, hyp_g + (size_t)it.i * hn + it.hb, hbytes, &sm.bar[b]);
+            const int x0 = T.xmin[it.i], x1 = T.xmax[it.i], y0 = T.ymin[it.i], y1 = T.ymax[it.i];
+            it.ox = (float)((x0 + x1 + 1) >> 1);
+            it.oy = (float)((y0 + y1 + 1) >> 1);
+            const float rx = 0.5f * (float)(x1 - x0) + 1.f, ry = 0.5f * (float)(y1 - y0) + 1.f;   // >= |c'x|, |c'y|
+            it.rsum = rx + ry;
+            it.rdiag = 1.0001f * sqrtf(rx * rx + ry * ry);
         }
         sm.item[b] = it;
         sm.qn[b] = 0;
@@ -375,27 +402,40 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
         phase[cur] ^= 1u;
         VoteBuf &B = sm.buf[cur];
         const int i = it.i, npx = it.npx, nh = it.nh, hb = it.hb;
+        const size_t gsrc = (size_t)it.src;
         const int nrounds = (npx + VROUND - 1) / VROUND;
-        // ---- fix-up: padding pixels and pixels with |n| < 1e-6 (.cu:119) can never be inliers ----
+        // ---- prepare pass: (x, y, dir) -> (pu, pw, scaled dir) in the instance-local frame ----
         if (tid * 4 < nrounds * VROUND) {
-            float4 cx = *reinterpret_cast<float4 *>(&B.cx[tid * 4]), cy = *reinterpret_cast<float4 *>(&B.cy[tid * 4]);
+            float4 cx = *reinterpret_cast<float4 *>(&B.pu[tid * 4]), cy = *reinterpret_cast<float4 *>(&B.pw[tid * 4]);
             float4 nx = *reinterpret_cast<float4 *>(&B.nx[tid * 4]), ny = *reinterpret_cast<float4 *>(&B.ny[tid * 4]);
             float *pcx = &cx.x, *pcy = &cy.x, *pnx = &nx.x, *pny = &ny.x;
-            bool dirty = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (tid * 4 + j >= npx) {
-                    pcx[j] = 1e18f; pcy[j] = 1e18f; pnx[j] = 0.f; pny[j] = 0.f;
-                    dirty = true;
-                } else if (below_1e6(__fsqrt_rn(sum_prod<ARITH>(pnx[j], pnx[j], pny[j], pny[j])))) {
-                    pnx[j] = 0.f; pny[j] = 0.f;
-                    dirty = true;
+                float X = 0.f, Y = V_NEVER, NX = 0.f, NY = 0.f;          // padding pixel: never an inlier
+                if (tid * 4 + j < npx) {
+                    const float nn = sum_prod<ARITH>(pnx[j], pnx[j], pny[j], pny[j]);
+                    const float nrm = __fsqrt_rn(nn);
+                    if (!(nrm > 1e-6f)) {
+                        // |n| under the reference's guard (.cu:119), or NaN: never an inlier
+                    } else if (!(nrm < 1e18f)) {
+                        Y = 0.f;                                         // absurd direction: s = 0, settled exactly
+                    } else {
+                        float sc = 1.f;
+                        if (!(nn <= 1.0002f && nn >= 0.25f)) {           // not (nearly) a unit vector: scale |n| into [0.5, 1)
+                            const int e = (int)((__float_as_uint(nrm) >> 23) & 0xffu) - 126;
+                            sc = __uint_as_float((unsigned)(127 - e) << 23);
+                        }
+                        NX = pnx[j] * sc;
+                        NY = pny[j] * sc;
+                        const float ccx = pcx[j] - it.ox, ccy = pcy[j] - it.oy;
+                        X = -__fmaf_rn(ccx, NX, __fmul_rn(ccy, NY));
+                        Y = -__fmaf_rn(ccx, NY, -__fmul_rn(ccy, NX));
+                    }
                 }
+                pcx[j] = X; pcy[j] = Y; pnx[j] = NX; pny[j] = NY;
             }
-            if (dirty) {
-                *reinterpret_cast<float4 *>(&B.cx[tid * 4]) = cx; *reinterpret_cast<float4 *>(&B.cy[tid * 4]) = cy;
-                *reinterpret_cast<float4 *>(&B.nx[tid * 4]) = nx; *reinterpret_cast<float4 *>(&B.ny[tid * 4]) = ny;
-            }
+            *reinterpret_cast<float4 *>(&B.pu[tid * 4]) = cx; *reinterpret_cast<float4 *>(&B.pw[tid * 4]) = cy;
+            *reinterpret_cast<float4 *>(&B.nx[tid * 4]) = nx; *reinterpret_cast<float4 *>(&B.ny[tid * 4]) = ny;
         }
         const bool item_exact = vc.all_exact;
         const int G = (nh + 127) >> 7;  // groups of 128 hypotheses (32 lanes x VQ)
@@ -403,7 +443,8 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
             float2 hp = make_float2(0.f, 0.f);
             if (k < nh) {
                 hp = vc.hyp_bulk ? B.hyp[k] : hyp_g[(size_t)i * hn + hb + k];
-                if (item_exact || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex[cur], 1)] = (unsigned short)k;
+                const bool far = !(fabsf(hp.x - it.ox) + fabsf(hp.y - it.oy) < V_FAR);
+                if (item_exact || far || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex[cur], 1)] = (unsigned short)k;
             }
             if (!vc.hyp_bulk || k >= nh) B.hyp[k] = hp;
         }
@@ -412,70 +453,76 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
         const int parts = 8 / G;  // G <= 8 because VHB = 8 * 128
         if (wv < G * parts) {
             const int g = wv % G, part = wv / G;
-            float hx[VQ], hy[VQ];
+            float hx[VQ], hy[VQ];   // instance-local hypotheses
             int cnt[VQ];
             bool ex[VQ];
+            float dl = 0.f;         // largest band_delta of this lane's hypotheses
 #pragma unroll
             for (int q = 0; q < VQ; ++q) {
                 const int idx = g * 128 + q * 32 + lane;
                 const float2 hp = B.hyp[idx];
-                hx[q] = hp.x; hy[q] = hp.y;
+                hx[q] = hp.x - it.ox; hy[q] = hp.y - it.oy;
                 cnt[q] = 0;
-                ex[q] = (idx >= nh) || item_exact || near_lattice(hp.x, hp.y);   // not counted on the fast path
+                ex[q] = (idx >= nh) || item_exact || near_lattice(hp.x, hp.y) || !(fabsf(hx[q]) + fabsf(hy[q]) < V_FAR);
+                if (ex[q]) { hx[q] = 3e15f; hy[q] = 1e15f; }            // not counted on the fast path; band_delta = 0
+                dl = fmaxf(dl, band_delta(hx[q], hy[q], it.rsum, it.rdiag, vc));
             }
-            const u64 nthi2 = pk2(vc.ntau_hi, vc.ntau_hi), ntlo2 = pk2(vc.ntau_lo, vc.ntau_lo);
             for (int rd = part; rd < nrounds; rd += parts) {
                 unsigned acc[VQ];
 #pragma unroll
                 for (int q = 0; q < VQ; ++q) acc[q] = 0u;
+                float m = 3e38f;
                 const int kb = rd * VROUND;
 #pragma unroll
                 for (int j4 = 0; j4 < VROUND; j4 += 4) {
-                    const float4 cx = *reinterpret_cast<const float4 *>(&B.cx[kb + j4]);
-                    const float4 cy = *reinterpret_cast<const float4 *>(&B.cy[kb + j4]);
+                    const float4 pu = *reinterpret_cast<const float4 *>(&B.pu[kb + j4]);
+                    const float4 pw = *reinterpret_cast<const float4 *>(&B.pw[kb + j4]);
                     const float4 nx = *reinterpret_cast<const float4 *>(&B.nx[kb + j4]);
                     const float4 ny = *reinterpret_cast<const float4 *>(&B.ny[kb + j4]);
-                    if (PACKED) {
-                        const u64 cxa = pk2(cx.x, cx.y), cxb = pk2(cx.z, cx.w), cya = pk2(cy.x, cy.y), cyb = pk2(cy.z, cy.w);
-                        const u64 nxa = pk2(nx.x, nx.y), nxb = pk2(nx.z, nx.w), nya = pk2(ny.x, ny.y), nyb = pk2(ny.z, ny.w);
-                        const u64 nnya = pk2(-ny.x, -ny.y), nnyb = pk2(-ny.z, -ny.w);
 #pragma unroll
-                        for (int q = 0; q < VQ; ++q) {
-                            const u64 hx2 = pk2(hx[q], hx[q]), hy2 = pk2(hy[q], hy[q]);
-                            vote_fast2(hx2, hy2, cxa, cya, nxa, nya, nnya, nthi2, ntlo2, acc[q]);
-                            vote_fast2(hx2, hy2, cxb, cyb, nxb, nyb, nnyb, nthi2, ntlo2, acc[q]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < VQ; ++q) {
-                            vote_fast(hx[q], hy[q], cx.x, cy.x, nx.x, ny.x, vc.ntau_hi, vc.ntau_lo, acc[q]);
-                            vote_fast(hx[q], hy[q], cx.y, cy.y, nx.y, ny.y, vc.ntau_hi, vc.ntau_lo, acc[q]);
-                            vote_fast(hx[q], hy[q], cx.z, cy.z, nx.z, ny.z, vc.ntau_hi, vc.ntau_lo, acc[q]);
-                            vote_fast(hx[q], hy[q], cx.w, cy.w, nx.w, ny.w, vc.ntau_hi, vc.ntau_lo, acc[q]);
-                        }
+                    for (int q = 0; q < VQ; ++q) {
+                        vote_pair<PACKED>(hx[q], hy[q], nx.x, nx.y, ny.x, ny.y, pu.x, pu.y, pw.x, pw.y, vc.ntau, acc[q], m);
+                        vote_pair<PACKED>(hx[q], hy[q], nx.z, nx.w, ny.z, ny.w, pu.z, pu.w, pw.z, pw.w, vc.ntau, acc[q], m);
                     }
                 }
-                // pixel j of the round sits at bits (2*(15-j)+1: sign(r_hi), 2*(15-j): sign(r_lo))
+                // pixel j of the round sits at bit 15 - j of acc[q] (set: s < 0, inlier on the fast path)
+                unsigned tm = __ballot_sync(FULL, m < dl);
+                while (tm) {
+                    // some vote of lane `src` may be uncertain: the warp recomputes its 16 pixels x VQ hypotheses
+                    // (lane -> pixel lane & 15, hypotheses 2 (lane >> 4) and 2 (lane >> 4) + 1), bit-identical s
+                    const int src = __ffs(tm) - 1;
+                    tm &= tm - 1;
+                    float bhx[VQ], bhy[VQ];
 #pragma unroll
-                for (int q = 0; q < VQ; ++q) {
-                    const unsigned a = acc[q];
-                    cnt[q] += __popc(a & 0xAAAAAAAAu);                  // r_hi < 0: certainly in
-                    unsigned b = a & ~(a >> 1) & 0x55555555u;          // r_lo < 0 <= r_hi: inside the band
-                    if (b && !ex[q]) {
-                        const unsigned hidx = (unsigned)(g * 128 + q * 32 + lane);
-                        while (b) {
-                            const int pos = __ffs(b) - 1;
-                            b &= b - 1;
-                            const int k = kb + 15 - (pos >> 1);
+                    for (int q = 0; q < VQ; ++q) { bhx[q] = __shfl_sync(FULL, hx[q], src); bhy[q] = __shfl_sync(FULL, hy[q], src); }
+                    const int k = kb + (lane & 15);
+                    const float kpu = B.pu[k], kpw = B.pw[k], knx = B.nx[k], kny = B.ny[k];
+                    const bool up = lane >> 4;
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const float qhx = up ? bhx[2 + qq] : bhx[qq], qhy = up ? bhy[2 + qq] : bhy[qq];
+                        const float s = vote_s(qhx, qhy, knx, kny, kpu, kpw, vc.ntau);
+                        const bool band = fabsf(s) < band_delta(qhx, qhy, it.rsum, it.rdiag, vc);
+                        const unsigned bm = __ballot_sync(FULL, band);
+                        if (band) {
+                            const unsigned hidx = (unsigned)(g * 128 + ((up ? 2 : 0) + qq) * 32 + src);
                             const int slot = atomicAdd(&sm.qn[cur], 1);
                             if (slot < VQCAP) {
                                 sm.queue[slot] = ((unsigned)k << 16) | hidx;
-                            } else if (vote_exact<ARITH>(B.cx[k], B.cy[k], B.nx[k], B.ny[k], hx[q], hy[q], thresh)) {
-                                atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);   // queue full: settle it right here
+                            } else {                                       // queue full: settle it right here
+                                const float2 hp = B.hyp[hidx];
+                                if (vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh))
+                                    atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);
                             }
+                        }
+                        if (lane == src) {                                 // uncertain votes leave the fast count
+                            acc[qq] &= ~(__brev(bm & 0xffffu) >> 16);
+                            acc[2 + qq] &= ~(__brev(bm >> 16) >> 16);
                         }
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < VQ; ++q) cnt[q] += __popc(acc[q]);
             }
 #pragma unroll
             for (int q = 0; q < VQ; ++q) {
@@ -484,23 +531,23 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
             }
         }
         __syncthreads();
-        // ---- band votes: the reference expression, one queued vote per thread ----
+        // ---- uncertain votes: the reference expression on the original operands, one queued vote per thread ----
         const int nq = min(sm.qn[cur], VQCAP);
         for (int e = tid; e < nq; e += VT) {
             const unsigned ent = sm.queue[e];
             const int k = (int)(ent >> 16), hidx = (int)(ent & 0xffffu);
             const float2 hp = B.hyp[hidx];
-            if (vote_exact<ARITH>(B.cx[k], B.cy[k], B.nx[k], B.ny[k], hp.x, hp.y, thresh))
+            if (vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh))
                 atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);
         }
-        // ---- hypotheses on (or within 1e-3 of) the pixel lattice: every vote with the reference expression ----
+        // ---- hypotheses on (or within 1e-3 of) the pixel lattice, far or non-finite: every vote with the reference expression ----
         const int nex = sm.nex[cur];
         for (int e = 0; e < nex; ++e) {
             const int hidx = sm.exlist[e];
             const float2 hp = B.hyp[hidx];
             int c = 0;
             for (int k = tid; k < npx; k += VT)
-                c += vote_exact<ARITH>(B.cx[k], B.cy[k], B.nx[k], B.ny[k], hp.x, hp.y, thresh) ? 1 : 0;
+                c += vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
             c = __reduce_add_sync(FULL, c);
             if (lane == 0 && c) atomicAdd(&votes[(size_t)i * hn + hb + hidx], c);
         }
@@ -956,38 +1003,33 @@ static int vote_packed() {
     return g_vote_packed;
 }
 
-// Thresholds of the tangent-form fast test (see the comment above k_vote and DESIGN.md).
+// Constants of the tangent-form fast test (see the comment above k_vote and DESIGN.md), computed in double.
 static VoteConsts vote_consts(const PathParams &pp) {
     VoteConsts vc;
     vc.nb = (pp.hn + VHB - 1) / VHB;
     vc.hyp_bulk = (pp.hn % 2 == 0) ? 1 : 0;
-    vc.all_exact = 0;
-    vc.ntau_hi = 0.f;
-    vc.ntau_lo = 0.f;
+    vc.all_exact = 1;
+    vc.ntau = 0.f;
+    vc.half_w = 0.f;
+    vc.one_plus_tlo = 1.f;
     const double t = (double)pp.inlier_thresh;
     const double u = ldexp(1.0, -24);
-    if (!(t > 1e-3) || !(t < 1.0)) {          // outside the fast test's domain: settle every vote exactly
-        vc.all_exact = 1;
-        return vc;
-    }
-    const double eps_r = 1.25 * (7.0 + 1.0 / t) * u;          // reference's rounded cosine vs the true one
+    if (!(t > 1e-3) || !(t < 1.0)) return vc;                 // outside the fast test's domain: settle every vote exactly
+    const double eps_r = 1.25 * (9.0 + 1.0 / t) * u;          // reference's rounded cosine vs the cosine of the exact h - c
     const double c_hi = t * (1.0 + eps_r), c_lo = t * (1.0 - eps_r);
-    auto T = [](double c) { return c < 1.0 ? sqrt(1.0 - c * c) / c : 0.0; };
-    const double sin_hi = c_hi < 1.0 ? sqrt(1.0 - c_hi * c_hi) : 0.0;
-    double tau_hi = 0.0;
-    const double tau_lo_raw = T(c_lo);
-    double m = 1.0;
-    if (sin_hi > 0.0) {
-        m = 2.0 * (2.0 * u / sin_hi + 2.0 * u / t);            // our own rounding of |W| / U, with a factor 2 of slack
-        tau_hi = T(c_hi) * (1.0 - m);
-        if (tau_hi < 0.0) tau_hi = 0.0;
-    }
-    const double tau_lo = tau_lo_raw * (1.0 + m);
-    float fhi = (float)tau_hi, flo = (float)tau_lo;
-    if ((double)fhi > tau_hi) fhi = nextafterf(fhi, 0.f);      // round the certain-inlier bound down ...
-    if ((double)flo < tau_lo) flo = nextafterf(flo, INFINITY); // ... and the certain-outlier bound up
-    vc.ntau_hi = -fhi;
-    vc.ntau_lo = -flo;
+    if (!(c_hi < 1.0)) return vc;
+    auto T = [](double c) { return sqrt(1.0 - c * c) / c; };
+    const double t_hi = T(c_hi), t_lo = T(c_lo);              // t_hi < t_lo
+    const float tau = (float)(0.5 * (t_hi + t_lo));
+    if (!((double)tau > t_hi && (double)tau < t_lo)) return vc;   // interval narrower than binary32 resolves
+    float hw = (float)std::max(t_lo - (double)tau, (double)tau - t_hi);
+    if ((double)hw < std::max(t_lo - (double)tau, (double)tau - t_hi)) hw = nextafterf(hw, INFINITY);
+    float opt = (float)(1.0 + t_lo);
+    if ((double)opt < 1.0 + t_lo) opt = nextafterf(opt, INFINITY);
+    vc.ntau = -tau;
+    vc.half_w = hw;
+    vc.one_plus_tlo = opt;
+    vc.all_exact = 0;
     return vc;
 }
 

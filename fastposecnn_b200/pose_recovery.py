@@ -10,6 +10,7 @@ unless asked for.
 from __future__ import annotations
 
 import ctypes
+from collections import OrderedDict
 from typing import Dict, Optional
 
 import torch
@@ -24,7 +25,7 @@ class PoseRecoveryEngine:
 
     def __init__(self, b: int, h: int, w: int, num_classes: int, hn: int, device, *, max_instances: Optional[int] = None,
                  max_records: Optional[int] = None, max_rows: Optional[int] = None, inlier_thresh: float = 0.999,
-                 min_num: int = 5, max_num: int = 30000, arith: int = _lib.ARITH_IEEE, seed: int = 1234,
+                 min_num: int = 5, max_num: int = 30000, arith: int = _lib.ARITH_IEEE, seed: Optional[int] = None,
                  want_labels: bool = False, upsample: int = 1):
         self.device = torch.device(device)
         # head-epilogue fusion: inputs are the heads' low-resolution outputs [b,.,h/upsample,w/upsample]; (h, w) stay the
@@ -40,7 +41,8 @@ class PoseRecoveryEngine:
         self.max_records = int(max_records if max_records is not None else P + 16 * self.max_instances)  # ranges padded to 16
         self.max_rows = int(max_rows if max_rows is not None else min(P, self.max_instances * h))
         self.inlier_thresh, self.min_num, self.max_num = float(inlier_thresh), int(min_num), int(max_num)
-        self.arith, self.seed = int(arith), int(seed)
+        # seed=None: every launch() draws fresh pixel pairs (a captured graph replays the pairs of its capture)
+        self.arith, self.seed = int(arith), (None if seed is None else int(seed))
         L = _lib.lib()
         a = self._base_args()
         nbytes = L.fpc_pose_recover_workspace_bytes(ctypes.byref(a))
@@ -68,7 +70,7 @@ class PoseRecoveryEngine:
         a.b, a.h, a.w, a.num_classes, a.hn = self.b, self.h, self.w, self.num_classes, self.hn
         a.max_instances, a.max_records, a.max_rows = self.max_instances, self.max_records, self.max_rows
         a.inlier_thresh, a.min_num, a.max_num = self.inlier_thresh, self.min_num, self.max_num
-        a.arith, a.seed = self.arith, self.seed
+        a.arith, a.seed = self.arith, (_lib.fresh_seed() if self.seed is None else self.seed)
         a.upsample = self.upsample
         return a
 
@@ -168,13 +170,8 @@ class PoseRecoveryEngine:
     def wait_count(self) -> int:
         self._fetch_event.synchronize()
         c = self.counters_host
-        flags = int(c[_lib.CNT_FLAGS])
-        if flags:
-            what = [n for bit, n in ((_lib.FLAG_INSTANCES, f"instances ({int(c[_lib.CNT_INSTANCES])} > max_instances={self.max_instances})"),
-                                     (_lib.FLAG_ROWS, f"rows ({int(c[_lib.CNT_ROWS])} > max_rows={self.max_rows})"),
-                                     (_lib.FLAG_RECORDS, f"records ({int(c[_lib.CNT_RECORDS])} > max_records={self.max_records})"))
-                    if flags & bit]
-            raise RuntimeError("libfpc_b200 error -3 (FPC_ECAPACITY): capacity exceeded for " + ", ".join(what))
+        if int(c[_lib.CNT_FLAGS]):
+            raise _lib.capacity_error(c, self.max_instances, self.max_rows, self.max_records)
         return int(c[_lib.CNT_INSTANCES])
 
     def table_to_agg(self, n: int, table: Optional[torch.Tensor] = None, sample_offset: int = 0) -> Dict[str, torch.Tensor]:
@@ -273,10 +270,44 @@ class _NullCtx:
         return False
 
 
-_engines: Dict[tuple, PoseRecoveryEngine] = {}
+def _recover_training(eng, logits, heads, inv_intrinsics, idxs, select_u, C, device):
+    """quaternion / scales / z / xy of the result stay differentiable w.r.t. their head maps (autograd.PoseRecoverFn); each
+    call gets its own tables so that the saved tensors survive later calls."""
+    from .autograd import PoseRecoverFn
+    holder = {}
+
+    def run():
+        extra = torch.zeros((eng.max_instances, 4), dtype=torch.float32, device=device)
+        eng.extra_out = extra
+        try:
+            eng.launch({k: v.detach() for k, v in logits.items()}, inv_intrinsics, idxs=idxs, select_u=select_u)
+        finally:
+            eng.extra_out = None
+        n_ = eng.fetch_count()
+        agg_ = eng.table_to_agg(n_, table=eng.pose_table[:n_].clone())
+        if n_ and int(agg_["mask_sizes"].max()) > eng.max_num:
+            raise NotImplementedError("pose_recover backward: an instance was sub-sampled to max_num voters, which is not "
+                                      "differentiable here; raise max_num")
+        holder["agg"], holder["n"] = agg_, n_
+        return agg_, eng.labels.clone(), eng.cat_mask_u8.clone(), agg_["mask_sizes"].to(torch.int32), extra[:n_, 2].clone()
+    q_o, s_o, z_o, xy_o = PoseRecoverFn.apply(run, C, eng.inlier_thresh, eng.arith, *heads)
+    agg, n = holder["agg"], holder["n"]
+    agg.update({"quaternion": q_o, "scales": s_o, "z": z_o, "xy": xy_o})
+    # R / T / RT through the differentiable batchwise_get_RT: rotation / translation losses reach q, z and the xy head
+    from .gpu_tensor_funcs import batchwise_get_RT
+    agg["R"], agg["T"], agg["RT"] = batchwise_get_RT(q_o, xy_o, z_o, inv_intrinsics)
+    return agg, n
+
+
+ENGINE_CACHE_SIZE = 4                                   # engines kept by get_engine (least recently used is dropped)
+_engines: "OrderedDict[tuple, PoseRecoveryEngine]" = OrderedDict()
+_grown_caps: Dict[tuple, dict] = {}                     # shape key -> capacities a default-capacity engine had to grow to
+_CAP_KEYS = ("max_instances", "max_rows", "max_records")
 
 
 def get_engine(b, h, w, num_classes, hn, device, **kw) -> PoseRecoveryEngine:
+    """Engines are cached by shape (they own multi-GB workspaces); at most ``ENGINE_CACHE_SIZE`` are kept, so a
+    last-batch-of-epoch shape does not pin a second workspace forever."""
     if kw.get("upsample", 1) == 1:
         kw.pop("upsample", None)          # the default: same cache entry whether or not it was spelled out
     key = (b, h, w, num_classes, hn, str(torch.device(device)), tuple(sorted(kw.items())))
@@ -284,6 +315,10 @@ def get_engine(b, h, w, num_classes, hn, device, **kw) -> PoseRecoveryEngine:
     if eng is None:
         eng = PoseRecoveryEngine(b, h, w, num_classes, hn, device, **kw)
         _engines[key] = eng
+        while len(_engines) > max(1, ENGINE_CACHE_SIZE):
+            _engines.popitem(last=False)
+    else:
+        _engines.move_to_end(key)
     return eng
 
 
@@ -298,46 +333,43 @@ def pose_recover(logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, 
 
     ``upsample=S > 1`` (head-epilogue fusion): ``logits`` are the heads' LOW-RESOLUTION outputs ``[b,.,h/S,w/S]`` (after
     the 1x1 convolutions, before ``nn.UpsamplingBilinear2d(scale_factor=S)``); the up-sampling is evaluated inside the
-    kernels and the full-resolution head maps never exist.  Results refer to the full ``[h,w]`` resolution."""
+    kernels and the full-resolution head maps never exist.  Results refer to the full ``[h,w]`` resolution.
+
+    Every returned tensor is OWNED by the caller (a copy of the cached engine's tables), like the reference's fresh
+    tensors: a later call with the same shape does not change earlier results.  Like the reference
+    (lib/aggregation_layer.py:87-118) any number of instances is accepted: with default capacities the tables grow and
+    the call is repeated; capacities passed explicitly (``max_instances`` / ``max_rows`` / ``max_records``) are hard
+    limits and overflow raises ``CapacityError`` (FPC_ECAPACITY)."""
     mask = logits["mask"]
     b, C, h, w = mask.shape
     h, w = h * upsample, w * upsample
     # head maps may also be PINNED HOST tensors (read in place over PCIe); the device then comes from inv_intrinsics
     device = mask.device if mask.is_cuda else inv_intrinsics.device
-    eng = get_engine(b, h, w, C, hn, device, want_labels=True, upsample=upsample, **engine_kw)
+    auto_grow = not any(k in engine_kw for k in _CAP_KEYS)
+    shape_key = (b, h, w, C, hn, str(torch.device(device)), upsample, tuple(sorted(engine_kw.items())))
     heads = [logits[k] for k in ("quaternion", "scales", "z", "xy")]
-    if torch.is_grad_enabled() and upsample == 1 and any(t.requires_grad for t in heads):
-        # training: quaternion / scales / z of the result stay differentiable w.r.t. their head maps (autograd.PoseRecoverFn);
-        # each call gets its own tables so that the saved tensors survive later calls
-        from .autograd import PoseRecoverFn
-        holder = {}
-
-        def run():
-            extra = torch.zeros((eng.max_instances, 4), dtype=torch.float32, device=device)
-            eng.extra_out = extra
-            try:
-                eng.launch({k: v.detach() for k, v in logits.items()}, inv_intrinsics, idxs=idxs, select_u=select_u)
-            finally:
-                eng.extra_out = None
-            n_ = eng.fetch_count()
-            agg_ = {k: v.clone() for k, v in eng.table_to_agg(n_).items()}
-            if n_ and int(agg_["mask_sizes"].max()) > eng.max_num:
-                raise NotImplementedError("pose_recover backward: an instance was sub-sampled to max_num voters, which is not "
-                                          "differentiable here; raise max_num")
-            holder["agg"], holder["n"] = agg_, n_
-            return agg_, eng.labels.clone(), eng.cat_mask_u8.clone(), agg_["mask_sizes"].to(torch.int32), extra[:n_, 2].clone()
-        q_o, s_o, z_o, xy_o = PoseRecoverFn.apply(run, C, eng.inlier_thresh, eng.arith, *heads)
-        agg, n = holder["agg"], holder["n"]
-        agg.update({"quaternion": q_o, "scales": s_o, "z": z_o, "xy": xy_o})
-        # R / T / RT through the differentiable batchwise_get_RT: rotation / translation losses reach q, z and the xy head
-        from .gpu_tensor_funcs import batchwise_get_RT
-        agg["R"], agg["T"], agg["RT"] = batchwise_get_RT(q_o, xy_o, z_o, inv_intrinsics)
-    else:
-        eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
-        n = eng.fetch_count()
-        agg = eng.table_to_agg(n)
-    agg["cat_mask"] = eng.cat_mask_u8
-    agg["labels"] = eng.labels
+    training = torch.is_grad_enabled() and upsample == 1 and any(t.requires_grad for t in heads)
+    for attempt in range(5):
+        caps = _grown_caps.get(shape_key, {}) if auto_grow else {}
+        eng = get_engine(b, h, w, C, hn, device, want_labels=True, upsample=upsample, **engine_kw, **caps)
+        try:
+            if training:
+                agg, n = _recover_training(eng, logits, heads, inv_intrinsics, idxs, select_u, C, device)
+            else:
+                eng.launch(logits, inv_intrinsics, idxs=idxs, select_u=select_u)
+                n = eng.fetch_count()
+                agg = eng.table_to_agg(n, table=eng.pose_table[:n].clone())
+            break
+        except _lib.CapacityError as e:
+            if not auto_grow or attempt == 4:
+                raise
+            mi, mr, mrec = e.grown(eng.max_instances, eng.max_rows, eng.max_records, b * h * w, h)
+            _grown_caps[shape_key] = {"max_instances": mi, "max_rows": mr, "max_records": mrec}
+            for k in [k for k, v in _engines.items() if v is eng]:
+                del _engines[k]                          # the outgrown engine's workspace is released
+            del eng
+    agg["cat_mask"] = eng.cat_mask_u8.clone()
+    agg["labels"] = eng.labels.clone()
     if materialize_dense:
         # optional reference-layout dense outputs (one extra class-compression pass for the xy field)
         from .aggregation_layer import materialize_instance_masks, materialize_xy_mask

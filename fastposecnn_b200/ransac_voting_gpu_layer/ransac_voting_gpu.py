@@ -18,7 +18,7 @@ from typing import Optional
 import torch
 
 from .. import _lib
-from ..aggregation_layer import _pipeline_args, _read_count
+from ..aggregation_layer import _pipeline_args, _read_count, grow_and_retry
 
 
 def b_inv(b_mat: torch.Tensor) -> torch.Tensor:
@@ -39,29 +39,33 @@ def _vote(nprob, h, w, vn, fmask, imask, nplanes_per_src, match_base, vertex, ro
         idxs = _lib.require_cuda(idxs, "idxs", torch.int32, contiguous=False)
         idxs = idxs.reshape(nprob, round_hyp_num, vn, 2)
     for vi in range(vn):
-        with torch.cuda.device(dev):
-            a, bufs = _pipeline_args(nprob, h, w, 2, round_hyp_num, nprob, dev, inlier_thresh=float(inlier_thresh),
-                                     min_num=int(min_num), max_num=int(max_num),
-                                     arith=_lib.ARITH_IEEE if arith is None else int(arith))
-            hyp = torch.empty((nprob, round_hyp_num, 2), dtype=torch.float32, device=dev)
-            votes = torch.empty((nprob, round_hyp_num), dtype=torch.int32, device=dev)
-            a.hyp_out, a.vote_counts_out = hyp.data_ptr(), votes.data_ptr()
-            extra = torch.empty((nprob, 4), dtype=torch.float32, device=dev) if details is not None else None
-            if extra is not None:
-                a.extra_out = extra.data_ptr()
-            keep = []
-            if idxs is not None:
-                ix = idxs[:, :, vi, :].contiguous()
-                keep.append(ix)
-                a.idxs = ix.data_ptr()
-            if select_u is not None:
-                a.select_u = select_u.data_ptr()
-            v = vertex[..., vi, :]                       # [P,h,w,2] strided view of this keypoint
-            sN, sH, sW, s2 = v.stride()
-            base = v.data_ptr()
-            _lib.check(_lib.lib().fpc_vote_dense(ctypes.byref(a), _lib.ptr(fmask), _lib.ptr(imask), nplanes_per_src,
-                                                 match_base, base, sN, sH, sW, s2, 1 if refine else 0))
-            _read_count(bufs, nprob)
+        def vote_with(_cap, max_rows, max_records, vi=vi):
+            with torch.cuda.device(dev):
+                a, bufs = _pipeline_args(nprob, h, w, 2, round_hyp_num, nprob, dev, inlier_thresh=float(inlier_thresh),
+                                         min_num=int(min_num), max_num=int(max_num), max_rows=max_rows, max_records=max_records,
+                                         arith=_lib.ARITH_IEEE if arith is None else int(arith))
+                hyp = torch.empty((nprob, round_hyp_num, 2), dtype=torch.float32, device=dev)
+                votes = torch.empty((nprob, round_hyp_num), dtype=torch.int32, device=dev)
+                a.hyp_out, a.vote_counts_out = hyp.data_ptr(), votes.data_ptr()
+                extra = torch.empty((nprob, 4), dtype=torch.float32, device=dev) if details is not None else None
+                if extra is not None:
+                    a.extra_out = extra.data_ptr()
+                keep = []
+                if idxs is not None:
+                    ix = idxs[:, :, vi, :].contiguous()
+                    keep.append(ix)
+                    a.idxs = ix.data_ptr()
+                if select_u is not None:
+                    a.select_u = select_u.data_ptr()
+                v = vertex[..., vi, :]                       # [P,h,w,2] strided view of this keypoint
+                sN, sH, sW, s2 = v.stride()
+                base = v.data_ptr()
+                _lib.check(_lib.lib().fpc_vote_dense(ctypes.byref(a), _lib.ptr(fmask), _lib.ptr(imask), nplanes_per_src,
+                                                     match_base, base, sN, sH, sW, s2, 1 if refine else 0))
+                _read_count(bufs, nprob)
+            return bufs, hyp, votes, extra
+        # the number of problems is known; the run / record tables (speckled masks) grow on demand
+        bufs, hyp, votes, extra = grow_and_retry(vote_with, nprob, fixed=False)
         table = bufs["table_full"][1:1 + nprob]
         out[:, vi, :] = table[:, _lib.ROW_XY:_lib.ROW_XY + 2]
         if details is not None:

@@ -99,7 +99,7 @@ def test_fused_path_backward():
     sum((ref_agg[k] * ups[k]).sum() for k in keys).backward()
     gpu_in = {k: v.to(DEV).requires_grad_(k in keys) for k, v in logits.items()}
     inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
-    out = fp.pose_recover(gpu_in, inv_k, 32)
+    out = fp.pose_recover(gpu_in, inv_k, 32, seed=1234)
     assert out["quaternion"].requires_grad
     for k in keys:
         assert rel(out[k], ref_agg[k]) <= helpers.REL_TOL, k
@@ -114,7 +114,7 @@ def test_fused_path_backward():
     (out["R"].sum() + out["T"].sum()).backward()
     assert float(gpu_in["quaternion"].grad.abs().max()) > 0 and float(gpu_in["z"].grad.abs().max()) > 0
     # a second call must not disturb the first call's saved tensors
-    out2 = fp.pose_recover(gpu_in, inv_k, 32)
+    out2 = fp.pose_recover(gpu_in, inv_k, 32, seed=1234)
     assert torch.equal(out2["class_ids"], out["class_ids"])
 
 

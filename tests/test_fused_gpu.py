@@ -92,9 +92,9 @@ def test_zero_copy_pinned_host_inputs_match_device_inputs():
     logits = syn.render_heads(frames, h, w, seed=3)
     dev = torch.device("cuda:0")
     inv_k = torch.inverse(syn.camera_intrinsics()).to(dev)
-    a = pose_recover({k: v.to(dev) for k, v in logits.items()}, inv_k, HN)
+    a = pose_recover({k: v.to(dev) for k, v in logits.items()}, inv_k, HN, seed=1234)
     ta = {k: v.clone() for k, v in a.items() if k in ("xy", "quaternion", "RT", "class_ids", "win_counts")}
-    b = pose_recover({k: v.pin_memory() for k, v in logits.items()}, inv_k, HN)
+    b = pose_recover({k: v.pin_memory() for k, v in logits.items()}, inv_k, HN, seed=1234)
     for k, v in ta.items():
         assert torch.equal(v, b[k]), k
     with pytest.raises(RuntimeError, match="pinned"):
@@ -108,11 +108,11 @@ def test_pipeline_and_cuda_graph_replay_are_bit_identical():
     dev = torch.device("cuda:0")
     logits = {k: v.to(dev) for k, v in syn.render_heads(frames, h, w, seed=3).items()}
     inv_k = torch.inverse(syn.camera_intrinsics()).to(dev).contiguous()
-    eng = PoseRecoveryEngine(len(frames), h, w, 7, HN, dev)
+    eng = PoseRecoveryEngine(len(frames), h, w, 7, HN, dev, seed=1234)
     eng.launch(logits, inv_k)
     n = eng.fetch_count()
     want = eng.pose_table[:n].clone()
-    pipe = PoseRecoveryPipeline(2, len(frames), h, w, 7, HN, dev)
+    pipe = PoseRecoveryPipeline(2, len(frames), h, w, 7, HN, dev, seed=1234)
     pipe.capture(logits, inv_k)
     got = []
     for k in range(5):
@@ -125,3 +125,50 @@ def test_pipeline_and_cuda_graph_replay_are_bit_identical():
         assert cnt == n
     for e in pipe.engines:
         assert torch.equal(e.pose_table[:n].view(torch.int32), want.view(torch.int32))
+
+
+def test_results_are_owned_by_the_caller():
+    """a later pose_recover() with the same shape (same cached engine) must not overwrite R / RT / labels /
+    cat_mask of an earlier result -- the reference returns fresh tensors on every call."""
+    from fastposecnn_b200.pose_recovery import pose_recover
+    dev = torch.device("cuda:0")
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(dev)
+    frames_a, h, w = helpers.scenes()["three_frames_one_empty"]
+    frames_b = [[(64, 48, 30, 4)], [], [(20, 20, 9, 2), (100, 70, 15, 6)]]
+    la = {k: v.to(dev) for k, v in syn.render_heads(frames_a, h, w, seed=3).items()}
+    lb = {k: v.to(dev) for k, v in syn.render_heads(frames_b, h, w, seed=4).items()}
+    first = pose_recover(la, inv_k, HN, seed=1234)
+    snap = {k: v.clone() for k, v in first.items()}
+    second = pose_recover(lb, inv_k, HN, seed=1234)
+    assert second["class_ids"].shape[0] != 0 and not torch.equal(second["labels"], snap["labels"])
+    for k, v in snap.items():
+        assert torch.equal(first[k], v), f"{k} of the first result changed"
+
+
+def test_default_capacity_grows_instead_of_raising():
+    """VERDICT r01 missing #5: > max(1024, 128 b) instances through the public API (noisy early-training mask)."""
+    from fastposecnn_b200 import pose_recovery
+    from fastposecnn_b200.pose_recovery import pose_recover
+    import fastposecnn_b200 as fp
+    g = torch.Generator().manual_seed(0)
+    b, h, w = 2, 240, 320
+    logits = syn.render_heads([[], []], h, w, seed=1)
+    logits["mask"][:, 1:] += (torch.rand(b, 6, h, w, generator=g) < 0.06) * 3.0
+    cat = helpers.port.class_compression(logits, 7)
+    lab_ref, total = helpers.port.label_instances(cat["mask"] != 0)
+    assert total > 4096
+    dev = torch.device("cuda:0")
+    out = pose_recover({k: v.to(dev) for k, v in logits.items()}, torch.inverse(syn.camera_intrinsics()).to(dev), 16)
+    assert out["class_ids"].shape[0] == total
+    assert torch.equal(out["labels"].cpu(), lab_ref.to(torch.int32))
+    assert len(pose_recovery._engines) <= pose_recovery.ENGINE_CACHE_SIZE
+
+    class HP:
+        HV_NUM_OF_HYPOTHESES = 16
+    layer = fp.AggregationLayer(HP, 7)
+    lab, n = layer.batchwise_break_segmentation_mask((cat["mask"] != 0).to(dev))
+    assert n == total and torch.equal(lab.cpu(), lab_ref.to(torch.int32))
+    agg = layer({k: v.to(dev) for k, v in cat.items()})
+    assert agg["class_ids"].shape[0] == total
+    with pytest.raises(RuntimeError, match="FPC_ECAPACITY"):
+        fp.AggregationLayer(HP, 7, max_instances=64)({k: v.to(dev) for k, v in cat.items()})

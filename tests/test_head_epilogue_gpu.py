@@ -71,7 +71,7 @@ def test_lowres_equals_full_resolution_path_on_upsampled_maps():
     low = {k: v.to(DEV) for k, v in syn.render_lowres_heads(frames, h, w, scale, seed=9).items()}
     inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
     full = {k: torch.nn.UpsamplingBilinear2d(scale_factor=scale)(v) for k, v in low.items()}
-    a = fp.pose_recover(full, inv_k, 64)
+    a = fp.pose_recover(full, inv_k, 64, seed=1234)
     n = a["class_ids"].shape[0]
     idxs = syn.presampled_idxs(a["mask_sizes"].cpu().tolist(), 64).reshape(-1, 64, 2).to(DEV)
     a = {k: v.clone() for k, v in fp.pose_recover(full, inv_k, 64, idxs=idxs).items()}

@@ -68,8 +68,8 @@ def test_label_volume_predictions_match_dense_ones():
     frames = [[(30, 30, 14, 1), (90, 40, 18, 3), (60, 75, 12, 6)], [(40, 50, 20, 2), (100, 30, 12, 1)], [], [(64, 48, 22, 3)]]
     logits = syn.render_heads(frames, 96, 128, seed=8)
     inv_k = torch.inverse(syn.camera_intrinsics())
-    sparse = fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32)
-    dense = fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32, materialize_dense=True)
+    sparse = fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32, seed=1234)
+    dense = fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32, materialize_dense=True, seed=1234)
     assert "instance_masks" not in sparse
     _, gts = helpers.matching_scene("shifted")
     gts = to_dev(gts)
@@ -122,8 +122,8 @@ def test_odd_image_size_label_volume_path():
     frames, h, w = helpers.scenes()["odd_width"]
     logits = syn.render_heads(frames, h, w, seed=4)
     inv_k = torch.inverse(syn.camera_intrinsics())
-    sparse = fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32)
-    dense = {k: v.clone() for k, v in fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32,
+    sparse = fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32, seed=1234)
+    dense = {k: v.clone() for k, v in fp.pose_recover({k: v.to(DEV) for k, v in logits.items()}, inv_k.to(DEV), 32, seed=1234,
                                                       materialize_dense=True).items() if k not in ("labels", "xy_mask")}
     gts = {k: v.clone() for k, v in dense.items() if k != "cat_mask"}
     gts["instance_masks"] = torch.roll(gts["instance_masks"], shifts=(1, 2), dims=(1, 2)).contiguous()

@@ -60,8 +60,8 @@ def test_fused_head_epilogue_equals_upsampled_flow_on_network_outputs():
         low["mask"] = (low["mask"] - low["mask"].mean(dim=(2, 3), keepdim=True)) * 8
         full = {k: torch.nn.UpsamplingBilinear2d(scale_factor=4)(v) for k, v in low.items()}
     inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
-    a = {k: v.clone() for k, v in fp.pose_recover(full, inv_k, 32).items()}
-    b = fp.pose_recover(low, inv_k, 32, upsample=4)
+    a = {k: v.clone() for k, v in fp.pose_recover(full, inv_k, 32, seed=1234).items()}
+    b = fp.pose_recover(low, inv_k, 32, upsample=4, seed=1234)
     assert a["class_ids"].shape[0] >= 1
     for k in ("cat_mask", "labels", "class_ids", "sample_ids", "mask_sizes", "quaternion", "scales", "z"):
         assert torch.equal(a[k], b[k]), k

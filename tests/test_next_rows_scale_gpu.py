@@ -34,7 +34,7 @@ def test_lowres_full_batch_determinism_and_layout():
     wl = syn.WORKLOADS["cfg2"]
     low = syn.render_lowres_heads([wl.discs()] * wl.batch, wl.h, wl.w, 4, wl.num_classes, seed=0, device=DEV)
     inv_k = torch.inverse(syn.camera_intrinsics()).to(DEV)
-    a = {k: v.clone() for k, v in fp.pose_recover(low, inv_k, wl.hyps, upsample=4).items()}
+    a = {k: v.clone() for k, v in fp.pose_recover(low, inv_k, wl.hyps, upsample=4, seed=1234).items()}
     n = wl.batch * len(wl.discs())
     assert a["class_ids"].shape[0] == n
     # interpolated discs of one grid row do not all start on the same pixel row, so the raster order inside a frame may
@@ -46,7 +46,7 @@ def test_lowres_full_batch_determinism_and_layout():
     cent = torch.tensor([[d[0], d[1]] for d in wl.discs()])
     dist = torch.cdist(a["xy"].cpu(), cent).min(dim=1).values
     assert float(dist.max()) < 2.5                             # discs are drawn at 1/4 resolution: centres land within a low-res pixel
-    b = fp.pose_recover(low, inv_k, wl.hyps, upsample=4)
+    b = fp.pose_recover(low, inv_k, wl.hyps, upsample=4, seed=1234)
     for k in ("cat_mask", "labels", "class_ids", "sample_ids", "mask_sizes", "quaternion", "scales", "z", "xy", "RT"):
         assert torch.equal(a[k], b[k]), k                       # bit-identical reruns (device-side sampling is seeded)
 
