@@ -16,13 +16,14 @@ namespace fpc {
 
 // I2. record offsets and vote work items per instance (single block)
 __global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counters, long long max_records, int chunk,
-                                                       int nbatch) {
+                                                       int nbatch, int tail_div) {
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const int tn = T.tn[i];
         T.pxoff[i] = (tn + 15) & ~15;                        // ranges padded to whole 16-pixel voting rounds
-        T.workoff[i] = ((tn + chunk - 1) / chunk) * nbatch;
+        const int ipx = vote_item_px(i, N, chunk, tail_div);
+        T.workoff[i] = ((tn + ipx - 1) / ipx) * nbatch;
     }
     __syncthreads();
     const int total = block_exclusive_scan_inplace(T.pxoff, N);
@@ -265,7 +266,7 @@ int launch_rows_and_records(const Workspace &ws, const PathParams &pp, const Fie
     const int grid = sm_count() * 32;   // one warp per (instance,row) item, grid-stride: plenty of loads in flight
     int rc = launch_slots(ws, pp, st);
     if (rc != FPC_OK) return rc;
-    k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk, vote_batches(pp.hn));
+    k_scan_records<<<1, 1024, 0, st>>>(ws.T, ws.counters, pp.max_records, vote_chunk, vote_batches(pp.hn), pp.vote_tail);
     FPC_LAUNCH_CHECK("k_scan_records");
     if (gather_mode == 0)
         k_gather<0><<<grid, 256, 0, st>>>(ws.cls, ws.T, ws.R, ws.counters, pp, F, ws.rec, want_records);

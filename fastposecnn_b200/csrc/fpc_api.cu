@@ -192,7 +192,10 @@ static size_t carve(Workspace &ws, void *base, long long P, long long rows_total
     ws.rec.y = c.take<float>((size_t)max_records);
     ws.rec.nx = c.take<float>((size_t)max_records);
     ws.rec.ny = c.take<float>((size_t)max_records);
-    ws.work = c.take<int4>(((size_t)max_records / vote_chunk_for(P) + (size_t)max_instances + 1) * (size_t)vote_batches(hn));
+    const size_t nwork = ((size_t)max_records / (size_t)vote_item_px(4, 5, vote_chunk_for(P, hn), vote_tail_div()) + (size_t)max_instances + 1) * (size_t)vote_batches(hn);
+    ws.work = c.take<int4>(nwork);
+    ws.workf = c.take<float4>(nwork);
+    ws.hloc = c.take<float4>((size_t)max_instances * hn);
     if (own_hyp) ws.hyp = c.take<float2>((size_t)max_instances * hn);
     if (own_votes) ws.votes = c.take<int>((size_t)max_instances * hn);
     return (c.off + 255) & ~size_t(255);
@@ -411,7 +414,8 @@ static int setup(const fpc_recover_args *a, Workspace &ws, PathParams &pp) {
     pp.inlier_thresh = a->inlier_thresh; pp.min_num = a->min_num; pp.max_num = a->max_num;
     pp.arith = a->arith; pp.seed = a->seed; pp.idxs = a->idxs; pp.select_u = a->select_u;
     pp.refine = 1;
-    pp.vote_chunk = vote_chunk_for(P);
+    pp.vote_chunk = vote_chunk_for(P, a->hn);
+    pp.vote_tail = vote_tail_div();
     pp.up = UpParams{0, a->h, a->w, 0.f, 0.f};
     pp.extra = a->extra_out;
     return FPC_OK;

@@ -59,6 +59,7 @@ struct PathParams {
     const float *select_u;       // [b,h,w] or nullptr
     int refine;                  // 1: inlier refinement (v3); 0: winning hypothesis as is (v1)
     int vote_chunk;              // pixels per vote work item for this problem size (vote_chunk_for)
+    int vote_tail;               // divisor of the item size at the tail of the queue (vote_item_px)
     UpParams up;                 // head-epilogue fusion: head maps are low resolution, x up.s bilinear on the fly
     float *extra;                // [max_instances,2] (v4 residual variance, v5 confidence at 0.999) or nullptr
 };
@@ -79,7 +80,9 @@ struct Workspace {
     RowTables R;
     RecPlanes rec;     // 4 x [max_records]
     int4 *work;        // vote work descriptors
+    float4 *workf;     // ... and the instance-local frame of each (origin, extents)
     float2 *hyp;       // [max_instances, hn]
+    float4 *hloc;      // [max_instances, hn] hypotheses prepared for the vote kernel: (h'x, h'y, band_delta, -)
     int *votes;        // [max_instances, hn]
 };
 
@@ -88,13 +91,15 @@ struct Workspace {
 #endif
 constexpr int VOTE_CHUNK = FPC_VOTE_CHUNK;  // pixels per vote work item (upper bound: shared-memory buffers have this size)
 // Small problems (a single frame, a few instances) would give the persistent vote kernel only a handful of work items;
-// they are cut into smaller chunks so that the votes still spread over the machine: P/2048 rounded down to a power of
-// two, clamped to [128, VOTE_CHUNK].  640x480: b = 1 -> 128, b = 4 -> 512, b >= 7 -> 1024.
-inline int vote_chunk_for(long long P) {
-    int c = VOTE_CHUNK;
-    while (c > 128 && (long long)c * 2048 > P) c >>= 1;
-    return c;
+// they are cut into smaller chunks so that the votes still spread over the machine (fpc_voting.cu).
+int vote_chunk_for(long long P, int hn);
+// Pixels per work item of instance i of N.  The vote kernel's blocks pull items in instance order; with only ~5 items per
+// block a block that draws one item more than its neighbours finishes up to 20 % later, so the items at the END of the
+// queue (the last fifth of the instances) are a quarter of the size: the tail shrinks to a quarter item.
+__host__ __device__ inline int vote_item_px(int i, int N, int chunk, int tail_div) {
+    return (chunk >= 128 * tail_div && i >= N - N / 5) ? chunk / tail_div : chunk;
 }
+int vote_tail_div();   // 4 by default, FPC_VOTE_TAIL_DIV in the environment (1 = all items the same size)
 
 // fpc_aggregate.cu
 int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,

@@ -129,63 +129,12 @@ __global__ void __launch_bounds__(256) k_voting_for_hypothesis_vp(const float *_
 }
 
 // =============================================================================================
-// Hypotheses (K1) for every live instance: one thread per (instance, hypothesis)
-// =============================================================================================
-template <int ARITH>
-__global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__restrict__ counters, PathParams pp, RecPlanes rec,
-                                                    float2 *__restrict__ hyp_g, int4 *__restrict__ work, int nb) {
-    if (counters[FPC_CNT_FLAGS]) return;
-    const int N = counters[FPC_CNT_INSTANCES];
-    const int hn = pp.hn;
-    const long long total = (long long)N * hn;
-    // threads [total, total + N): work descriptors of the vote kernel (instance, first record, pixels | hypotheses << 16,
-    // first hypothesis) and the padding records of one instance each; threads [0, total): one hypothesis each
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total + N; idx += (long long)gridDim.x * blockDim.x) {
-        if (idx >= total) {
-            const int i = (int)(idx - total);
-            const int tn = T.tn[i], w0 = T.workoff[i], px = T.pxoff[i];
-            const int chunk = pp.vote_chunk;
-            const int chunks = (tn + chunk - 1) / chunk;
-            for (int k = tn; k < ((tn + 15) & ~15); ++k) {            // padding records: can never be inliers
-                const size_t o = (size_t)px + k;
-                rec.x[o] = 1e18f; rec.y[o] = 1e18f; rec.nx[o] = 0.f; rec.ny[o] = 0.f;
-            }
-            for (int c = 0; c < chunks; ++c)
-                for (int b = 0; b < nb; ++b) {
-                    const int npx = min(chunk, tn - c * chunk), nh = min(1024, hn - b * 1024);
-                    work[w0 + c * nb + b] = make_int4(i, px + c * chunk, npx | (nh << 16), b * 1024);
-                }
-            continue;
-        }
-        const int i = (int)(idx / hn), h = (int)(idx - (long long)i * hn);
-        const int tn = T.tn[i];
-        float2 hp = make_float2(0.f, 0.f);
-        if (tn > 0) {
-            int t0, t1;
-            if (pp.idxs) {
-                t0 = min(max(pp.idxs[idx * 2], 0), tn - 1);
-                t1 = min(max(pp.idxs[idx * 2 + 1], 0), tn - 1);
-            } else {
-                t0 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 0u) % (uint32_t)tn);
-                t1 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 1u) % (uint32_t)tn);
-            }
-            const size_t b0 = (size_t)T.pxoff[i] + t0, b1 = (size_t)T.pxoff[i] + t1;
-            float x, y;
-            if (hypothesis_exact<ARITH>(rec.nx[b0], rec.ny[b0], rec.x[b0], rec.y[b0], rec.nx[b1], rec.ny[b1], rec.x[b1],
-                                        rec.y[b1], x, y))
-                hp = make_float2(x, y);
-        }
-        hyp_g[idx] = hp;
-    }
-}
-
-// =============================================================================================
-// Vote counting
+// Vote counting: constants, geometry of the instance-local frame, the per-vote arithmetic
 // =============================================================================================
 // Work item = (instance, chunk of <= VOTE_CHUNK voting records, batch of <= VHB hypotheses), handed out through
 // an atomic ticket so every resident block stays busy until the work runs out.  Staging is double buffered and
 // done by the copy engine: one thread arms an mbarrier and issues five bulk copies (cp.async.bulk: the four
-// SoA record planes x, y, dir_x, dir_y of the chunk and the hypotheses of the batch) for the NEXT item while
+// SoA record planes x, y, dir_x, dir_y of the chunk and the prepared hypotheses of the batch) for the NEXT item while
 // all warps vote on the current one.  Every lane keeps VQ hypotheses in registers and walks the pixels with
 // broadcast LDS.128 loads (4 pixels per load), two pixels per packed f32x2 instruction (FFMA2).
 // No inlier matrix is ever written (the reference materialises hn*tn bytes and re-reads them,
@@ -200,26 +149,127 @@ __global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__r
 // the direction n is scaled by a power of two (exact) so that |n| <= 1, and the pixel planes (x, y) are overwritten by
 //   pu = -(c'.n),  pw = -(c' x n)        so that        U = fma(h'x, nx, fma(h'y, ny, pu)),
 //                                                        W = fma(h'x, ny, fma(-h'y, nx, pw)),   s = fma(U, -tau, |W|)
-// with tau = T(t) (middle of the reference's uncertainty interval).  sign(s) is the fast answer, collected with one
-// funnel shift per vote.  The absolute error of U and W is <= 8u (|h'x| + |h'y| + Rx + Ry) =: E (Rx, Ry = half extents of
-// the bounding box), so the answer is certain as soon as
+// with tau = T(t) (middle of the reference's uncertainty interval).  sign(s) is the fast answer, added to the count
+// with one LEA.HI per vote.  The absolute error of U and W is <= 8u (|h'x| + |h'y| + Rx + Ry) =: E (Rx, Ry = half
+// extents of the bounding box), so the answer is certain as soon as
 //   |s| >= delta(h) = 1.01 [ max(T_lo - tau, tau - T_hi) (|d|max + E) + (1 + T_lo) E ],   |d|max = |h'| + |(Rx, Ry)|,
 // T_hi = T(t (1 + eps)), T_lo = T(t (1 - eps)), eps = 1.25 (9 + 1/t) u  (derivation in DESIGN.md).  The hot loop only
-// tracks  m = min |s|  over a 16-pixel round (one 3-input FMNMX per two votes); a round with m < delta (about one
-// vote in 10^4 lands there) is re-examined by the whole warp, its uncertain votes are removed from the fast count and
-// queued in shared memory, and the queue is settled afterwards by all lanes in parallel with the reference
-// expression itself (explicitly rounded intrinsics, original operands re-read from the record planes).  Hypotheses
-// within 1e-3 of a pixel-lattice point (where |d| may fall under the reference's 1e-6 guard), non-finite or absurdly
-// far hypotheses have ALL their votes settled that way; pixels whose direction the reference's |n| < 1e-6 guard skips
-// are given pw = 1e30 (never an inlier), pixels with an absurd |n| get n = 0, pw = 0 (s = 0: always uncertain).
+// tracks  m = min |s|  per hypothesis over a 16-pixel round (one 3-input FMNMX per two votes) and leaves a one-word
+// note per (lane, round); rounds with m < delta (about one vote in 10^3 lands there) are re-examined after the
+// loop -- bit-identical s, one thread per note -- and their uncertain votes are settled by all lanes in parallel with
+// the reference expression itself (explicitly rounded intrinsics, original operands re-read from the record planes),
+// which corrects the fast count.  Hypotheses within 1e-3 of a pixel-lattice point (where |d| may fall under the
+// reference's 1e-6 guard), non-finite or absurdly far hypotheses have ALL their votes settled that way; pixels whose
+// direction the reference's |n| < 1e-6 guard skips are given pw = 1e30 (never an inlier), pixels with an absurd |n|
+// get n = 0, pw = 0 (s = 0: always uncertain).
 constexpr int VT = 256;            // threads per block
 constexpr int VQ = 4;              // hypotheses per lane
-constexpr int VHB = 1024;          // hypotheses per batch (8 groups of 32 lanes x VQ)
-constexpr int VROUND = 16;         // pixels per sign-collection round
-constexpr int VQCAP = 2048;        // deferred exact-vote queue entries
+constexpr int VHB = 512;           // hypotheses per batch (4 groups of 32 lanes x VQ)
+constexpr int VROUND = 16;         // pixels per round
+constexpr int VTRIGCAP = 1024;     // flagged (group, lane, round) notes per work item; beyond that the whole item is re-examined
+constexpr int VNOTES = 4096;       // raw notes per work item: rounds x hypothesis groups (padded to 2^k) x 32 lanes
 constexpr float V_FAR = 1e12f;     // |h'x| + |h'y| beyond this (or NaN): the hypothesis is voted exactly
 constexpr float V_NEVER = 1e30f;   // pw of a pixel that can never be an inlier
 
+struct VoteConsts {
+    float ntau;               // -tau
+    float half_w;             // max(T_lo - tau, tau - T_hi), rounded up
+    float one_plus_tlo;       // 1 + T_lo, rounded up
+    int all_exact;            // thresh outside the fast test's domain: settle every vote exactly
+    int nb;                   // hypothesis batches per (instance, chunk)
+    int debug_skip;           // FPC_VOTE_DEBUG_SKIP (timing experiments only): 1 re-examination, 2 exact list, 4 hot loop, 8 prepare
+};
+
+// Instance-local frame: origin = centre of the bounding box (integer valued), half extents bound |c'x|, |c'y|.
+struct VoteFrame {
+    float ox, oy, rsum, rdiag;
+};
+__device__ __forceinline__ VoteFrame vote_frame(const InstTables &T, int i) {
+    const int x0 = T.xmin[i], x1 = T.xmax[i], y0 = T.ymin[i], y1 = T.ymax[i];
+    VoteFrame f;
+    f.ox = (float)((x0 + x1 + 1) >> 1);
+    f.oy = (float)((y0 + y1 + 1) >> 1);
+    const float rx = 0.5f * (float)(x1 - x0) + 1.f, ry = 0.5f * (float)(y1 - y0) + 1.f;   // >= |c'x|, |c'y|
+    f.rsum = rx + ry;
+    f.rdiag = 1.0001f * sqrtf(rx * rx + ry * ry);
+    return f;
+}
+__device__ __forceinline__ bool near_lattice(float x, float y) {
+    return fabsf(x - rintf(x)) < 1e-3f && fabsf(y - rintf(y)) < 1e-3f;
+}
+// |s| >= band_delta(h') : the sign of s is certainly the reference's answer (see the comment above)
+__device__ __forceinline__ float band_delta(float hx, float hy, float rsum, float rdiag, const VoteConsts &vc) {
+    const float a = fabsf(hx) + fabsf(hy);
+    const float E = 4.8e-7f * (a + rsum);               // 8 u (|h'x| + |h'y| + Rx + Ry), rounded up
+    return 1.01f * (vc.half_w * (1.0002f * (a + rdiag) + E) + vc.one_plus_tlo * E);
+}
+
+// =============================================================================================
+// Hypotheses (K1) for every live instance: one thread per (instance, hypothesis)
+// =============================================================================================
+// Besides the hypothesis itself (absolute coordinates, the reference's value) every thread writes what the vote kernel
+// needs of it, so that no block recomputes it per work item: hloc = (h'x, h'y, band_delta, 0) in the instance-local
+// frame; band_delta = 0 marks a hypothesis that stays off the fast path (the fast loop then sees a far-away dummy).
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_hypotheses(InstTables T, const int *__restrict__ counters, PathParams pp, RecPlanes rec,
+                                                    float2 *__restrict__ hyp_g, float4 *__restrict__ hloc, int4 *__restrict__ work,
+                                                    float4 *__restrict__ workf, VoteConsts vc) {
+    if (counters[FPC_CNT_FLAGS]) return;
+    const int N = counters[FPC_CNT_INSTANCES];
+    const int hn = pp.hn, nb = vc.nb;
+    const long long total = (long long)N * hn;
+    // threads [total, total + N): work descriptors of the vote kernel (instance, first record, pixels | hypotheses << 16,
+    // first hypothesis) and the padding records of one instance each; threads [0, total): one hypothesis each
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total + N; idx += (long long)gridDim.x * blockDim.x) {
+        if (idx >= total) {
+            const int i = (int)(idx - total);
+            const int tn = T.tn[i], w0 = T.workoff[i], px = T.pxoff[i];
+            const int chunk = vote_item_px(i, N, pp.vote_chunk, pp.vote_tail);
+            const int chunks = (tn + chunk - 1) / chunk;
+            for (int k = tn; k < ((tn + 15) & ~15); ++k) {            // padding records: can never be inliers
+                const size_t o = (size_t)px + k;
+                rec.x[o] = 1e18f; rec.y[o] = 1e18f; rec.nx[o] = 0.f; rec.ny[o] = 0.f;
+            }
+            const VoteFrame f = vote_frame(T, i);
+            for (int c = 0; c < chunks; ++c)
+                for (int b = 0; b < nb; ++b) {
+                    const int npx = min(chunk, tn - c * chunk), nh = min(VHB, hn - b * VHB);
+                    work[w0 + c * nb + b] = make_int4(i, px + c * chunk, npx | (nh << 16), b * VHB);
+                    workf[w0 + c * nb + b] = make_float4(f.ox, f.oy, f.rsum, f.rdiag);
+                }
+            continue;
+        }
+        const int i = (int)(idx / hn), h = (int)(idx - (long long)i * hn);
+        const int tn = T.tn[i];
+        float2 hp = make_float2(0.f, 0.f);
+        float4 hl = make_float4(3e15f, 1e15f, 0.f, 0.f);
+        if (tn > 0) {
+            int t0, t1;
+            if (pp.idxs) {
+                t0 = min(max(pp.idxs[idx * 2], 0), tn - 1);
+                t1 = min(max(pp.idxs[idx * 2 + 1], 0), tn - 1);
+            } else {
+                t0 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 0u) % (uint32_t)tn);
+                t1 = (int)(hash3(pp.seed, (uint32_t)i, (uint32_t)h, 1u) % (uint32_t)tn);
+            }
+            const size_t b0 = (size_t)T.pxoff[i] + t0, b1 = (size_t)T.pxoff[i] + t1;
+            float x, y;
+            if (hypothesis_exact<ARITH>(rec.nx[b0], rec.ny[b0], rec.x[b0], rec.y[b0], rec.nx[b1], rec.ny[b1], rec.x[b1],
+                                        rec.y[b1], x, y))
+                hp = make_float2(x, y);
+            const VoteFrame f = vote_frame(T, i);
+            const float lx = hp.x - f.ox, ly = hp.y - f.oy;
+            if (!vc.all_exact && !near_lattice(hp.x, hp.y) && fabsf(lx) + fabsf(ly) < V_FAR)
+                hl = make_float4(lx, ly, band_delta(lx, ly, f.rsum, f.rdiag, vc), 0.f);
+        }
+        hyp_g[idx] = hp;
+        hloc[idx] = hl;
+    }
+}
+
+// =============================================================================================
+// Vote counting kernel
+// =============================================================================================
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
     u64 r;
@@ -262,36 +312,27 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, uint32_t parity) {
     } while (!ok);
 }
 
-__device__ __forceinline__ bool near_lattice(float x, float y) {
-    return fabsf(x - rintf(x)) < 1e-3f && fabsf(y - rintf(y)) < 1e-3f;
-}
-
 // After the prepare pass: pu[] = -(c'.n), pw[] = -(c' x n), nx[] / ny[] = the power-of-two scaled direction.
 struct __align__(128) VoteBuf {
     float pu[VOTE_CHUNK], pw[VOTE_CHUNK], nx[VOTE_CHUNK], ny[VOTE_CHUNK];
-    float2 hyp[VHB];
+    float4 hloc[VHB];      // (h'x, h'y, band_delta, -) of the batch, written by k_hypotheses
 };
 struct VoteItem {
     int wi, i, hb, nh, npx, src;
-    float ox, oy;          // origin of the instance-local frame (centre of the bounding box, integer valued)
-    float rsum, rdiag;     // Rx + Ry and |(Rx, Ry)| of the box half extents (bounds on |c'x| + |c'y| and |c'|)
+    VoteFrame f;
 };
 struct __align__(128) VoteSmem {
     VoteBuf buf[2];
-    unsigned queue[VQCAP];
+    unsigned notes[VNOTES];        // [round][group][lane]: sign bytes of (min |s| - band_delta) of the lane's VQ hypotheses;
+                                   // after the notes are compacted: queue of uncertain votes (fast << 31 | pixel << 16 | hypothesis)
+    unsigned trig[VTRIGCAP];       // compacted flagged notes: (q mask << 24 | group << 16 | lane << 8 | round)
     unsigned short exlist[VHB];
     u64 bar[2];
+    int4 dw[2];                    // descriptor of the item that goes into buffer b next (cp.async by thread 0, one item ahead)
+    float4 df[2];
+    int dwi[2];                    // its ticket
     VoteItem item[2];
-    int qn[2], nex[2];
-};
-
-struct VoteConsts {
-    float ntau;               // -tau
-    float half_w;             // max(T_lo - tau, tau - T_hi), rounded up
-    float one_plus_tlo;       // 1 + T_lo, rounded up
-    int all_exact;            // thresh outside the fast test's domain: settle every vote exactly
-    int nb;                   // hypothesis batches per (instance, chunk)
-    int hyp_bulk;             // hypotheses can be bulk-copied (hn even -> 16-byte aligned batches)
+    int ntrig[2], nex[2], nq[2];
 };
 
 // s of one vote, scalar twin of vote_pair below: the SAME five roundings in the same order.
@@ -300,10 +341,10 @@ __device__ __forceinline__ float vote_s(float hx, float hy, float nx, float ny, 
     const float W = __fmaf_rn(hx, ny, __fmaf_rn(-hy, nx, pw));
     return __fmaf_rn(U, ntau, fabsf(W));
 }
-// one hypothesis against two pixels (packed f32x2 lanes): appends the two sign bits to acc, folds |s| into m
+// one hypothesis against two pixels (packed f32x2 lanes): adds the two sign bits to cnt, folds |s| into m
 template <bool PACKED>
 __device__ __forceinline__ void vote_pair(float hx, float hy, float nxa, float nxb, float nya, float nyb, float pua, float pub,
-                                          float pwa, float pwb, float ntau, unsigned &acc, float &m) {
+                                          float pwa, float pwb, float ntau, unsigned &cnt, float &m) {
     float sa, sb;
     if (PACKED) {
         const u64 hx2 = pk2(hx, hx), hy2 = pk2(hy, hy), nhy2 = pk2(-hy, -hy);
@@ -317,22 +358,20 @@ __device__ __forceinline__ void vote_pair(float hx, float hy, float nxa, float n
         sa = vote_s(hx, hy, nxa, nya, pua, pwa, ntau);
         sb = vote_s(hx, hy, nxb, nyb, pub, pwb, ntau);
     }
-    acc = __funnelshift_l(__float_as_uint(sa), acc, 1);
-    acc = __funnelshift_l(__float_as_uint(sb), acc, 1);
+    cnt += __float_as_uint(sa) >> 31;      // LEA.HI: one instruction per sign
+    cnt += __float_as_uint(sb) >> 31;
     m = min3(m, fabsf(sa), fabsf(sb));
 }
-// |s| >= band_delta(h') : the sign of s is certainly the reference's answer (see the comment above)
-__device__ __forceinline__ float band_delta(float hx, float hy, float rsum, float rdiag, const VoteConsts &vc) {
-    const float a = fabsf(hx) + fabsf(hy);
-    if (!(a < V_FAR)) return 0.f;                       // voted exactly, never on the fast path
-    const float E = 4.8e-7f * (a + rsum);               // 8 u (|h'x| + |h'y| + Rx + Ry), rounded up
-    return 1.01f * (vc.half_w * (1.0002f * (a + rdiag) + E) + vc.one_plus_tlo * E);
-}
+
+#ifndef FPC_VOTE_MINB
+#define FPC_VOTE_MINB 3
+#endif
 
 template <int ARITH, bool PACKED>
-__global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ counters, PathParams pp, RecPlanes rec,
-                                                const float2 *__restrict__ hyp_g, int *__restrict__ votes,
-                                                const int4 *__restrict__ work, VoteConsts vc) {
+__global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *__restrict__ counters, PathParams pp, RecPlanes rec,
+                                                            const float2 *__restrict__ hyp_g, const float4 *__restrict__ hloc_g,
+                                                            int *__restrict__ votes, const int4 *__restrict__ work,
+                                                            const float4 *__restrict__ workf, VoteConsts vc) {
     extern __shared__ __align__(128) unsigned char vote_smem_raw[];
     VoteSmem &sm = *reinterpret_cast<VoteSmem *>(vote_smem_raw);
     if (counters[FPC_CNT_FLAGS]) return;
@@ -341,21 +380,34 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
     const int hn = pp.hn;
     const float thresh = pp.inlier_thresh;
 
-    // thread 0: if ticket `wi` is live, arm the buffer's barrier and start its bulk copies
-    auto fetch = [&](int b, int wi) {
-        VoteItem it;
-        it.wi = wi;
-        it.i = it.hb = it.nh = it.npx = it.src = 0;
-        it.ox = it.oy = it.rsum = it.rdiag = 0.f;
+    // Thread 0 feeds the pipeline and must never wait for global memory (its warp votes too, and the other seven wait
+    // for it at the next barrier): tickets are drawn three items ahead, the descriptor of item k+2 travels to shared
+    // memory by cp.async while item k is voted on, and staging item k+1 only touches shared memory.
+    auto request = [&](int slot, int wi) {      // descriptor of ticket wi -> slot (asynchronous)
+        sm.dwi[slot] = wi;
         if (wi < W) {
-            const int4 d = work[wi];
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&sm.dw[slot])), "l"(work + wi) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&sm.df[slot])), "l"(workf + wi) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto stage = [&](int b) {                   // descriptor in slot b -> arm the buffer's barrier, start its bulk copies
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        VoteItem it;
+        it.wi = sm.dwi[b];
+        it.i = it.hb = it.nh = it.npx = it.src = 0;
+        it.f.ox = it.f.oy = it.f.rsum = it.f.rdiag = 0.f;
+        if (it.wi < W) {
+            const int4 d = sm.dw[b];
+            const float4 f = sm.df[b];
             it.i = d.x;
             it.src = d.y;
             it.npx = d.z & 0xffff;
             it.nh = d.z >> 16;
             it.hb = d.w;
+            it.f.ox = f.x; it.f.oy = f.y; it.f.rsum = f.z; it.f.rdiag = f.w;
             const uint32_t pbytes = (uint32_t)((it.npx + 3) & ~3) * 4u;
-            const uint32_t hbytes = vc.hyp_bulk ? (uint32_t)it.nh * 8u : 0u;
+            const uint32_t hbytes = (uint32_t)it.nh * 16u;
             const size_t src = (size_t)d.y;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this buffer are done
             mbar_expect_tx(&sm.bar[b], 4u * pbytes + hbytes);
@@ -363,17 +415,12 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
             bulk_g2s(sm.buf[b].pw, rec.y + src, pbytes, &sm.bar[b]);
             bulk_g2s(sm.buf[b].nx, rec.nx + src, pbytes, &sm.bar[b]);
             bulk_g2s(sm.buf[b].ny, rec.ny + src, pbytes, &sm.bar[b]);
-            if (hbytes) bulk_g2s(sm.buf[b].hyp, hyp_g + (size_t)it.i * hn + it.hb, hbytes, &sm.bar[b]);
-            const int x0 = T.xmin[it.i], x1 = T.xmax[it.i], y0 = T.ymin[it.i], y1 = T.ymax[it.i];
-            it.ox = (float)((x0 + x1 + 1) >> 1);
-            it.oy = (float)((y0 + y1 + 1) >> 1);
-            const float rx = 0.5f * (float)(x1 - x0) + 1.f, ry = 0.5f * (float)(y1 - y0) + 1.f;   // >= |c'x|, |c'y|
-            it.rsum = rx + ry;
-            it.rdiag = 1.0001f * sqrtf(rx * rx + ry * ry);
+            bulk_g2s(sm.buf[b].hloc, hloc_g + (size_t)it.i * hn + it.hb, hbytes, &sm.bar[b]);
         }
         sm.item[b] = it;
-        sm.qn[b] = 0;
+        sm.ntrig[b] = 0;
         sm.nex[b] = 0;
+        sm.nq[b] = 0;
     };
 
     if (tid == 0) {
@@ -382,11 +429,14 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    int ticket_ahead = 0;   // thread 0 only: ticket of the item after the one being prefetched (hides the atomic's latency)
+    int ticket_ahead = 0;   // thread 0 only: ticket of the item two after the current one
     if (tid == 0) {
         const int t0 = atomicAdd(&counters[FPC_CNT_TICKET], 1);
+        const int t1 = atomicAdd(&counters[FPC_CNT_TICKET], 1);
         ticket_ahead = atomicAdd(&counters[FPC_CNT_TICKET], 1);
-        fetch(0, t0);
+        request(0, t0);
+        stage(0);
+        request(1, t1);
     }
     __syncthreads();
     int cur = 0;
@@ -394,8 +444,9 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
     while (true) {
         const VoteItem it = sm.item[cur];
         if (it.wi >= W) break;
-        if (tid == 0) {                        // prefetch the next item while this one is voted on
-            fetch(cur ^ 1, ticket_ahead);
+        if (tid == 0) {                        // stage the next item while this one is voted on; ask for the one after
+            stage(cur ^ 1);
+            request(cur, ticket_ahead);
             ticket_ahead = atomicAdd(&counters[FPC_CNT_TICKET], 1);
         }
         mbar_wait(&sm.bar[cur], phase[cur]);
@@ -403,75 +454,89 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
         VoteBuf &B = sm.buf[cur];
         const int i = it.i, npx = it.npx, nh = it.nh, hb = it.hb;
         const size_t gsrc = (size_t)it.src;
+        const float2 *hyp_i = hyp_g + (size_t)i * hn + hb;             // absolute hypotheses of the batch (exact paths only)
+        int *votes_i = votes + (size_t)i * hn + hb;
         const int nrounds = (npx + VROUND - 1) / VROUND;
         // ---- prepare pass: (x, y, dir) -> (pu, pw, scaled dir) in the instance-local frame ----
-        if (tid * 4 < nrounds * VROUND) {
+        if (!(vc.debug_skip & 8) && tid * 4 < nrounds * VROUND) {
             float4 cx = *reinterpret_cast<float4 *>(&B.pu[tid * 4]), cy = *reinterpret_cast<float4 *>(&B.pw[tid * 4]);
             float4 nx = *reinterpret_cast<float4 *>(&B.nx[tid * 4]), ny = *reinterpret_cast<float4 *>(&B.ny[tid * 4]);
             float *pcx = &cx.x, *pcy = &cy.x, *pnx = &nx.x, *pny = &ny.x;
+            bool rare = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float X = 0.f, Y = V_NEVER, NX = 0.f, NY = 0.f;          // padding pixel: never an inlier
-                if (tid * 4 + j < npx) {
+                // common case, branch-free: a (nearly) unit direction of a real pixel
+                const float nn = sum_prod<ARITH>(pnx[j], pnx[j], pny[j], pny[j]);
+                const bool unit = (tid * 4 + j < npx) && nn <= 1.0002f && nn >= 0.25f;
+                rare |= !unit;
+                const float ccx = pcx[j] - it.f.ox, ccy = pcy[j] - it.f.oy;
+                pcx[j] = -__fmaf_rn(ccx, pnx[j], __fmul_rn(ccy, pny[j]));
+                pcy[j] = -__fmaf_rn(ccx, pny[j], -__fmul_rn(ccy, pnx[j]));
+            }
+            if (rare) {
+                // padding, a direction the reference skips, or one that needs scaling: redo these pixels the long way
+                const float4 ox4 = *reinterpret_cast<float4 *>(&B.pu[tid * 4]), oy4 = *reinterpret_cast<float4 *>(&B.pw[tid * 4]);
+                const float ocx[4] = {ox4.x, ox4.y, ox4.z, ox4.w}, ocy[4] = {oy4.x, oy4.y, oy4.z, oy4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
                     const float nn = sum_prod<ARITH>(pnx[j], pnx[j], pny[j], pny[j]);
-                    const float nrm = __fsqrt_rn(nn);
-                    if (!(nrm > 1e-6f)) {
-                        // |n| under the reference's guard (.cu:119), or NaN: never an inlier
-                    } else if (!(nrm < 1e18f)) {
-                        Y = 0.f;                                         // absurd direction: s = 0, settled exactly
-                    } else {
-                        float sc = 1.f;
-                        if (!(nn <= 1.0002f && nn >= 0.25f)) {           // not (nearly) a unit vector: scale |n| into [0.5, 1)
-                            const int e = (int)((__float_as_uint(nrm) >> 23) & 0xffu) - 126;
-                            sc = __uint_as_float((unsigned)(127 - e) << 23);
+                    if ((tid * 4 + j < npx) && nn <= 1.0002f && nn >= 0.25f) continue;
+                    float X = 0.f, Y = V_NEVER, NX = 0.f, NY = 0.f;      // padding pixel: never an inlier
+                    if (tid * 4 + j < npx) {
+                        // the reference skips |n| = sqrt(nn) < 1e-6 (.cu:119): certain without the square root unless nn is
+                        // within 10 % of 1e-12 (sqrt(0.9e-12) < 1e-6 - 5e-8, sqrt(1.1e-12) > 1e-6 + 4e-8)
+                        bool live = nn > 1.1e-12f;
+                        if (!live && nn >= 0.9e-12f) live = !below_1e6(__fsqrt_rn(nn));
+                        if (!live) {
+                            // |n| under the reference's guard, or NaN: never an inlier
+                        } else if (!(nn < 1e36f)) {
+                            Y = 0.f;                                     // absurd direction: s = 0, settled exactly
+                        } else {
+                            // scale by a power of two so that nn lands in [0.25, 1): nn = f * 2^e2, f in [1, 2)
+                            const int e2 = (int)((__float_as_uint(nn) >> 23) & 0xffu) - 127;
+                            const int sh = (e2 + 2) >> 1;                // ceil((e2 + 1) / 2), also for e2 < 0
+                            const float sc = __uint_as_float((unsigned)(127 - sh) << 23);
+                            NX = pnx[j] * sc;
+                            NY = pny[j] * sc;
+                            const float ccx = ocx[j] - it.f.ox, ccy = ocy[j] - it.f.oy;
+                            X = -__fmaf_rn(ccx, NX, __fmul_rn(ccy, NY));
+                            Y = -__fmaf_rn(ccx, NY, -__fmul_rn(ccy, NX));
                         }
-                        NX = pnx[j] * sc;
-                        NY = pny[j] * sc;
-                        const float ccx = pcx[j] - it.ox, ccy = pcy[j] - it.oy;
-                        X = -__fmaf_rn(ccx, NX, __fmul_rn(ccy, NY));
-                        Y = -__fmaf_rn(ccx, NY, -__fmul_rn(ccy, NX));
                     }
+                    pcx[j] = X; pcy[j] = Y; pnx[j] = NX; pny[j] = NY;
                 }
-                pcx[j] = X; pcy[j] = Y; pnx[j] = NX; pny[j] = NY;
             }
             *reinterpret_cast<float4 *>(&B.pu[tid * 4]) = cx; *reinterpret_cast<float4 *>(&B.pw[tid * 4]) = cy;
             *reinterpret_cast<float4 *>(&B.nx[tid * 4]) = nx; *reinterpret_cast<float4 *>(&B.ny[tid * 4]) = ny;
         }
-        const bool item_exact = vc.all_exact;
-        const int G = (nh + 127) >> 7;  // groups of 128 hypotheses (32 lanes x VQ)
+        // hypotheses off the fast path (band_delta = 0) -> exact list; dummies behind the last hypothesis of a partial group
+        const int G = (nh + 127) >> 7;  // groups of 128 hypotheses (32 lanes x VQ), <= 4
+        const int gsh = G > 2 ? 2 : G - 1, Gp = 1 << gsh;                  // groups padded to a power of two (note index)
         for (int k = tid; k < G * 128; k += VT) {
-            float2 hp = make_float2(0.f, 0.f);
-            if (k < nh) {
-                hp = vc.hyp_bulk ? B.hyp[k] : hyp_g[(size_t)i * hn + hb + k];
-                const bool far = !(fabsf(hp.x - it.ox) + fabsf(hp.y - it.oy) < V_FAR);
-                if (item_exact || far || near_lattice(hp.x, hp.y)) sm.exlist[atomicAdd(&sm.nex[cur], 1)] = (unsigned short)k;
-            }
-            if (!vc.hyp_bulk || k >= nh) B.hyp[k] = hp;
+            if (k >= nh) B.hloc[k] = make_float4(3e15f, 1e15f, 0.f, 0.f);
+            else if (B.hloc[k].z == 0.f) sm.exlist[atomicAdd(&sm.nex[cur], 1)] = (unsigned short)k;
         }
         __syncthreads();
         // ---- fast voting: warp -> (hypothesis group g, every parts-th round) ----
-        const int parts = 8 / G;  // G <= 8 because VHB = 8 * 128
-        if (wv < G * parts) {
+        const int parts = 8 / Gp;
+        if (!(vc.debug_skip & 4) && wv < G * parts) {
             const int g = wv % G, part = wv / G;
             float hx[VQ], hy[VQ];   // instance-local hypotheses
-            int cnt[VQ];
-            bool ex[VQ];
-            float dl = 0.f;         // largest band_delta of this lane's hypotheses
+            unsigned dqi[VQ];       // bit pattern of band_delta of each (0: not on the fast path)
+            unsigned cnt[VQ];
 #pragma unroll
             for (int q = 0; q < VQ; ++q) {
-                const int idx = g * 128 + q * 32 + lane;
-                const float2 hp = B.hyp[idx];
-                hx[q] = hp.x - it.ox; hy[q] = hp.y - it.oy;
-                cnt[q] = 0;
-                ex[q] = (idx >= nh) || item_exact || near_lattice(hp.x, hp.y) || !(fabsf(hx[q]) + fabsf(hy[q]) < V_FAR);
-                if (ex[q]) { hx[q] = 3e15f; hy[q] = 1e15f; }            // not counted on the fast path; band_delta = 0
-                dl = fmaxf(dl, band_delta(hx[q], hy[q], it.rsum, it.rdiag, vc));
+                const float4 v = B.hloc[g * 128 + q * 32 + lane];
+                hx[q] = v.x; hy[q] = v.y;
+                dqi[q] = __float_as_uint(v.z);
+                cnt[q] = 0u;
             }
-            for (int rd = part; rd < nrounds; rd += parts) {
-                unsigned acc[VQ];
+            unsigned *note = &sm.notes[(part * Gp + g) * 32 + lane];
+            const int note_step = parts * Gp * 32;
+            for (int rd = part; rd < nrounds; rd += parts, note += note_step) {
+                float m[VQ];
 #pragma unroll
-                for (int q = 0; q < VQ; ++q) acc[q] = 0u;
-                float m = 3e38f;
+                for (int q = 0; q < VQ; ++q) m[q] = 3e38f;
                 const int kb = rd * VROUND;
 #pragma unroll
                 for (int j4 = 0; j4 < VROUND; j4 += 4) {
@@ -481,75 +546,103 @@ __global__ void __launch_bounds__(VT, 3) k_vote(InstTables T, int *__restrict__ 
                     const float4 ny = *reinterpret_cast<const float4 *>(&B.ny[kb + j4]);
 #pragma unroll
                     for (int q = 0; q < VQ; ++q) {
-                        vote_pair<PACKED>(hx[q], hy[q], nx.x, nx.y, ny.x, ny.y, pu.x, pu.y, pw.x, pw.y, vc.ntau, acc[q], m);
-                        vote_pair<PACKED>(hx[q], hy[q], nx.z, nx.w, ny.z, ny.w, pu.z, pu.w, pw.z, pw.w, vc.ntau, acc[q], m);
+                        vote_pair<PACKED>(hx[q], hy[q], nx.x, nx.y, ny.x, ny.y, pu.x, pu.y, pw.x, pw.y, vc.ntau, cnt[q], m[q]);
+                        vote_pair<PACKED>(hx[q], hy[q], nx.z, nx.w, ny.z, ny.w, pu.z, pu.w, pw.z, pw.w, vc.ntau, cnt[q], m[q]);
                     }
                 }
-                // pixel j of the round sits at bit 15 - j of acc[q] (set: s < 0, inlier on the fast path)
-                unsigned tm = __ballot_sync(FULL, m < dl);
-                while (tm) {
-                    // some vote of lane `src` may be uncertain: the warp recomputes its 16 pixels x VQ hypotheses
-                    // (lane -> pixel lane & 15, hypotheses 2 (lane >> 4) and 2 (lane >> 4) + 1), bit-identical s
-                    const int src = __ffs(tm) - 1;
-                    tm &= tm - 1;
-                    float bhx[VQ], bhy[VQ];
+                // byte q of the note: sign set <=> some vote of hypothesis q in this round may be uncertain (min |s| < band_delta,
+                // compared as integers: both are non-negative floats).  Stored unconditionally -- no branch, no atomic; the
+                // signs counted above stay in the count, the re-examination below corrects them.
+                unsigned t[VQ];
 #pragma unroll
-                    for (int q = 0; q < VQ; ++q) { bhx[q] = __shfl_sync(FULL, hx[q], src); bhy[q] = __shfl_sync(FULL, hy[q], src); }
-                    const int k = kb + (lane & 15);
-                    const float kpu = B.pu[k], kpw = B.pw[k], knx = B.nx[k], kny = B.ny[k];
-                    const bool up = lane >> 4;
-#pragma unroll
-                    for (int qq = 0; qq < 2; ++qq) {
-                        const float qhx = up ? bhx[2 + qq] : bhx[qq], qhy = up ? bhy[2 + qq] : bhy[qq];
-                        const float s = vote_s(qhx, qhy, knx, kny, kpu, kpw, vc.ntau);
-                        const bool band = fabsf(s) < band_delta(qhx, qhy, it.rsum, it.rdiag, vc);
-                        const unsigned bm = __ballot_sync(FULL, band);
-                        if (band) {
-                            const unsigned hidx = (unsigned)(g * 128 + ((up ? 2 : 0) + qq) * 32 + src);
-                            const int slot = atomicAdd(&sm.qn[cur], 1);
-                            if (slot < VQCAP) {
-                                sm.queue[slot] = ((unsigned)k << 16) | hidx;
-                            } else {                                       // queue full: settle it right here
-                                const float2 hp = B.hyp[hidx];
-                                if (vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh))
-                                    atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);
-                            }
-                        }
-                        if (lane == src) {                                 // uncertain votes leave the fast count
-                            acc[qq] &= ~(__brev(bm & 0xffffu) >> 16);
-                            acc[2 + qq] &= ~(__brev(bm >> 16) >> 16);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < VQ; ++q) cnt[q] += __popc(acc[q]);
+                for (int q = 0; q < VQ; ++q) t[q] = __float_as_uint(m[q]) - dqi[q];
+                *note = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x7300), 0x7610);
             }
 #pragma unroll
-            for (int q = 0; q < VQ; ++q) {
-                const int idx = g * 128 + q * 32 + lane;
-                if (!ex[q] && cnt[q]) atomicAdd(&votes[(size_t)i * hn + hb + idx], cnt[q]);
+            for (int q = 0; q < VQ; ++q)
+                if (dqi[q] && cnt[q]) atomicAdd(&votes_i[g * 128 + q * 32 + lane], (int)cnt[q]);
+        }
+        __syncthreads();
+        // ---- re-examination.  (1) compact the flagged notes (sign bit of a byte set) into sm.trig
+        const int nnotes = (vc.debug_skip & 1) ? 0 : nrounds * Gp * 32;
+        for (int e = tid; e < nnotes; e += VT) {
+            const unsigned w = sm.notes[e] & 0x80808080u;
+            const int g = (e >> 5) & (Gp - 1);
+            if (w && g < G) {
+                const unsigned qm = ((w >> 7) & 1u) | ((w >> 14) & 2u) | ((w >> 21) & 4u) | ((w >> 28) & 8u);
+                const int slot = atomicAdd(&sm.ntrig[cur], 1);
+                if (slot < VTRIGCAP) sm.trig[slot] = (qm << 24) | ((unsigned)g << 16) | ((unsigned)(e & 31) << 8) | (unsigned)(e >> (5 + gsh));
             }
         }
         __syncthreads();
-        // ---- uncertain votes: the reference expression on the original operands, one queued vote per thread ----
-        const int nq = min(sm.qn[cur], VQCAP);
-        for (int e = tid; e < nq; e += VT) {
-            const unsigned ent = sm.queue[e];
-            const int k = (int)(ent >> 16), hidx = (int)(ent & 0xffffu);
-            const float2 hp = B.hyp[hidx];
-            if (vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh))
-                atomicAdd(&votes[(size_t)i * hn + hb + hidx], 1);
+        const int ntrig = sm.ntrig[cur];
+        if (ntrig <= VTRIGCAP) {
+            // (2) one thread per note: its flagged hypotheses x the 16 pixels of the round, bit-identical s (pixel order
+            //     staggered by thread so that neighbouring threads hit different shared-memory banks); uncertain votes
+            //     (|s| < band_delta) are queued in the note table, which is free again
+            for (int e = tid; e < ntrig; e += VT) {
+                const unsigned ent = sm.trig[e];
+                unsigned qm = ent >> 24;
+                const int g = (int)((ent >> 16) & 0xffu), ln = (int)((ent >> 8) & 0xffu), kb = (int)(ent & 0xffu) * VROUND;
+                while (qm) {
+                    const int q = __ffs(qm) - 1;
+                    qm &= qm - 1;
+                    const int hidx = g * 128 + q * 32 + ln;
+                    const float4 v = B.hloc[hidx];
+                    for (int j = 0; j < VROUND; ++j) {
+                        const int k = kb + ((j + tid) & (VROUND - 1));
+                        const float s = vote_s(v.x, v.y, B.nx[k], B.ny[k], B.pu[k], B.pw[k], vc.ntau);
+                        if (fabsf(s) < v.z) {
+                            const int slot = atomicAdd(&sm.nq[cur], 1);
+                            const unsigned fast = __float_as_uint(s) >> 31;
+                            if (slot < VNOTES) {
+                                sm.notes[slot] = (fast << 31) | ((unsigned)k << 16) | (unsigned)hidx;
+                            } else {                                       // queue full: settle it right here
+                                const float2 hp = hyp_i[hidx];
+                                const int exact = vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
+                                if (exact != (int)fast) atomicAdd(&votes_i[hidx], exact - (int)fast);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // (3) the reference expression on the ORIGINAL operands decides; the fast answer is corrected
+            const int nq = min(sm.nq[cur], VNOTES);
+            for (int e = tid; e < nq; e += VT) {
+                const unsigned ent = sm.notes[e];
+                const int fast = (int)(ent >> 31), k = (int)((ent >> 16) & 0x7fffu), hidx = (int)(ent & 0xffffu);
+                const float2 hp = hyp_i[hidx];
+                const int exact = vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
+                if (exact != fast) atomicAdd(&votes_i[hidx], exact - fast);
+            }
+        } else {
+            // too many notes for the list: re-examine every (hypothesis, pixel) pair of the item
+            const int total = G * 128 * nrounds * VROUND;
+            for (int idx = tid; idx < total; idx += VT) {
+                const int hidx = idx % (G * 128), k = idx / (G * 128);
+                if (hidx >= nh || k >= npx) continue;
+                const float4 v = B.hloc[hidx];
+                if (v.z == 0.f) continue;
+                const float s = vote_s(v.x, v.y, B.nx[k], B.ny[k], B.pu[k], B.pw[k], vc.ntau);
+                if (fabsf(s) < v.z) {
+                    const int fast = (int)(__float_as_uint(s) >> 31);
+                    const float2 hp = hyp_i[hidx];
+                    const int exact = vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
+                    if (exact != fast) atomicAdd(&votes_i[hidx], exact - fast);
+                }
+            }
         }
         // ---- hypotheses on (or within 1e-3 of) the pixel lattice, far or non-finite: every vote with the reference expression ----
-        const int nex = sm.nex[cur];
+        const int nex = (vc.debug_skip & 2) ? 0 : sm.nex[cur];
         for (int e = 0; e < nex; ++e) {
             const int hidx = sm.exlist[e];
-            const float2 hp = B.hyp[hidx];
+            const float2 hp = hyp_i[hidx];
             int c = 0;
             for (int k = tid; k < npx; k += VT)
                 c += vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
             c = __reduce_add_sync(FULL, c);
-            if (lane == 0 && c) atomicAdd(&votes[(size_t)i * hn + hb + hidx], c);
+            if (lane == 0 && c) atomicAdd(&votes_i[hidx], c);
         }
         __syncthreads();   // every read of buffer `cur` is done: it may be refilled by the next prefetch
         cur ^= 1;
@@ -1007,8 +1100,8 @@ static int vote_packed() {
 static VoteConsts vote_consts(const PathParams &pp) {
     VoteConsts vc;
     vc.nb = (pp.hn + VHB - 1) / VHB;
-    vc.hyp_bulk = (pp.hn % 2 == 0) ? 1 : 0;
     vc.all_exact = 1;
+    { const char *e = getenv("FPC_VOTE_DEBUG_SKIP"); vc.debug_skip = e ? atoi(e) : 0; }
     vc.ntau = 0.f;
     vc.half_w = 0.f;
     vc.one_plus_tlo = 1.f;
@@ -1036,7 +1129,7 @@ static VoteConsts vote_consts(const PathParams &pp) {
 template <int ARITH>
 static int launch_hypotheses_t(const Workspace &ws, const PathParams &pp, float2 *hyp_out, cudaStream_t st) {
     const VoteConsts vc = vote_consts(pp);
-    k_hypotheses<ARITH><<<sm_count() * 8, 256, 0, st>>>(ws.T, ws.counters, pp, ws.rec, hyp_out, ws.work, vc.nb);
+    k_hypotheses<ARITH><<<sm_count() * 8, 256, 0, st>>>(ws.T, ws.counters, pp, ws.rec, hyp_out, ws.hloc, ws.work, ws.workf, vc);
     FPC_LAUNCH_CHECK("k_hypotheses");
     return FPC_OK;
 }
@@ -1055,7 +1148,7 @@ static int launch_vote_t(const Workspace &ws, const PathParams &pp, const float2
         blocks_per_sm = n;
     }
     const VoteConsts vc = vote_consts(pp);
-    k_vote<ARITH, PACKED><<<sm_count() * blocks_per_sm, VT, smem, st>>>(ws.T, ws.counters, pp, ws.rec, hyp, votes, ws.work, vc);
+    k_vote<ARITH, PACKED><<<sm_count() * blocks_per_sm, VT, smem, st>>>(ws.T, ws.counters, pp, ws.rec, hyp, ws.hloc, votes, ws.work, ws.workf, vc);
     FPC_LAUNCH_CHECK("k_vote");
     return FPC_OK;
 }
@@ -1072,6 +1165,37 @@ int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int 
 }
 
 int vote_batches(int hn) { return (hn + VHB - 1) / VHB; }
+
+int vote_tail_div() {
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("FPC_VOTE_TAIL_DIV");
+        v = e ? std::max(1, std::min(8, atoi(e))) : 4;
+    }
+    return v;
+}
+
+// Pixels per vote work item: P/2048 rounded down to a power of two, clamped to [128, FPC_VOTE_ITEM_PX].  The upper clamp
+// (default 512, FPC_VOTE_ITEM_PX in the environment, at most VOTE_CHUNK = the shared-memory buffer) trades per-item overhead
+// against the tail of the ticket queue: with ~5 items per resident block a block that draws one item more than its
+// neighbours finishes 20 % later.  640x480: b = 1 -> 128, b = 2 -> 256, b >= 4 -> 512.
+int vote_chunk_for(long long P, int hn) {
+    static int cap = 0;
+    if (cap == 0) {
+        const char *e = getenv("FPC_VOTE_ITEM_PX");
+        int v = e ? atoi(e) : 512;
+        int c = 128;
+        while (c * 2 <= v && c * 2 <= VOTE_CHUNK) c *= 2;
+        cap = c;
+    }
+    int c = cap;
+    while (c > 128 && (long long)c * 2048 > P) c >>= 1;
+    // the note table holds rounds x hypothesis groups (padded to 1, 2 or 4) <= 128 per item: 1024 px for hn <= 128,
+    // 512 px for hn <= 256, 256 px beyond
+    const int G = (std::min(hn, VHB) + 127) / 128, Gp = G > 2 ? 4 : G;
+    while (c > 128 && Gp * (c / VROUND) > VNOTES / 32) c >>= 1;
+    return c;
+}
 
 int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp, const int *votes, const float *inv_k,
                     float *pose_table, cudaStream_t st) {
