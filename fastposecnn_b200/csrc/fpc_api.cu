@@ -195,6 +195,9 @@ static size_t carve(Workspace &ws, void *base, long long P, long long rows_total
     const size_t nwork = ((size_t)max_records / (size_t)vote_item_px(4, 5, vote_chunk_for(P, hn), vote_tail_div()) + (size_t)max_instances + 1) * (size_t)vote_batches(hn);
     ws.work = c.take<int4>(nwork);
     ws.workf = c.take<float4>(nwork);
+    const size_t vote_blocks = (size_t)sm_count() * 4;          // upper bound of the persistent vote grid
+    ws.segs = c.take<uint4>(vote_blocks * (size_t)vote_seg_cap());
+    ws.segcnt = c.take<int>(vote_blocks);
     ws.hloc = c.take<float4>((size_t)max_instances * hn);
     if (own_hyp) ws.hyp = c.take<float2>((size_t)max_instances * hn);
     if (own_votes) ws.votes = c.take<int>((size_t)max_instances * hn);
@@ -376,13 +379,13 @@ int fpc_upsample_bilinear(const float *in, long long planes, int hl, int wl, int
     return FPC_OK;
 }
 
-int fpc_pose_recover_num_launches(void) { return 15; }
+int fpc_pose_recover_num_launches(void) { return 16; }
 
 const char *fpc_pose_recover_kernel_name(int k) {
-    static const char *names[15] = {"k_argmax_runs", "k_scan_tiles", "k_emit_runs",    "k_run_merge",  "k_run_flatten",
+    static const char *names[16] = {"k_argmax_runs", "k_scan_tiles", "k_emit_runs",    "k_run_merge",  "k_run_flatten",
                                     "k_scan_roots",  "k_run_assign", "k_run_stats",    "k_scan_slots", "k_run_slots",
-                                    "k_scan_records", "k_gather",    "k_hypotheses",   "k_vote",       "k_finalize"};
-    return (k >= 0 && k < 15) ? names[k] : "";
+                                    "k_scan_records", "k_gather",    "k_hypotheses",   "k_vote",       "k_vote_settle", "k_finalize"};
+    return (k >= 0 && k < 16) ? names[k] : "";
 }
 
 int fpc_bench_fp32_fma(float *sink, int blocks, int iters, void *stream) {

@@ -81,6 +81,8 @@ struct Workspace {
     RecPlanes rec;     // 4 x [max_records]
     int4 *work;        // vote work descriptors
     float4 *workf;     // ... and the instance-local frame of each (origin, extents)
+    uint4 *segs;       // [vote blocks, vote_seg_cap()] flagged rounds handed from k_vote to k_vote_settle: (work item, note)
+    int *segcnt;       // [vote blocks]
     float2 *hyp;       // [max_instances, hn]
     float4 *hloc;      // [max_instances, hn] hypotheses prepared for the vote kernel: (h'x, h'y, band_delta, -)
     int *votes;        // [max_instances, hn]
@@ -130,6 +132,7 @@ int launch_vote_refine_backward_labels(const int *labels, const uint8_t *cls, co
                                        int n, int K, int h, int w, int arith, float *d_xy_head, cudaStream_t st);
 void set_vote_packed(int v);
 int vote_batches(int hn);
+int vote_seg_cap();
 int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int *votes, cudaStream_t st);
 int launch_finalize(const Workspace &ws, const PathParams &pp, const float2 *hyp, const int *votes, const float *inv_k,
                     float *pose_table, cudaStream_t st);

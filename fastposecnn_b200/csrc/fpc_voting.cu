@@ -165,8 +165,9 @@ __global__ void __launch_bounds__(256) k_voting_for_hypothesis_vp(const float *_
 constexpr int VT = 256;            // threads per block
 constexpr int VQ = 4;              // hypotheses per lane
 constexpr int VHB = 512;           // hypotheses per batch (4 groups of 32 lanes x VQ)
-constexpr int VROUND = 16;         // pixels per round
-constexpr int VTRIGCAP = 1024;     // flagged (group, lane, round) notes per work item; beyond that the whole item is re-examined
+constexpr int VROUND = 16;         // pixels per round (unit of the work split between warps)
+constexpr int VHALF = VROUND;      // pixels per note (unit of the re-examination)
+constexpr int VSEGCAP = 4096;      // flagged notes one block can hand to k_vote_settle; beyond that items are re-examined in place
 constexpr int VNOTES = 4096;       // raw notes per work item: rounds x hypothesis groups (padded to 2^k) x 32 lanes
 constexpr float V_FAR = 1e12f;     // |h'x| + |h'y| beyond this (or NaN): the hypothesis is voted exactly
 constexpr float V_NEVER = 1e30f;   // pw of a pixel that can never be an inlier
@@ -323,16 +324,15 @@ struct VoteItem {
 };
 struct __align__(128) VoteSmem {
     VoteBuf buf[2];
-    unsigned notes[VNOTES];        // [round][group][lane]: sign bytes of (min |s| - band_delta) of the lane's VQ hypotheses;
-                                   // after the notes are compacted: queue of uncertain votes (fast << 31 | pixel << 16 | hypothesis)
-    unsigned trig[VTRIGCAP];       // compacted flagged notes: (q mask << 24 | group << 16 | lane << 8 | round)
+    unsigned notes[VNOTES];        // [round][group][lane]: sign bytes of (min |s| - band_delta) of the lane's VQ hypotheses
     unsigned short exlist[VHB];
     u64 bar[2];
     int4 dw[2];                    // descriptor of the item that goes into buffer b next (cp.async by thread 0, one item ahead)
     float4 df[2];
     int dwi[2];                    // its ticket
     VoteItem item[2];
-    int ntrig[2], nex[2], nq[2];
+    int nex[2];
+    int segn;                      // entries in this block's segment of the global note list
 };
 
 // s of one vote, scalar twin of vote_pair below: the SAME five roundings in the same order.
@@ -363,6 +363,48 @@ __device__ __forceinline__ void vote_pair(float hx, float hy, float nxa, float n
     m = min3(m, fabsf(sa), fabsf(sb));
 }
 
+// ---- prepare: one voting record (x, y, dir) -> (pu, pw, scaled dir) in the instance-local frame.  Used by the vote kernel
+//      (on the staged chunk) and by the settle kernel (on single records): the SAME roundings, bit-identical results.
+// Common case, branch-free: a (nearly) unit direction of a real pixel; in: cx, cy = pixel, out: cx, cy = pu, pw.
+// Returns false if the pixel needs prepare_pixel_rare (which is then given the ORIGINAL pixel coordinates).
+template <int ARITH>
+__device__ __forceinline__ bool prepare_pixel_fast(float &cx, float &cy, const float nx, const float ny, bool real, const VoteFrame &f) {
+    const float nn = sum_prod<ARITH>(nx, nx, ny, ny);
+    const float ccx = cx - f.ox, ccy = cy - f.oy;
+    cx = -__fmaf_rn(ccx, nx, __fmul_rn(ccy, ny));
+    cy = -__fmaf_rn(ccx, ny, -__fmul_rn(ccy, nx));
+    return real && nn <= 1.0002f && nn >= 0.25f;
+}
+template <int ARITH>
+__device__ __forceinline__ void prepare_pixel_rare(float ocx, float ocy, float &pu, float &pw, float &nx, float &ny, bool real,
+                                                   const VoteFrame &f) {
+    const float nn = sum_prod<ARITH>(nx, nx, ny, ny);
+    if (real && nn <= 1.0002f && nn >= 0.25f) return;         // handled by prepare_pixel_fast
+    float X = 0.f, Y = V_NEVER, NX = 0.f, NY = 0.f;           // padding pixel: never an inlier
+    if (real) {
+        // the reference skips |n| = sqrt(nn) < 1e-6 (.cu:119): certain without the square root unless nn is within 10 % of
+        // 1e-12 (sqrt(0.9e-12) < 1e-6 - 5e-8, sqrt(1.1e-12) > 1e-6 + 4e-8)
+        bool live = nn > 1.1e-12f;
+        if (!live && nn >= 0.9e-12f) live = !below_1e6(__fsqrt_rn(nn));
+        if (!live) {
+            // |n| under the reference's guard, or NaN: never an inlier
+        } else if (!(nn < 1e36f)) {
+            Y = 0.f;                                          // absurd direction: s = 0, settled exactly
+        } else {
+            // scale by a power of two so that nn lands in [0.25, 1): nn = f * 2^e2, f in [1, 2)
+            const int e2 = (int)((__float_as_uint(nn) >> 23) & 0xffu) - 127;
+            const int sh = (e2 + 2) >> 1;                     // ceil((e2 + 1) / 2), also for e2 < 0
+            const float sc = __uint_as_float((unsigned)(127 - sh) << 23);
+            NX = nx * sc;
+            NY = ny * sc;
+            const float ccx = ocx - f.ox, ccy = ocy - f.oy;
+            X = -__fmaf_rn(ccx, NX, __fmul_rn(ccy, NY));
+            Y = -__fmaf_rn(ccx, NY, -__fmul_rn(ccy, NX));
+        }
+    }
+    pu = X; pw = Y; nx = NX; ny = NY;
+}
+
 #ifndef FPC_VOTE_MINB
 #define FPC_VOTE_MINB 3
 #endif
@@ -371,7 +413,8 @@ template <int ARITH, bool PACKED>
 __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *__restrict__ counters, PathParams pp, RecPlanes rec,
                                                             const float2 *__restrict__ hyp_g, const float4 *__restrict__ hloc_g,
                                                             int *__restrict__ votes, const int4 *__restrict__ work,
-                                                            const float4 *__restrict__ workf, VoteConsts vc) {
+                                                            const float4 *__restrict__ workf, uint4 *__restrict__ segs,
+                                                            int *__restrict__ segcnt, VoteConsts vc) {
     extern __shared__ __align__(128) unsigned char vote_smem_raw[];
     VoteSmem &sm = *reinterpret_cast<VoteSmem *>(vote_smem_raw);
     if (counters[FPC_CNT_FLAGS]) return;
@@ -418,15 +461,15 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
             bulk_g2s(sm.buf[b].hloc, hloc_g + (size_t)it.i * hn + it.hb, hbytes, &sm.bar[b]);
         }
         sm.item[b] = it;
-        sm.ntrig[b] = 0;
         sm.nex[b] = 0;
-        sm.nq[b] = 0;
     };
 
+    uint4 *seg = segs + (size_t)blockIdx.x * VSEGCAP;
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.segn = 0;
     }
     __syncthreads();
     int ticket_ahead = 0;   // thread 0 only: ticket of the item two after the current one
@@ -463,48 +506,16 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
             float4 nx = *reinterpret_cast<float4 *>(&B.nx[tid * 4]), ny = *reinterpret_cast<float4 *>(&B.ny[tid * 4]);
             float *pcx = &cx.x, *pcy = &cy.x, *pnx = &nx.x, *pny = &ny.x;
             bool rare = false;
+            float ocx[4], ocy[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                // common case, branch-free: a (nearly) unit direction of a real pixel
-                const float nn = sum_prod<ARITH>(pnx[j], pnx[j], pny[j], pny[j]);
-                const bool unit = (tid * 4 + j < npx) && nn <= 1.0002f && nn >= 0.25f;
-                rare |= !unit;
-                const float ccx = pcx[j] - it.f.ox, ccy = pcy[j] - it.f.oy;
-                pcx[j] = -__fmaf_rn(ccx, pnx[j], __fmul_rn(ccy, pny[j]));
-                pcy[j] = -__fmaf_rn(ccx, pny[j], -__fmul_rn(ccy, pnx[j]));
+                ocx[j] = pcx[j]; ocy[j] = pcy[j];
+                rare |= !prepare_pixel_fast<ARITH>(pcx[j], pcy[j], pnx[j], pny[j], tid * 4 + j < npx, it.f);
             }
             if (rare) {
                 // padding, a direction the reference skips, or one that needs scaling: redo these pixels the long way
-                const float4 ox4 = *reinterpret_cast<float4 *>(&B.pu[tid * 4]), oy4 = *reinterpret_cast<float4 *>(&B.pw[tid * 4]);
-                const float ocx[4] = {ox4.x, ox4.y, ox4.z, ox4.w}, ocy[4] = {oy4.x, oy4.y, oy4.z, oy4.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float nn = sum_prod<ARITH>(pnx[j], pnx[j], pny[j], pny[j]);
-                    if ((tid * 4 + j < npx) && nn <= 1.0002f && nn >= 0.25f) continue;
-                    float X = 0.f, Y = V_NEVER, NX = 0.f, NY = 0.f;      // padding pixel: never an inlier
-                    if (tid * 4 + j < npx) {
-                        // the reference skips |n| = sqrt(nn) < 1e-6 (.cu:119): certain without the square root unless nn is
-                        // within 10 % of 1e-12 (sqrt(0.9e-12) < 1e-6 - 5e-8, sqrt(1.1e-12) > 1e-6 + 4e-8)
-                        bool live = nn > 1.1e-12f;
-                        if (!live && nn >= 0.9e-12f) live = !below_1e6(__fsqrt_rn(nn));
-                        if (!live) {
-                            // |n| under the reference's guard, or NaN: never an inlier
-                        } else if (!(nn < 1e36f)) {
-                            Y = 0.f;                                     // absurd direction: s = 0, settled exactly
-                        } else {
-                            // scale by a power of two so that nn lands in [0.25, 1): nn = f * 2^e2, f in [1, 2)
-                            const int e2 = (int)((__float_as_uint(nn) >> 23) & 0xffu) - 127;
-                            const int sh = (e2 + 2) >> 1;                // ceil((e2 + 1) / 2), also for e2 < 0
-                            const float sc = __uint_as_float((unsigned)(127 - sh) << 23);
-                            NX = pnx[j] * sc;
-                            NY = pny[j] * sc;
-                            const float ccx = ocx[j] - it.f.ox, ccy = ocy[j] - it.f.oy;
-                            X = -__fmaf_rn(ccx, NX, __fmul_rn(ccy, NY));
-                            Y = -__fmaf_rn(ccx, NY, -__fmul_rn(ccy, NX));
-                        }
-                    }
-                    pcx[j] = X; pcy[j] = Y; pnx[j] = NX; pny[j] = NY;
-                }
+                for (int j = 0; j < 4; ++j) prepare_pixel_rare<ARITH>(ocx[j], ocy[j], pcx[j], pcy[j], pnx[j], pny[j], tid * 4 + j < npx, it.f);
             }
             *reinterpret_cast<float4 *>(&B.pu[tid * 4]) = cx; *reinterpret_cast<float4 *>(&B.pw[tid * 4]) = cy;
             *reinterpret_cast<float4 *>(&B.nx[tid * 4]) = nx; *reinterpret_cast<float4 *>(&B.ny[tid * 4]) = ny;
@@ -531,13 +542,14 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
                 dqi[q] = __float_as_uint(v.z);
                 cnt[q] = 0u;
             }
+            // one note word per (lane, round): index (rd Gp + g) 32 + lane
             unsigned *note = &sm.notes[(part * Gp + g) * 32 + lane];
             const int note_step = parts * Gp * 32;
             for (int rd = part; rd < nrounds; rd += parts, note += note_step) {
+                const int kb = rd * VROUND;
                 float m[VQ];
 #pragma unroll
                 for (int q = 0; q < VQ; ++q) m[q] = 3e38f;
-                const int kb = rd * VROUND;
 #pragma unroll
                 for (int j4 = 0; j4 < VROUND; j4 += 4) {
                     const float4 pu = *reinterpret_cast<const float4 *>(&B.pu[kb + j4]);
@@ -552,7 +564,7 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
                 }
                 // byte q of the note: sign set <=> some vote of hypothesis q in this round may be uncertain (min |s| < band_delta,
                 // compared as integers: both are non-negative floats).  Stored unconditionally -- no branch, no atomic; the
-                // signs counted above stay in the count, the re-examination below corrects them.
+                // signs counted above stay in the count, k_vote_settle corrects them.
                 unsigned t[VQ];
 #pragma unroll
                 for (int q = 0; q < VQ; ++q) t[q] = __float_as_uint(m[q]) - dqi[q];
@@ -563,73 +575,38 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
                 if (dqi[q] && cnt[q]) atomicAdd(&votes_i[g * 128 + q * 32 + lane], (int)cnt[q]);
         }
         __syncthreads();
-        // ---- re-examination.  (1) compact the flagged notes (sign bit of a byte set) into sm.trig
+        // ---- flagged notes (sign bit of a byte set) -> this block's segment of the global list; k_vote_settle re-examines
+        //      them after the kernel (bit-identical s, the reference expression where |s| < band_delta) and corrects the counts
         const int nnotes = (vc.debug_skip & 1) ? 0 : nrounds * Gp * 32;
         for (int e = tid; e < nnotes; e += VT) {
             const unsigned w = sm.notes[e] & 0x80808080u;
             const int g = (e >> 5) & (Gp - 1);
             if (w && g < G) {
-                const unsigned qm = ((w >> 7) & 1u) | ((w >> 14) & 2u) | ((w >> 21) & 4u) | ((w >> 28) & 8u);
-                const int slot = atomicAdd(&sm.ntrig[cur], 1);
-                if (slot < VTRIGCAP) sm.trig[slot] = (qm << 24) | ((unsigned)g << 16) | ((unsigned)(e & 31) << 8) | (unsigned)(e >> (5 + gsh));
-            }
-        }
-        __syncthreads();
-        const int ntrig = sm.ntrig[cur];
-        if (ntrig <= VTRIGCAP) {
-            // (2) one thread per note: its flagged hypotheses x the 16 pixels of the round, bit-identical s (pixel order
-            //     staggered by thread so that neighbouring threads hit different shared-memory banks); uncertain votes
-            //     (|s| < band_delta) are queued in the note table, which is free again
-            for (int e = tid; e < ntrig; e += VT) {
-                const unsigned ent = sm.trig[e];
-                unsigned qm = ent >> 24;
-                const int g = (int)((ent >> 16) & 0xffu), ln = (int)((ent >> 8) & 0xffu), kb = (int)(ent & 0xffu) * VROUND;
-                while (qm) {
-                    const int q = __ffs(qm) - 1;
-                    qm &= qm - 1;
-                    const int hidx = g * 128 + q * 32 + ln;
-                    const float4 v = B.hloc[hidx];
-                    for (int j = 0; j < VROUND; ++j) {
-                        const int k = kb + ((j + tid) & (VROUND - 1));
-                        const float s = vote_s(v.x, v.y, B.nx[k], B.ny[k], B.pu[k], B.pw[k], vc.ntau);
-                        if (fabsf(s) < v.z) {
-                            const int slot = atomicAdd(&sm.nq[cur], 1);
-                            const unsigned fast = __float_as_uint(s) >> 31;
-                            if (slot < VNOTES) {
-                                sm.notes[slot] = (fast << 31) | ((unsigned)k << 16) | (unsigned)hidx;
-                            } else {                                       // queue full: settle it right here
+                unsigned qm = ((w >> 7) & 1u) | ((w >> 14) & 2u) | ((w >> 21) & 4u) | ((w >> 28) & 8u);
+                const int ln = e & 31, hr = e >> (5 + gsh);             // lane, round
+                const int slot = atomicAdd(&sm.segn, 1);
+                if (slot < VSEGCAP) {
+                    // self-contained entry: first record of the round, first hypothesis of the lane, frame origin, q mask | live pixels
+                    seg[slot] = make_uint4((unsigned)(gsrc + hr * VHALF), (unsigned)((size_t)i * hn + hb + g * 128 + ln),
+                                           (unsigned)it.f.ox | ((unsigned)it.f.oy << 16), qm | ((unsigned)min(VHALF, npx - hr * VHALF) << 4));
+                } else {
+                    // the segment is full: re-examine this note right here
+                    while (qm) {
+                        const int q = __ffs(qm) - 1;
+                        qm &= qm - 1;
+                        const int hidx = g * 128 + q * 32 + ln;
+                        const float4 v = B.hloc[hidx];
+                        for (int j = 0; j < VHALF; ++j) {
+                            const int k = hr * VHALF + j;
+                            const float s = vote_s(v.x, v.y, B.nx[k], B.ny[k], B.pu[k], B.pw[k], vc.ntau);
+                            if (fabsf(s) < v.z) {
+                                const int fast = (int)(__float_as_uint(s) >> 31);
                                 const float2 hp = hyp_i[hidx];
                                 const int exact = vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
-                                if (exact != (int)fast) atomicAdd(&votes_i[hidx], exact - (int)fast);
+                                if (exact != fast) atomicAdd(&votes_i[hidx], exact - fast);
                             }
                         }
                     }
-                }
-            }
-            __syncthreads();
-            // (3) the reference expression on the ORIGINAL operands decides; the fast answer is corrected
-            const int nq = min(sm.nq[cur], VNOTES);
-            for (int e = tid; e < nq; e += VT) {
-                const unsigned ent = sm.notes[e];
-                const int fast = (int)(ent >> 31), k = (int)((ent >> 16) & 0x7fffu), hidx = (int)(ent & 0xffffu);
-                const float2 hp = hyp_i[hidx];
-                const int exact = vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
-                if (exact != fast) atomicAdd(&votes_i[hidx], exact - fast);
-            }
-        } else {
-            // too many notes for the list: re-examine every (hypothesis, pixel) pair of the item
-            const int total = G * 128 * nrounds * VROUND;
-            for (int idx = tid; idx < total; idx += VT) {
-                const int hidx = idx % (G * 128), k = idx / (G * 128);
-                if (hidx >= nh || k >= npx) continue;
-                const float4 v = B.hloc[hidx];
-                if (v.z == 0.f) continue;
-                const float s = vote_s(v.x, v.y, B.nx[k], B.ny[k], B.pu[k], B.pw[k], vc.ntau);
-                if (fabsf(s) < v.z) {
-                    const int fast = (int)(__float_as_uint(s) >> 31);
-                    const float2 hp = hyp_i[hidx];
-                    const int exact = vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
-                    if (exact != fast) atomicAdd(&votes_i[hidx], exact - fast);
                 }
             }
         }
@@ -646,6 +623,50 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
         }
         __syncthreads();   // every read of buffer `cur` is done: it may be refilled by the next prefetch
         cur ^= 1;
+    }
+    if (tid == 0) segcnt[blockIdx.x] = min(sm.segn, VSEGCAP);
+}
+
+// Re-examination of the rounds the vote kernel flagged: thread = (note, pixel of its round).  The record is prepared
+// and s recomputed with the vote kernel's own functions (bit-identical); where |s| < band_delta the reference expression on
+// the original operands decides, and a fast answer that differs is corrected in the vote counts.
+constexpr int SETTLE_SPLIT = 16;
+template <int ARITH>
+__global__ void __launch_bounds__(256) k_vote_settle(const int *__restrict__ counters, PathParams pp, RecPlanes rec,
+                                                     const float2 *__restrict__ hyp_g, const float4 *__restrict__ hloc_g,
+                                                     int *__restrict__ votes, const uint4 *__restrict__ segs,
+                                                     const int *__restrict__ segcnt, int nseg, VoteConsts vc) {
+    if (counters[FPC_CNT_FLAGS]) return;
+    // every thread's iteration is a chain of dependent loads (note -> record, hypothesis): the kernel is latency-bound, so
+    // each segment is spread over SETTLE_SPLIT blocks
+    for (int job = blockIdx.x; job < nseg * SETTLE_SPLIT; job += gridDim.x) {
+        const int sgi = job / SETTLE_SPLIT, part = job - sgi * SETTLE_SPLIT;
+        const int n = min(segcnt[sgi], VSEGCAP);
+        const uint4 *seg = segs + (size_t)sgi * VSEGCAP;
+        for (int idx = part * blockDim.x + threadIdx.x; idx < n * VHALF; idx += SETTLE_SPLIT * blockDim.x) {
+            const uint4 ent = seg[idx / VHALF];
+            const int j = idx % VHALF;
+            const VoteFrame f{(float)(ent.z & 0xffffu), (float)(ent.z >> 16), 0.f, 0.f};
+            const bool real = j < (int)(ent.w >> 4);
+            unsigned qm = ent.w & 0xfu;
+            const size_t r = (size_t)ent.x + j;                    // padded ranges: always readable
+            const float x = rec.x[r], y = rec.y[r], dx = rec.nx[r], dy = rec.ny[r];
+            float pu = x, pw = y, nx = dx, ny = dy;
+            if (!prepare_pixel_fast<ARITH>(pu, pw, nx, ny, real, f)) prepare_pixel_rare<ARITH>(x, y, pu, pw, nx, ny, real, f);
+            while (qm) {
+                const int q = __ffs(qm) - 1;
+                qm &= qm - 1;
+                const size_t h = (size_t)ent.y + q * 32;
+                const float4 v = hloc_g[h];
+                const float s = vote_s(v.x, v.y, nx, ny, pu, pw, vc.ntau);
+                if (fabsf(s) < v.z) {
+                    const int fast = (int)(__float_as_uint(s) >> 31);
+                    const float2 hp = hyp_g[h];
+                    const int exact = vote_exact<ARITH>(x, y, dx, dy, hp.x, hp.y, pp.inlier_thresh) ? 1 : 0;
+                    if (exact != fast) atomicAdd(&votes[h], exact - fast);
+                }
+            }
+        }
     }
 }
 
@@ -1108,7 +1129,10 @@ static VoteConsts vote_consts(const PathParams &pp) {
     const double t = (double)pp.inlier_thresh;
     const double u = ldexp(1.0, -24);
     if (!(t > 1e-3) || !(t < 1.0)) return vc;                 // outside the fast test's domain: settle every vote exactly
-    const double eps_r = 1.25 * (9.0 + 1.0 / t) * u;          // reference's rounded cosine vs the cosine of the exact h - c
+    // reference's rounded cosine vs the cosine of the exact d = h - c, first order in u: dot (1 + 1/t) u (two products,
+    // one sum; |dx nx| + |dy ny| <= |d||n|), each norm 2u, their product u, the quotient u, and fl(h - c) turns d by at
+    // most u rad = T(t) u relative in the cosine; 2 % for the second-order terms
+    const double eps_r = 1.02 * (7.0 + 1.0 / t + sqrt(1.0 - t * t) / t) * u;
     const double c_hi = t * (1.0 + eps_r), c_lo = t * (1.0 - eps_r);
     if (!(c_hi < 1.0)) return vc;
     auto T = [](double c) { return sqrt(1.0 - c * c) / c; };
@@ -1148,8 +1172,11 @@ static int launch_vote_t(const Workspace &ws, const PathParams &pp, const float2
         blocks_per_sm = n;
     }
     const VoteConsts vc = vote_consts(pp);
-    k_vote<ARITH, PACKED><<<sm_count() * blocks_per_sm, VT, smem, st>>>(ws.T, ws.counters, pp, ws.rec, hyp, ws.hloc, votes, ws.work, ws.workf, vc);
+    k_vote<ARITH, PACKED><<<sm_count() * blocks_per_sm, VT, smem, st>>>(ws.T, ws.counters, pp, ws.rec, hyp, ws.hloc, votes, ws.work, ws.workf, ws.segs, ws.segcnt, vc);
     FPC_LAUNCH_CHECK("k_vote");
+    k_vote_settle<ARITH><<<sm_count() * blocks_per_sm * SETTLE_SPLIT, 256, 0, st>>>(ws.counters, pp, ws.rec, hyp, ws.hloc, votes, ws.segs, ws.segcnt,
+                                                          sm_count() * blocks_per_sm, vc);
+    FPC_LAUNCH_CHECK("k_vote_settle");
     return FPC_OK;
 }
 
@@ -1165,6 +1192,7 @@ int launch_vote(const Workspace &ws, const PathParams &pp, float2 *hyp_out, int 
 }
 
 int vote_batches(int hn) { return (hn + VHB - 1) / VHB; }
+int vote_seg_cap() { return VSEGCAP; }
 
 int vote_tail_div() {
     static int v = 0;
@@ -1190,7 +1218,7 @@ int vote_chunk_for(long long P, int hn) {
     }
     int c = cap;
     while (c > 128 && (long long)c * 2048 > P) c >>= 1;
-    // the note table holds rounds x hypothesis groups (padded to 1, 2 or 4) <= 128 per item: 1024 px for hn <= 128,
+    // the note table holds half rounds x hypothesis groups (padded to 1, 2 or 4) <= 128 per item: 1024 px for hn <= 128,
     // 512 px for hn <= 256, 256 px beyond
     const int G = (std::min(hn, VHB) + 127) / 128, Gp = G > 2 ? 4 : G;
     while (c > 128 && Gp * (c / VROUND) > VNOTES / 32) c >>= 1;

@@ -54,7 +54,7 @@ def test_error_codes_not_exit():
     assert L.fpc_pack_masks(None, 0, 3, 4, 4, None, None, None) == _lib.FPC_EINVAL
     assert L.fpc_mask_iou(None, None, 0, None, None, 5, 4, 4, None, None) == _lib.FPC_OK
     assert L.fpc_match_instances(None, None, None, 2, None, None, None, 2, 4, 4, None, None, None, None, None) == _lib.FPC_EINVAL
-    assert L.fpc_pose_recover_num_launches() == 15
+    assert L.fpc_pose_recover_num_launches() == 16
     assert L.fpc_pose_recover_kernel_name(13) == b"k_vote"
 
 

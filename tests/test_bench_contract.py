@@ -34,11 +34,11 @@ def test_one_gpu_line_has_the_contract_keys():
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
-    assert d["gpu_launches"] == 15 * d["steps"]
+    assert d["gpu_launches"] == 16 * d["steps"]
     k = d["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(k)
     assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(k["reasons"]))
-    assert len(d["kernel_ms"]) == 15 and d["dominant_kernel"] in d["kernel_ms"]
+    assert len(d["kernel_ms"]) == 16 and d["dominant_kernel"] in d["kernel_ms"]
 
 
 def test_reference_arm_line():

@@ -102,7 +102,7 @@ def test_zero_copy_pinned_host_inputs_match_device_inputs():
 
 
 def test_pipeline_and_cuda_graph_replay_are_bit_identical():
-    """Two batches in flight + CUDA-graph replay of the 15-kernel sequence give the eager results bit for bit."""
+    """Two batches in flight + CUDA-graph replay of the 16-kernel sequence give the eager results bit for bit."""
     from fastposecnn_b200.pose_recovery import PoseRecoveryEngine, PoseRecoveryPipeline
     frames, h, w = helpers.scenes()["wide"]
     dev = torch.device("cuda:0")
