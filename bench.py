@@ -30,9 +30,28 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "aggregation+voting frames/s @640x480 b32"
-# bytes per launch (dram read + write) measured by ncu on B200 for cfg2, 32 frames (profiles/)
-NCU_TRAFFIC_CFG2_B32 = {"k_argmax_runs": 283.2e6, "k_gather": 155.0e6, "k_vote": 36.5e6}
 UNIT = "frames/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, extracted from the committed `ncu --set full` capture of this very
+# command by tools/ncu_traffic.py: {"<workload>_b<frames per GPU>": {"<kernel>": bytes}}
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+
+
+def load_ncu_traffic(workload: str, bpg: int):
+    try:
+        with open(NCU_TRAFFIC_FILE) as f:
+            return json.load(f).get(f"{workload}_b{bpg}", {})
+    except (OSError, ValueError):
+        return {}
+
+
+# the reference's four timed stages (lib/pose_regressor.py:43-48, 563-570; tools/timer.py) and the kernels that do their work
+STAGES = {
+    "class_compression": ("k_argmax_runs",),
+    "aggregate": ("k_scan_tiles", "k_emit_runs", "k_run_merge", "k_run_flatten", "k_scan_roots", "k_run_assign", "k_run_stats",
+                  "k_scan_slots", "k_run_slots", "k_scan_records", "k_gather"),
+    "hough_voting": ("k_hypotheses", "k_vote", "k_vote_settle"),
+    "perform_RT_calculation": ("k_finalize",),
+}
 
 
 # --------------------------------------------------------------------------------------------
@@ -95,23 +114,33 @@ class ClockSampler:
 
 
 def cpu_reference_frames_per_s(wl, frames_per_step: int, steps: int, warmup: int):
-    """The oracle port (reference algorithm on CPU tensors: torch-CPU aggregation + scipy CCL + the C
-    restatement of the voting kernels) on a bounded sample of the workload, all host threads."""
+    """The reference's CPU path on a bounded sample of the workload, all host threads: the reference's OWN modules
+    (lib/gpu_tensor_funcs.py, aggregation_layer.py, hough_voting.py, ransac_voting_gpu.py, unmodified, installed under
+    baseline/_ref by __graft_entry__.build()) on CPU tensors -- torch-CPU aggregation + scipy CCL + the C restatement of
+    the two voting kernels behind the pybind module's names (kind "reference"); the oracle port if they are not installed
+    (kind "port").  Returns (frames/s, s per step, cores, OpenMP threads, kind)."""
     from fastposecnn_b200 import synthetic as syn
-    from oracle import native, port
+    from oracle import native, port, ref_import
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
     logits = syn.render_workload(wl, batch=frames_per_step, seed=0, device="cpu")
     inv_k = torch.inverse(syn.camera_intrinsics())
+    kind = "reference" if ref_import.available() else "port"
     times = []
+    import warnings
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        port.pose_recover(logits, inv_k, wl.hyps, idx_source=port.seeded_idx_source(1234))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if kind == "reference":
+                ref_import.reference_pose_recover(logits, inv_k, wl.hyps, port.seeded_idx_source(1234))
+            else:
+                port.pose_recover(logits, inv_k, wl.hyps, idx_source=port.seeded_idx_source(1234))
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     total = sum(times)
-    return frames_per_step * len(times) / total, total / len(times), ncores, native.num_threads()
+    return frames_per_step * len(times) / total, total / len(times), ncores, native.num_threads(), kind
 
 
 # --------------------------------------------------------------------------------------------
@@ -122,18 +151,20 @@ def run_reference(args):
     if rank != 0:
         return
     from fastposecnn_b200 import synthetic as syn
-    wl = syn.WORKLOADS[args.workload]
+    wl = syn.WORKLOADS.get(args.workload, syn.WORKLOADS["cfg2"])     # cfg5: the path's share, on cfg2-shaped head maps
     frames_per_step = args.ref_frames
-    fps, s_per_step, ncores, omp = cpu_reference_frames_per_s(wl, frames_per_step, args.steps, args.warmup)
+    fps, s_per_step, ncores, omp, kind = cpu_reference_frames_per_s(wl, frames_per_step, args.steps, args.warmup)
+    what = ("the reference's own lib/ modules (baseline/_ref, unmodified) on CPU tensors" if kind == "reference"
+            else "oracle/port.py on CPU tensors")
     sample = (f"{frames_per_step} frames of {wl.name} per step ({args.steps} timed steps after {args.warmup} warm-up), "
-              f"oracle/port.py on CPU tensors, torch threads={ncores}, OpenMP threads={omp}")
+              f"{what}, torch threads={ncores}, OpenMP threads={omp}")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "frames_per_step": frames_per_step, "hypotheses": wl.hyps,
                    "instances_per_frame": wl.instances_per_frame},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -160,7 +191,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = syn.WORKLOADS[args.workload]
-    bpg = args.batch_per_gpu or wl.batch
+    # frames per GPU: cfg2 32 (weak scaling); cfg3 = 256 frames image-sharded over the ranks (32 per GPU at 8; one GPU alone
+    # runs one such 32-frame shard); cfg4 = 4 frames of 1280x960; cfg1 = 1
+    default_bpg = {"cfg3": max(32, wl.batch // max(world, 8)) if world == 1 else wl.batch // world, "cfg4": 4}.get(args.workload, wl.batch)
+    bpg = args.batch_per_gpu or default_bpg
     hn = wl.hyps
     hbm_peak, peak_src = load_peaks()
 
@@ -302,10 +336,9 @@ def run_b200(args):
     bytes_agg = (4 * wl.num_classes * hw + 40 * fg + 184 * len(discs)) * bpg
     flop_vote = sum(12.0 * tn * (hn + 1) + 4.0 * tn for tn in tn_disc) * bpg
     i_arg, i_gather, i_vote = kernel_names.index("k_argmax_runs"), kernel_names.index("k_gather"), kernel_names.index("k_vote")
-    agg_ms = sum(kernel_ms[k] for k in range(nk) if k not in (i_vote,))
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this very
-    # command (profiles/r01_ncu_full_all_kernels_final.md); only meaningful for the default workload
-    ncu_traffic = NCU_TRAFFIC_CFG2_B32 if (args.workload == "cfg2" and bpg == 32) else {}
+    vote_side = {kernel_names.index(k) for k in ("k_hypotheses", "k_vote", "k_vote_settle") if k in kernel_names}
+    agg_ms = sum(kernel_ms[k] for k in range(nk) if k not in vote_side)
+    ncu_traffic = load_ncu_traffic(args.workload, bpg)
 
     def hbm(bytes_, ms, kernel=None):
         a = bytes_ / (ms * 1e-3) / 1e9
@@ -315,14 +348,17 @@ def run_b200(args):
                        algorithmic_bytes=bytes_argmax, peak_source=peak_src)
     roof_gather = dict(hbm(bytes_gather, kernel_ms[i_gather], "k_gather"), kernel="k_gather", ms=kernel_ms[i_gather],
                        algorithmic_bytes=bytes_gather, peak_source=peak_src)
-    roof_agg = dict(hbm(bytes_agg, agg_ms), kernel="all aggregation kernels (everything but k_vote)", ms=agg_ms,
+    roof_agg = dict(hbm(bytes_agg, agg_ms), kernel="all aggregation kernels (everything but the voting kernels)", ms=agg_ms,
                     algorithmic_bytes=bytes_agg, peak_source=peak_src)
     a_v = flop_vote / (kernel_ms[i_vote] * 1e-3) / 1e12
     roof_vote = {"bound": "fp32", "achieved": a_v, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": a_v / fp32_peak_tflops,
                  "traffic": ncu_traffic.get("k_vote"), "kernel": "k_vote", "ms": kernel_ms[i_vote], "algorithmic_flop": flop_vote,
                  "votes_per_s": flop_vote / 12.0 / (kernel_ms[i_vote] * 1e-3),
-                 "peak_source": "measured in this run: fpc_bench_fp32_fma (pure FFMA loop), 2 flop per FMA"}
+                 "peak_source": "measured in this run: fpc_bench_fp32_fma (pure FFMA loop), 2 flop per FMA; the voting kernel is "
+                                "bound by the FP32 pipe, not by HBM or the tensor cores (BASELINE.json north_star)"}
     dominant = max(range(nk), key=lambda k: kernel_ms[k])
+    per_kernel = {"k_argmax_runs": roof_argmax, "k_gather": roof_gather, "k_vote": roof_vote}
+    stage_ms = {st: round(sum(kernel_ms[kernel_names.index(k)] for k in ks if k in kernel_names), 5) for st, ks in STAGES.items()}
 
     # ---- end to end through the public API with HOST buffers ----
     e2e = None
@@ -408,10 +444,11 @@ def run_b200(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        fps, s_per, ncores, omp = cpu_reference_frames_per_s(wl, args.ref_frames, 3, 1)
-        cpu = {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port",
-               "sample": f"{args.ref_frames} frames of {wl.name}, 1 warm-up + 3 timed passes of oracle/port.py "
-                         f"(torch-CPU aggregation + scipy CCL + C voting kernels, OpenMP threads={omp})"}
+        fps, s_per, ncores, omp, kind = cpu_reference_frames_per_s(wl, args.ref_frames, 3, 1)
+        cpu = {"value": fps, "unit": UNIT, "cores": ncores, "kind": kind,
+               "sample": f"{args.ref_frames} frames of {wl.name}, 1 warm-up + 3 timed passes of "
+                         + ("the reference's own lib/ modules (baseline/_ref)" if kind == "reference" else "oracle/port.py")
+                         + f" (torch-CPU aggregation + scipy CCL + C voting kernels, OpenMP threads={omp})"}
 
     matching = head_epilogue = None
     if rank == 0 and world == 1 and not args.no_matching:
@@ -430,11 +467,18 @@ def run_b200(args):
                        "arith": "IEEE (un-contracted) voting arithmetic", "timed": f"{nk} kernels (one CUDA graph) + D2H read of N per step; {depth} steps in flight"
                                 + ("" if args.single_stream else ", one stream each (kernels of different batches overlap)")
                                 + (" + NCCL all-gather of pose tables" if world > 1 else "")},
-            "roofline": roof_argmax if kernel_names[dominant] != "k_gather" else roof_gather,
+            # the dominant kernel = the one with the largest share of the step (live CUDA-event times below)
+            "roofline": per_kernel.get(kernel_names[dominant], roof_vote),
+            "roofline_per_kernel": [roof_vote, roof_argmax, roof_gather],
             "roofline_fp32_voting": roof_vote,
             "roofline_gather": roof_gather,
             "roofline_aggregation_total": roof_agg,
             "dominant_kernel": kernel_names[dominant],
+            "stage_ms": stage_ms,
+            "stage_ms_note": "the reference's four timed stages (lib/pose_regressor.py:43-48) = sums of the kernels that do their "
+                             "work: " + "; ".join(f"{st} = {' + '.join(ks)}" for st, ks in STAGES.items())
+                             + " (the class selection / normalisation of class_compress runs inside k_gather, the refinement "
+                               "solve of hough_voting inside k_finalize)",
             "kernel_ms": {kernel_names[k]: round(kernel_ms[k], 5) for k in range(nk)},
             "kernel_ms_note": "per-kernel CUDA-event times from an instrumented, serial repeat of the same K steps "
                               f"({instrumented_ms_per_step:.4f} ms/step: one stream, eager launches, 16 event records per "
@@ -448,6 +492,160 @@ def run_b200(args):
             "gpu_launches": nk * args.steps,
             "clocks": clocks,
             "instances": n,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# cfg5: BASELINE.json configs[4] -- random-init encoder/decoder in torch feeding the path
+# --------------------------------------------------------------------------------------------
+def run_cfg5(args):
+    """One step = 64 frames per GPU (weak scaling): images -> encoder / 4 FPN decoders / 4 head convolutions (plain torch,
+    random init: examples/network_feed.TorchFeeder restates the SHAPE of lib/pose_regressor.py:582-743) -> low-resolution head
+    maps -> fpc_pose_recover(upsample=4) -> pose table; network and path are captured in ONE CUDA graph
+    (lib/pose_regressor.py:706-770, inference.py:84-95).  Next to it the reference flow: the heads up-sample all 67
+    channels x4 in torch, then the full-resolution path."""
+    import torch.distributed as dist
+    from examples.network_feed import TorchFeeder
+    from fastposecnn_b200 import _lib
+    from fastposecnn_b200 import synthetic as syn
+    from fastposecnn_b200.pose_recovery import PoseRecoveryEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device: the path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b, h, w, C, hn = args.batch_per_gpu or 64, 480, 640, 7, 128
+    torch.manual_seed(1234 + rank)
+    net = TorchFeeder(C).to(dev).eval()
+    host_imgs = torch.randn(b, 3, h, w).pin_memory()
+    imgs = torch.empty((b, 3, h, w), device=dev)
+    imgs.copy_(host_imgs)
+    inv_k = torch.inverse(syn.camera_intrinsics()).to(dev).contiguous()
+
+    def make_engine(upsample, caps):
+        return PoseRecoveryEngine(b, h, w, C, hn, dev, upsample=upsample, seed=1234, **caps)
+
+    def settle_capacity(upsample, feed):
+        """Random-init heads give thousands of speckle instances: grow the tables until one batch fits."""
+        caps = {"max_instances": 16384}
+        for _ in range(6):
+            eng = make_engine(upsample, caps)
+            with torch.no_grad():
+                eng.launch(feed(imgs), inv_k)
+            try:
+                return eng, eng.fetch_count()
+            except _lib.CapacityError as e:
+                mi, mr, mrec = e.grown(eng.max_instances, eng.max_rows, eng.max_records, b * h * w, h)
+                caps = {"max_instances": mi, "max_rows": mr, "max_records": mrec}
+                del eng
+        raise RuntimeError("cfg5: capacity did not settle")
+
+    results = {}
+    with torch.no_grad():
+        for name, upsample, feed in (("fused", 4, net.lowres), ("reference_flow", 1, net.forward)):
+            eng, n_inst = settle_capacity(upsample, feed)
+            # eager, instrumented: network vs path
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            tn = tp = 0.0
+            reps = max(3, min(args.steps, 5))
+            for it in range(reps + 2):
+                ev[0].record()
+                logits = feed(imgs)
+                ev[1].record()
+                eng.launch(logits, inv_k)
+                eng.enqueue_fetch()
+                ev[2].record()
+                eng.wait_count()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    tn += ev[0].elapsed_time(ev[1])
+                    tp += ev[1].elapsed_time(ev[2])
+            results[name] = {"network_ms": tn / reps, "path_ms": tp / reps, "instances": n_inst,
+                             "frames_per_s_eager": b / ((tn + tp) / reps * 1e-3)}
+            if name == "reference_flow":
+                del eng
+                continue
+            # one CUDA graph: H2D of the images, network, path
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    imgs.copy_(host_imgs, non_blocking=True)
+                    eng.launch(net.lowres(imgs), inv_k)
+                graph_dev = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_dev, stream=side):
+                    eng.launch(net.lowres(imgs), inv_k)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            table_host = torch.empty((eng.max_instances, _lib.POSE_ROW), dtype=torch.float32).pin_memory()
+            gathered = torch.empty((world,) + tuple(eng.table_full.shape), dtype=torch.float32, device=dev) if world > 1 else None
+
+            def step(g, read_table):
+                g.replay()
+                if gathered is not None:
+                    dist.all_gather_into_tensor(gathered.view(-1), eng.table_full.view(-1))
+                n = eng.fetch_count()
+                if read_table:
+                    table_host[:n].copy_(eng.pose_table[:n], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                return n
+            sampler = ClockSampler(local_rank)
+            timed = {}
+            for key, g, read_table in (("resident", graph_dev, False), ("e2e", graph, True)):
+                for _ in range(max(args.warmup, 3)):
+                    step(g, read_table)
+                if rank == 0 and key == "resident":
+                    sampler.start()
+                    time.sleep(0.3)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(args.steps):
+                    n_last = step(g, read_table)
+                t1.record()
+                torch.cuda.synchronize()
+                ms = t0.elapsed_time(t1)
+                if world > 1:
+                    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                timed[key] = ms / args.steps
+            clocks = sampler.stop() if rank == 0 else None
+            results[name].update({"graph_ms_per_step": timed["resident"], "e2e_ms_per_step": timed["e2e"], "instances": n_last,
+                                  "d2h": n_last * _lib.POSE_ROW * 4 + _lib.NUM_COUNTERS * 4})
+    if rank == 0:
+        fused = results["fused"]
+        line = {
+            "metric": "end-to-end inference frames/s @640x480 b64 (torch encoder/decoder + pose recovery)", "unit": UNIT,
+            "value": world * b / (fused["graph_ms_per_step"] * 1e-3), "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": fused["graph_ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg5_b64_640x480_resnet18fpn_random_init_hn128", "frames_per_gpu": b, "global_batch": world * b,
+                       "hypotheses": hn, "parallelism": f"image-sharded x{world}",
+                       "network": "torchvision ResNet-18 + 4 FPN decoders + 4 1x1 heads, random init, fp32 (cuDNN; out of scope, it only "
+                                  "feeds the path)",
+                       "l2": "every step streams 236 MB of images and ~1 GB of activations: far larger than the 126 MB L2",
+                       "timed": "one CUDA graph per step (network + 16 path kernels) + D2H read of N"
+                                + (" + NCCL all-gather of pose tables" if world > 1 else "")},
+            "roofline": None,
+            "cfg5": results,
+            "e2e": {"value": world * b / (fused["e2e_ms_per_step"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": host_imgs.numel() * 4,
+                    "d2h_bytes_per_step": fused["d2h"], "ms_per_step": fused["e2e_ms_per_step"],
+                    "note": "pinned host images -> H2D copy (inside the graph) -> network -> path -> D2H of N and the pose table"},
+            "cpu_baseline": None,
+            "gpu_launches": 16 * args.steps,
+            "clocks": clocks,
+            "instances": fused["instances"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -696,8 +894,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
-    ap.add_argument("--batch-per-gpu", type=int, default=0, help="frames per GPU (default: the workload's batch, 32 for cfg2)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[0..4]; cfg5 = random-init encoder/decoder in torch feeding the path (b=64)")
+    ap.add_argument("--batch-per-gpu", type=int, default=0, help="frames per GPU (default: 32 for cfg2/cfg3, 4 for cfg4, 64 for cfg5)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference pass (bounded sample)")
     ap.add_argument("--pipeline-depth", type=int, default=4, help="batches in flight (1 = wait for N after every step)")
     ap.add_argument("--single-stream", action="store_true", help="all pipeline slots on one stream (no cross-batch overlap)")
@@ -715,6 +914,8 @@ def main():
             raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cfg5(args)
     else:
         run_b200(args)
 

@@ -55,6 +55,7 @@ class RecoverArgs(ctypes.Structure):
         ("stage_events", ctypes.POINTER(_vp)), ("num_stage_events", ctypes.c_int32),
         ("upsample", ctypes.c_int32),
         ("extra_out", _vp),
+        ("stage_stamps", _vp),
     ]
 
 

@@ -15,7 +15,7 @@
 namespace fpc {
 
 // I2. record offsets and vote work items per instance (single block)
-__global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counters, long long max_records, int chunk,
+__global__ void __launch_bounds__(1024, 3) k_scan_records(InstTables T, int *counters, long long max_records, int chunk,
                                                        int nbatch, int tail_div) {
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];

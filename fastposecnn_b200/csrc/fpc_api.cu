@@ -25,8 +25,14 @@ struct StageRec {
     void **ev = nullptr;
     int n = 0, idx = 0;
     cudaStream_t st = nullptr;
+    unsigned long long *stamps = nullptr;
 };
 static thread_local StageRec g_stage;
+__global__ void k_stamp(unsigned long long *slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
 void stage_begin(void **events, int n, cudaStream_t st) {
     g_stage.ev = events;
     g_stage.n = events ? n : 0;
@@ -34,11 +40,13 @@ void stage_begin(void **events, int n, cudaStream_t st) {
     g_stage.st = st;
     stage_mark();
 }
+void stage_stamps(unsigned long long *stamps) { g_stage.stamps = stamps; }
 void stage_mark() {
     if (g_stage.idx < g_stage.n) {
         void *e = g_stage.ev[g_stage.idx];
         if (e) cudaEventRecord((cudaEvent_t)e, g_stage.st);
     }
+    if (g_stage.stamps) k_stamp<<<1, 1, 0, g_stage.st>>>(g_stage.stamps + g_stage.idx);
     ++g_stage.idx;
 }
 void stage_end() { g_stage = StageRec(); }
@@ -499,6 +507,7 @@ int fpc_pose_recover(const fpc_recover_args *a) {
     rc = setup_upsample(a, pp);
     if (rc != FPC_OK) return rc;
     cudaStream_t st = (cudaStream_t)a->stream;
+    stage_stamps(a->stage_stamps);
     stage_begin(a->stage_events, a->num_stage_events, st);
     rc = launch_label_and_tables(ws, pp, a->mask_logits, nullptr, st);
     FieldSrc F{a->quaternion, a->scales, a->xy, a->z, 0, 0, 0, 0, 1};

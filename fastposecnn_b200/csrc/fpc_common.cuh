@@ -24,6 +24,7 @@ int fail(int code, const char *fmt, ...);
 // Optional per-kernel timing: the caller may hand fpc_pose_recover an array of cudaEvent_t; event 0 is
 // recorded before the first kernel and event k after the k-th launch (thread-local cursor).
 void stage_begin(void **events, int n, cudaStream_t st);
+void stage_stamps(unsigned long long *stamps);   // call before stage_begin: device slots for %globaltimer stamps (graph-capturable)
 void stage_mark();
 void stage_end();
 

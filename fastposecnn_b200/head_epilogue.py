@@ -38,10 +38,11 @@ def upsample_bilinear(x: torch.Tensor, scale: int) -> torch.Tensor:
 
 def split_xyz(xyz_logits: torch.Tensor) -> Dict[str, torch.Tensor]:
     """lib/pose_regressor.py:729-732: channels (3k, 3k+1) of class k are its xy direction, channel 3k+2 its z."""
-    c = xyz_logits.shape[1]
-    xy_index = [i for i in range(c) if i % 3 != 2]
-    z_index = [i for i in range(c) if i % 3 == 2]
-    return {"xy": xyz_logits[:, xy_index].contiguous(), "z": xyz_logits[:, z_index].contiguous()}
+    b, c, h, w = xyz_logits.shape
+    if c % 3:
+        raise RuntimeError("split_xyz: the translation head has 3 channels per class")
+    v = xyz_logits.reshape(b, c // 3, 3, h, w)          # no index tensors: capturable in a CUDA graph
+    return {"xy": v[:, :, :2].reshape(b, 2 * (c // 3), h, w).contiguous(), "z": v[:, :, 2].contiguous()}
 
 
 def _conv_of(head) -> torch.nn.Module:

@@ -75,8 +75,9 @@ class PoseRecoveryEngine:
         return a
 
     def launch(self, logits: Dict[str, torch.Tensor], inv_intrinsics: torch.Tensor, idxs: Optional[torch.Tensor] = None,
-               select_u: Optional[torch.Tensor] = None, stage_events=None) -> None:
-        """Enqueues the 15 kernels on the current stream.  No synchronisation."""
+               select_u: Optional[torch.Tensor] = None, stage_events=None, stage_stamps: Optional[torch.Tensor] = None) -> None:
+        """Enqueues the kernels on the current stream.  No synchronisation.  ``stage_stamps``: optional int64 device tensor
+        ``[num_launches + 1]`` that receives %globaltimer before / after every kernel (graph-capturable timeline)."""
         b, C, K = self.b, self.num_classes, self.num_classes - 1
         h, w = self.h // self.upsample, self.w // self.upsample      # resolution of the head maps handed in
         f32 = torch.float32
@@ -124,6 +125,10 @@ class PoseRecoveryEngine:
             a.extra_out = self.extra_out.data_ptr()
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
         a.stream = _lib.current_stream(self.device)
+        if stage_stamps is not None:
+            if stage_stamps.dtype != torch.int64 or stage_stamps.numel() < self.num_launches + 1 or not stage_stamps.is_cuda:
+                raise RuntimeError("stage_stamps must be a CUDA int64 tensor of num_launches + 1 elements")
+            a.stage_stamps = stage_stamps.data_ptr()
         if stage_events is not None:
             # torch creates the cudaEvent_t lazily on the first record(); callers pass recorded events
             arr = (ctypes.c_void_p * len(stage_events))(*[int(e.cuda_event) for e in stage_events])
@@ -133,9 +138,11 @@ class PoseRecoveryEngine:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().fpc_pose_recover(ctypes.byref(a)))
 
-    def capture(self, logits, inv_intrinsics, idxs=None, select_u=None) -> None:
+    def capture(self, logits, inv_intrinsics, idxs=None, select_u=None, stage_stamps=None) -> None:
         """Captures the launch sequence for these (fixed-address) inputs into a CUDA graph; ``replay()`` then
-        re-issues all kernels with one driver call.  The inputs' storage must stay alive and in place."""
+        re-issues all kernels with one driver call.  The inputs' storage must stay alive and in place.
+        ``stage_stamps`` (int64 device tensor, one more element than kernels): %globaltimer stamps between the kernels, re-written
+        by every replay (tools/timeline.py; CUDA events recorded inside a graph cannot be used for timing)."""
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -143,7 +150,8 @@ class PoseRecoveryEngine:
             side.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                self.launch(logits, inv_intrinsics, idxs=self._idxs_keepalive if idxs is not None else None, select_u=select_u)
+                self.launch(logits, inv_intrinsics, idxs=self._idxs_keepalive if idxs is not None else None, select_u=select_u,
+                            stage_stamps=stage_stamps)
         torch.cuda.current_stream(self.device).wait_stream(side)
         self._graph = graph
         self._graph_inputs = (logits, inv_intrinsics, idxs, select_u)

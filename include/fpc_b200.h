@@ -192,6 +192,10 @@ typedef struct fpc_recover_args {
      * PVNet v5 :855-857; norm of the mean quaternion before its normalisation, needed by the backward of the aggregation;
      * 0).  One extra pass over the instance's records. */
     float *extra_out;
+    /* Optional device timeline (fpc_pose_recover only): [fpc_pose_recover_num_launches() + 1] uint64 in device memory.  A
+     * one-thread kernel writes %globaltimer (ns) into slot 0 before the first kernel and into slot k after the k-th: unlike
+     * CUDA events these stamps can be captured in a CUDA graph (tools/timeline.py).  Adds one tiny launch per kernel. */
+    unsigned long long *stage_stamps;
 } fpc_recover_args;
 
 /* sizeof(fpc_recover_args) as this library was compiled: lets a binding check its own struct definition. */

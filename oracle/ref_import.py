@@ -29,11 +29,30 @@ import torch
 
 from . import native
 
-REFERENCE_LIB = "/root/reference/source_code/FastPoseCNN/lib"
+_SRC_LIB = "/root/reference/source_code/FastPoseCNN/lib"
+# On the GPU box there is no /root/reference: `__graft_entry__.build()` installs the reference's own, unmodified Python
+# modules of this path under the git-ignored baseline/_ref/ (which travels with the gpurun snapshot), so that the reference
+# arm of bench.py runs the reference's code there too.
+_INSTALLED_LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "FastPoseCNN", "lib")
+REFERENCE_LIB = _SRC_LIB if os.path.isdir(_SRC_LIB) else _INSTALLED_LIB
+MODULES = ("gpu_tensor_funcs.py", "aggregation_layer.py", "hough_voting.py", "matching.py", "metrics.py", "type_hinting.py",
+           os.path.join("ransac_voting_gpu_layer", "ransac_voting_gpu.py"))
 
 
 def available() -> bool:
-    return os.path.isdir(REFERENCE_LIB)
+    return os.path.isfile(os.path.join(REFERENCE_LIB, "aggregation_layer.py"))
+
+
+def install(dst_lib: str = _INSTALLED_LIB) -> bool:
+    """Copies the reference modules the path needs, byte for byte, into baseline/_ref (build container only)."""
+    import shutil
+    if not os.path.isdir(_SRC_LIB):
+        return False
+    for rel in MODULES:
+        dst = os.path.join(dst_lib, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(_SRC_LIB, rel), dst)
+    return True
 
 
 _loaded = None

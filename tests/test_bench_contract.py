@@ -1,4 +1,4 @@
-"""CPU: the committed bench lines (profiles/r01_bench_*.json, produced by bench.py on a B200) carry every key of the
+"""CPU: the committed bench lines (profiles/rNN_bench_*.json, produced by bench.py on a B200) carry every key of the
 bench contract, and bench.py's static pieces (argument parser, metric / unit) match BASELINE.json."""
 import json
 import os
@@ -13,43 +13,45 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def load(name):
-    path = os.path.join(ROOT, "profiles", name)
-    if not os.path.exists(path):
-        pytest.skip(f"{name} not committed yet")
-    return json.load(open(path))
+    """The newest committed round's file of that name (profiles/r02_... before profiles/r01_...)."""
+    for rnd in ("r02", "r01"):
+        path = os.path.join(ROOT, "profiles", f"{rnd}_{name}")
+        if os.path.exists(path):
+            return json.load(open(path))
+    pytest.skip(f"{name} not committed yet")
 
 
 def test_one_gpu_line_has_the_contract_keys():
-    d = load("r01_bench_1gpu.json")
+    d = load("bench_1gpu.json")
     assert BASE_KEYS <= set(d)
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert d["unit"] == "frames/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["data"] == "synthetic"
     assert d["metric"].split()[0] in base["metric"] or "frames/s" in base["metric"]
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and "workload" in d["config"] and "model" not in d["config"]
     r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor")
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor", "fp32")
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
     c = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference") and c["value"] > 0
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
-    assert d["gpu_launches"] == 16 * d["steps"]
+    assert d["gpu_launches"] == len(d["kernel_ms"]) * d["steps"]
     k = d["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(k)
     assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(k["reasons"]))
-    assert len(d["kernel_ms"]) == 16 and d["dominant_kernel"] in d["kernel_ms"]
+    assert len(d["kernel_ms"]) in (15, 16) and d["dominant_kernel"] in d["kernel_ms"]
 
 
 def test_reference_arm_line():
-    d = load("r01_bench_reference_arm.json")
+    d = load("bench_reference_arm.json")
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["value"] == d["value"] and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
 def test_eight_gpu_line_scales():
-    one, eight = load("r01_bench_1gpu.json"), load("r01_bench_8gpu.json")
+    one, eight = load("bench_1gpu.json"), load("bench_8gpu.json")
     assert eight["n_gpus"] == 8 and eight["config"]["global_batch"] == 8 * one["config"]["global_batch"]
     assert eight["value"] > 5 * one["value"]
 
