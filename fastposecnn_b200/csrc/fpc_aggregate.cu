@@ -11,11 +11,12 @@
 #include "fpc_internal.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace fpc {
 
 // I2. record offsets and vote work items per instance (single block)
-__global__ void __launch_bounds__(1024, 3) k_scan_records(InstTables T, int *counters, long long max_records, int chunk,
+__global__ void __launch_bounds__(1024) k_scan_records(InstTables T, int *counters, long long max_records, int chunk,
                                                        int nbatch, int tail_div) {
     if (counters[FPC_CNT_FLAGS]) return;
     const int N = counters[FPC_CNT_INSTANCES];
@@ -68,6 +69,14 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
         const int rec0 = (want_rec && votes) ? T.pxoff[i] + d.w : 0;
         LerpCoord LY{0, 0, 0.f, 0.f};
         if (MODE == 3) LY = lerp_coord(y, pp.up.sy, pp.up.hl);
+        // MODE 0: bases of the run's first pixel in the four head maps (class 1, channel 0)
+        const float *qrow = nullptr, *srow = nullptr, *vrow = nullptr, *zrow = nullptr;
+        if (MODE == 0) {
+            qrow = F.quaternion + (size_t)img * 4 * K * hw + pix0;
+            srow = F.scales + (size_t)img * 3 * K * hw + pix0;
+            vrow = F.xy + (size_t)img * 2 * K * hw + pix0;
+            zrow = F.z + (size_t)img * K * hw + pix0;
+        }
         int running = 0, cmin = INT_MAX;
         float acc[8];
 #pragma unroll
@@ -140,13 +149,13 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
                     const int cp = MODE == 3 ? lr_cp : (int)cls[p];
                     cmin = min(cmin, cp);
                     if (MODE == 0) {
-                        const size_t koff = (size_t)(cp - 1) * hw;            // predicted class of THIS pixel (class_compress is per pixel)
-                        const float *q = F.quaternion + (size_t)img * 4 * K * hw + 4 * koff + pix;
-                        const float *s = F.scales + (size_t)img * 3 * K * hw + 3 * koff + pix;
-                        const float *v = F.xy + (size_t)img * 2 * K * hw + 2 * koff + pix;
+                        // predicted class of THIS pixel (class_compress is per pixel); 32-bit offsets from per-run bases
+                        const unsigned o = (unsigned)(cp - 1) * (unsigned)pp.hw;
+                        const float *q = qrow + (4u * o + (unsigned)kx), *s = srow + (3u * o + (unsigned)kx);
+                        const float *v = vrow + (2u * o + (unsigned)kx);
                         q0 = __ldcs(q); q1 = __ldcs(q + hw); q2 = __ldcs(q + 2 * hw); q3 = __ldcs(q + 3 * hw);
                         s0 = __ldcs(s); s1 = __ldcs(s + hw); s2 = __ldcs(s + 2 * hw);
-                        zz = __ldcs(F.z + (size_t)img * K * hw + koff + pix);
+                        zz = __ldcs(zrow + (o + (unsigned)kx));
                         vx = __ldcs(v); vy = __ldcs(v + hw);
                     } else {
                         q0 = lr[0]; q1 = lr[1]; q2 = lr[2]; q3 = lr[3];
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
         }
     }
 }
+
 
 
 // Dense reference-layout outputs of AggregationLayer.forward (aggregation_layer.py:101-105,152-153):

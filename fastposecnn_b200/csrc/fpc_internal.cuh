@@ -30,7 +30,8 @@ struct RunTables {
 constexpr int ROW_CONTIG = 1 << 30;   // the slot's members are one contiguous run: no label test needed
 constexpr int ROW_SUB = 1 << 29;      // instance larger than max_num: Bernoulli sub-sampling of the voters
 constexpr int ROW_VOTES = 1 << 28;    // instance has at least min_num pixels
-constexpr int ROW_LEN_MASK = (1 << 28) - 1;
+constexpr int ROW_LEN_MASK = (1 << 20) - 1;  // run length (<= image width < 65536)
+constexpr int ROW_CLS_SHIFT = 20;            // bits 20..27: class of the run's FIRST pixel (k_gather_p prefetches its channels)
 
 // Per-(instance,run) slot tables, instance-major, raster order inside an instance.
 struct RowTables {

@@ -69,103 +69,33 @@ __global__ void __launch_bounds__(256) k_argmax_runs_v4(const float *__restrict_
 }
 
 
-// Persistent, copy-engine fed variant of k_argmax_runs_v4 (hw % 1024 == 0, 16-byte aligned logits).  The short-lived blocks of
-// the plain kernel need ~8 resident blocks per SM to keep HBM busy (measured: 56 us at 8 blocks/SM, 88 us at 3, 118 us at 2),
-// so they cannot share an SM with the register-heavy vote kernel of another batch.  Here ONE block per SM keeps
-// ARGMAX_STAGES x C x 4 KB of bulk copies (cp.async.bulk + mbarrier, the TMA path) in flight in shared memory -- the bytes in
-// flight no longer depend on how many threads are resident or how often they get an issue slot -- and 256 threads pick
-// the arg-max out of shared memory.  Same outputs as k_argmax_runs_v4: class map, run starts per 1024-pixel tile.
-constexpr int ARGMAX_STAGES = 3;
-__device__ __forceinline__ uint32_t rs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(256) k_argmax_runs_tma(const float *__restrict__ mask, uint8_t *__restrict__ cls,
-                                                         int *__restrict__ tile_runs, int C, int hw, int w, int ntiles) {
-    extern __shared__ __align__(128) unsigned char argmax_smem[];
-    float *stage = reinterpret_cast<float *>(argmax_smem);                                // [STAGES][C][1024]
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(argmax_smem + (size_t)ARGMAX_STAGES * C * TILE * 4);
-    __shared__ int s_n;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t tile_bytes = (uint32_t)C * TILE * 4u;
-    auto issue = [&](int k) {                      // thread 0: tile blockIdx.x + k * gridDim.x -> stage k % STAGES
-        const int tile = blockIdx.x + k * gridDim.x;
-        if (tile >= ntiles) return;
-        const int sidx = k % ARGMAX_STAGES;
-        const long long p = (long long)tile * TILE;
-        const int bi = (int)(p / hw), pix = (int)(p - (long long)bi * hw);
-        const float *src = mask + (size_t)bi * C * hw + pix;
-        const uint32_t b = rs_smem_u32(&bar[sidx]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(tile_bytes) : "memory");
-        for (int c = 0; c < C; ++c)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             rs_smem_u32(stage + ((size_t)sidx * C + c) * TILE)),
-                         "l"(src + (size_t)c * hw), "r"((uint32_t)TILE * 4u), "r"(b)
-                         : "memory");
-    };
-    if (tid == 0) {
-        for (int k = 0; k < ARGMAX_STAGES; ++k)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rs_smem_u32(&bar[k])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int k = 0; k < ARGMAX_STAGES; ++k) issue(k);
-    }
-    __syncthreads();
-    for (int k = 0, tile = blockIdx.x; tile < ntiles; ++k, tile += gridDim.x) {
-        const int sidx = k % ARGMAX_STAGES;
-        const uint32_t parity = (uint32_t)(k / ARGMAX_STAGES) & 1u, b = rs_smem_u32(&bar[sidx]);
-        uint32_t ok;
-        do {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(ok) : "r"(b), "r"(parity) : "memory");
-        } while (!ok);
-        const float *src = stage + (size_t)sidx * C * TILE + tid * 4;
-        float4 best = *reinterpret_cast<const float4 *>(src);
-        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        for (int c = 1; c < C; ++c) {
-            const float4 v = *reinterpret_cast<const float4 *>(src + (size_t)c * TILE);
-            // strict '>' keeps the first maximum, like torch.argmax
-            if (v.x > best.x) { best.x = v.x; a0 = c; }
-            if (v.y > best.y) { best.y = v.y; a1 = c; }
-            if (v.z > best.z) { best.z = v.z; a2 = c; }
-            if (v.w > best.w) { best.w = v.w; a3 = c; }
-        }
-        const int p = tile * TILE + tid * 4;
-        const int x0 = (p % hw) % w;
-        const int nib = (a0 != 0) | ((a1 != 0) << 1) | ((a2 != 0) << 2) | ((a3 != 0) << 3);
-        *reinterpret_cast<uchar4 *>(cls + p) = make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3);
-        int prev_last = __shfl_up_sync(FULL, (nib >> 3) & 1, 1);
-        if (lane == 0 || x0 == 0) prev_last = 0;                 // span start or row start: a new run begins
-        const int starts = nib & ~((nib << 1) | prev_last);      // foreground whose left neighbour is not
-        if (tid == 0) s_n = 0;
-        __syncthreads();                                         // also: every thread is done reading the stage
-        const int n = __reduce_add_sync(FULL, __popc(starts & 0xF));
-        if (lane == 0 && n) atomicAdd(&s_n, n);
-        if (tid == 0) issue(k + ARGMAX_STAGES);                  // refill the stage just consumed
-        __syncthreads();
-        if (tid == 0) tile_runs[tile] = s_n;
-    }
-}
-
-
 // Persistent, software-pipelined variant of k_argmax_runs_v4 (P % 1024 == 0): a block walks over tiles and issues the C
 // 16-byte loads of its NEXT tile before it picks the arg-max of the current one, so every thread keeps 2 C loads in flight
 // and the bandwidth no longer depends on how many short-lived blocks are resident (plain kernel: 56 us at 8 blocks/SM, 88 us
 // at 3, 118 us at 2).  Two blocks per SM reach the HBM rate and fit next to the vote kernel of another batch
 // (tools/microbench_overlap.cu: an issue-bound kernel and a streaming kernel with deep loads in flight slow each other by
-// 5-15 % only).  Same outputs as k_argmax_runs_v4.
+// 5-15 % only).  A copy-engine fed variant (cp.async.bulk of whole tiles into a 3-stage shared-memory ring, one block per
+// SM) was measured too: 84 us, the 4 KB bulk copies of one block do not keep enough bytes in flight.  Same outputs as
+// k_argmax_runs_v4.
 template <int CT>
 __global__ void __launch_bounds__(256) k_argmax_runs_p4(const float *__restrict__ mask, uint8_t *__restrict__ cls,
                                                         int *__restrict__ tile_runs, int hw, int w, int ntiles) {
     __shared__ int s_n[2];
     const int tid = threadIdx.x, lane = tid & 31;
     const int plane4 = hw >> 2;
-    auto tile_src = [&](int tile) {
-        const long long p = (long long)tile * TILE + tid * 4;
-        const int bi = (int)(p / hw), pix = (int)(p - (long long)bi * hw);
-        return reinterpret_cast<const float4 *>(mask + (size_t)bi * CT * hw + pix);
-    };
-    float4 nxt[CT];
+    // (image, pixel in image, column) of this thread's first pixel, advanced incrementally from tile to tile: no division in
+    // the loop (a 64-bit p / hw per tile used to be a third of this kernel's instructions)
+    const int step = gridDim.x * TILE;
+    const int step_img = step / hw, step_pix = step - step_img * hw, step_x = step % w;
     int tile = blockIdx.x;
+    int p = tile * TILE + tid * 4;
+    int bi = p / hw, pix = p - bi * hw, x0 = p % w;                 // hw is a multiple of w: (p % hw) % w == p % w
+    // the NEXT tile's coordinates
+    int bi_n = bi, pix_n = pix;
+    auto src_of = [&](int img, int px) { return reinterpret_cast<const float4 *>(mask + (size_t)img * CT * hw + px); };
+    float4 nxt[CT];
     if (tile < ntiles) {
-        const float4 *src = tile_src(tile);
+        const float4 *src = src_of(bi, pix);
 #pragma unroll
         for (int c = 0; c < CT; ++c) nxt[c] = __ldcs(src + (size_t)c * plane4);
     }
@@ -174,8 +104,10 @@ __global__ void __launch_bounds__(256) k_argmax_runs_p4(const float *__restrict_
 #pragma unroll
         for (int c = 0; c < CT; ++c) cur[c] = nxt[c];
         const int tn = tile + gridDim.x;
+        bi_n = bi + step_img; pix_n = pix + step_pix;
+        if (pix_n >= hw) { pix_n -= hw; ++bi_n; }
         if (tn < ntiles) {
-            const float4 *src = tile_src(tn);
+            const float4 *src = src_of(bi_n, pix_n);
 #pragma unroll
             for (int c = 0; c < CT; ++c) nxt[c] = __ldcs(src + (size_t)c * plane4);
         }
@@ -189,8 +121,6 @@ __global__ void __launch_bounds__(256) k_argmax_runs_p4(const float *__restrict_
             if (cur[c].z > best.z) { best.z = cur[c].z; a2 = c; }
             if (cur[c].w > best.w) { best.w = cur[c].w; a3 = c; }
         }
-        const int p = tile * TILE + tid * 4;
-        const int x0 = (p % hw) % w;
         const int nib = (a0 != 0) | ((a1 != 0) << 1) | ((a2 != 0) << 2) | ((a3 != 0) << 3);
         *reinterpret_cast<uchar4 *>(cls + p) = make_uchar4((unsigned char)a0, (unsigned char)a1, (unsigned char)a2, (unsigned char)a3);
         int prev_last = __shfl_up_sync(FULL, (nib >> 3) & 1, 1);
@@ -208,6 +138,9 @@ __global__ void __launch_bounds__(256) k_argmax_runs_p4(const float *__restrict_
         __syncthreads();
         if (tid == 0) tile_runs[tile] = *cnt;
         tile = tn;
+        p += step; bi = bi_n; pix = pix_n;
+        x0 += step_x;
+        if (x0 >= w) x0 -= w;
     }
 }
 
@@ -384,7 +317,7 @@ __global__ void __launch_bounds__(1024) k_cls_runs(const long long *__restrict__
 }
 
 // 2/6. exclusive scan of per-tile counts (single block); total -> counters[which] (+ capacity flag)
-__global__ void __launch_bounds__(1024, 3) k_scan_tiles(int *tile_counts, int ntiles, int *counters, int which, long long cap,
+__global__ void __launch_bounds__(1024) k_scan_tiles(int *tile_counts, int ntiles, int *counters, int which, long long cap,
                                                      int flag, int reset_flags) {
     const int total = block_exclusive_scan_inplace(tile_counts, ntiles);
     if (threadIdx.x == 0) {
@@ -586,7 +519,7 @@ __global__ void __launch_bounds__(256) k_run_merge(RunTables RT, const int *__re
 }
 
 // 5. path compression + number of roots per 1024-run tile
-__global__ void __launch_bounds__(1024, 3) k_run_flatten(RunTables RT, const int *__restrict__ counters, int *__restrict__ tile_roots,
+__global__ void __launch_bounds__(1024) k_run_flatten(RunTables RT, const int *__restrict__ counters, int *__restrict__ tile_roots,
                                                       long long cap) {
     const int M = (counters[FPC_CNT_FLAGS] & FPC_FLAG_ROWS) ? 0 : (int)min((long long)counters[FPC_CNT_ROWS], cap);
     const int m = blockIdx.x * TILE + threadIdx.x;
@@ -600,7 +533,7 @@ __global__ void __launch_bounds__(1024, 3) k_run_flatten(RunTables RT, const int
 }
 
 // 7. instance id = rank of the root run in raster order (== scipy.ndimage.label's numbering, aggregation_layer.py:178)
-__global__ void __launch_bounds__(1024, 3) k_run_assign(RunTables RT, const int *__restrict__ counters, const int *__restrict__ tile_base,
+__global__ void __launch_bounds__(1024) k_run_assign(RunTables RT, const int *__restrict__ counters, const int *__restrict__ tile_base,
                                                      InstTables T, int max_instances, long long cap) {
     __shared__ int s_w[32];
     const int M = (counters[FPC_CNT_FLAGS] & FPC_FLAG_ROWS) ? 0 : (int)min((long long)counters[FPC_CNT_ROWS], cap);
@@ -645,7 +578,7 @@ __global__ void __launch_bounds__(256) k_run_stats(RunTables RT, const int *__re
 }
 
 // 9. run slots of every instance -> rowoff (exclusive scan over instances, single block)
-__global__ void __launch_bounds__(1024, 3) k_scan_slots(InstTables T, int *counters, int max_instances) {
+__global__ void __launch_bounds__(1024) k_scan_slots(InstTables T, int *counters, int max_instances) {
     const int N = min(counters[FPC_CNT_INSTANCES], max_instances);
     for (int i = threadIdx.x; i < N; i += blockDim.x) T.rowoff[i] = T.nruns[i];
     __syncthreads();
@@ -658,7 +591,7 @@ __global__ void __launch_bounds__(1024, 3) k_scan_slots(InstTables T, int *count
 //     vote counters.  ransac_voting_gpu.py:536-545: fewer than min_num pixels -> the instance does not vote; more than
 //     max_num -> Bernoulli(max_num / count) sub-sampling.
 __global__ void __launch_bounds__(256) k_run_slots(RunTables RT, InstTables T, RowTables R, const int *__restrict__ counters,
-                                                   PathParams pp, int *__restrict__ votes) {
+                                                   PathParams pp, int *__restrict__ votes, const uint8_t *__restrict__ cls) {
     __shared__ int s_w[8];
     __shared__ int s_carry[2];
     if (counters[FPC_CNT_FLAGS]) return;
@@ -710,7 +643,7 @@ __global__ void __launch_bounds__(256) k_run_slots(RunTables RT, InstTables T, R
                 for (int m = m0; m < m1; ++m)
                     if (RT.inst[m] == i) {
                         const int s = RT.start[m], len = RT.end[m] - s + 1;
-                        R.desc[slot0 + slot] = make_int4(i, s, len | flags, pref);
+                        R.desc[slot0 + slot] = make_int4(i, s, len | ((int)cls[s] << ROW_CLS_SHIFT) | flags, pref);
                         ++slot;
                         if (votes_at_all) {
                             if (!sub) pref += len;
@@ -817,42 +750,19 @@ int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const flo
         const bool vec_ok = (pp.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(mask_logits) & 15) == 0) &&
                             ((reinterpret_cast<uintptr_t>(ws.cls) & 3) == 0);
         if (vec_ok) {
-            static int pad = -1;          // FPC_ARGMAX_PAD_SMEM: occupancy experiment only
-            if (pad < 0) {
-                const char *e = getenv("FPC_ARGMAX_PAD_SMEM");
-                pad = e ? atoi(e) : 0;
-                if (pad > 0) cudaFuncSetAttribute(k_argmax_runs_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-            }
-            static int use_tma = -1;      // FPC_ARGMAX_MODE: 0 plain kernel, 1 copy-engine fed, 2 persistent pipelined (default)
-            if (use_tma < 0) {
+            // persistent pipelined kernel (default); FPC_ARGMAX_MODE=0 selects the one-tile-per-block kernel (A/B measurements)
+            static int mode = -1, p4_blocks = 2;
+            if (mode < 0) {
                 const char *e = getenv("FPC_ARGMAX_MODE");
-                use_tma = e ? atoi(e) : 2;
+                mode = e ? atoi(e) : 2;
+                const char *bpsm = getenv("FPC_ARGMAX_BLOCKS_PER_SM");
+                if (bpsm && atoi(bpsm) >= 1) p4_blocks = atoi(bpsm);
             }
-            if (use_tma == 2 && pp.num_classes == 7 && P % TILE == 0) {
-                static int p4_blocks = 0;
-                if (p4_blocks == 0) {
-                    const char *e = getenv("FPC_ARGMAX_BLOCKS_PER_SM");
-                    p4_blocks = e ? std::max(1, atoi(e)) : 2;
-                }
+            if (mode != 0 && pp.num_classes == 7 && P % TILE == 0)
                 k_argmax_runs_p4<7><<<std::min(ntiles, sm_count() * p4_blocks), 256, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.hw,
                                                                                              pp.w, ntiles);
-                FPC_LAUNCH_CHECK("k_argmax_runs");
-                return launch_run_tables(ws, pp, 128, /*dense=*/false, 0, st);
-            }
-            const size_t tma_smem = (size_t)ARGMAX_STAGES * pp.num_classes * TILE * 4 + ARGMAX_STAGES * 8;
-            // pinned HOST logits (zero-copy ingestion over PCIe) keep the plain kernel: many small requests in flight suit the bus
-            cudaPointerAttributes pa;
-            const bool on_device = cudaPointerGetAttributes(&pa, mask_logits) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
-            if (use_tma == 1 && on_device && pp.hw % TILE == 0 && P % TILE == 0 && tma_smem <= 200 * 1024) {
-                static size_t attr_set = 0;
-                if (attr_set < tma_smem) {
-                    FPC_CUDA_TRY(cudaFuncSetAttribute(k_argmax_runs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
-                    attr_set = tma_smem;
-                }
-                k_argmax_runs_tma<<<std::min(ntiles, sm_count()), 256, tma_smem, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes,
-                                                                                        pp.hw, pp.w, ntiles);
-            } else
-                k_argmax_runs_v4<<<ntiles, 256, pad, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P / 4);
+            else
+                k_argmax_runs_v4<<<ntiles, 256, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P / 4);
             span = 128;
         } else {
             k_argmax_runs_v1<<<ntiles, 1024, 0, st>>>(mask_logits, ws.cls, ws.tile_roots, pp.num_classes, pp.hw, pp.w, P);
@@ -877,7 +787,7 @@ int launch_dense_problems(const Workspace &ws, const PathParams &pp, const float
 }
 
 int launch_slots(const Workspace &ws, const PathParams &pp, cudaStream_t st) {
-    k_run_slots<<<sm_count() * 8, 256, 0, st>>>(ws.RT, ws.T, ws.R, ws.counters, pp, ws.votes);
+    k_run_slots<<<sm_count() * 8, 256, 0, st>>>(ws.RT, ws.T, ws.R, ws.counters, pp, ws.votes, ws.cls);
     FPC_LAUNCH_CHECK("k_run_slots");
     return FPC_OK;
 }
