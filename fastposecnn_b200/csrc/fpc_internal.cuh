@@ -102,7 +102,7 @@ int vote_chunk_for(long long P, int hn);
 __host__ __device__ inline int vote_item_px(int i, int N, int chunk, int tail_div) {
     return (chunk >= 128 * tail_div && i >= N - N / 5) ? chunk / tail_div : chunk;
 }
-int vote_tail_div();   // 4 by default, FPC_VOTE_TAIL_DIV in the environment (1 = all items the same size)
+int vote_tail_div();   // 1 by default (measured: smaller tail items cost more instructions than the tail they save), FPC_VOTE_TAIL_DIV in the environment (1 = all items the same size)
 
 // fpc_aggregate.cu
 int launch_label_and_tables(const Workspace &ws, const PathParams &pp, const float *mask_logits,

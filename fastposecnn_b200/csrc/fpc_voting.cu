@@ -578,10 +578,16 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
         // ---- flagged notes (sign bit of a byte set) -> this block's segment of the global list; k_vote_settle re-examines
         //      them after the kernel (bit-identical s, the reference expression where |s| < band_delta) and corrects the counts
         const int nnotes = (vc.debug_skip & 1) ? 0 : nrounds * Gp * 32;
-        for (int e = tid; e < nnotes; e += VT) {
-            const unsigned w = sm.notes[e] & 0x80808080u;
-            const int g = (e >> 5) & (Gp - 1);
-            if (w && g < G) {
+        for (int e4 = tid * 4; e4 < nnotes; e4 += VT * 4) {
+            // four notes per 16-byte load; almost all of them carry no flag
+            const uint4 w4 = *reinterpret_cast<const uint4 *>(&sm.notes[e4]);
+            if (!((w4.x | w4.y | w4.z | w4.w) & 0x80808080u)) continue;
+            const unsigned ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned w = ws[k] & 0x80808080u;
+                const int e = e4 + k, g = (e >> 5) & (Gp - 1);
+                if (!w || g >= G) continue;
                 unsigned qm = ((w >> 7) & 1u) | ((w >> 14) & 2u) | ((w >> 21) & 4u) | ((w >> 28) & 8u);
                 const int ln = e & 31, hr = e >> (5 + gsh);             // lane, round
                 const int slot = atomicAdd(&sm.segn, 1);
@@ -597,12 +603,12 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
                         const int hidx = g * 128 + q * 32 + ln;
                         const float4 v = B.hloc[hidx];
                         for (int j = 0; j < VHALF; ++j) {
-                            const int k = hr * VHALF + j;
-                            const float s = vote_s(v.x, v.y, B.nx[k], B.ny[k], B.pu[k], B.pw[k], vc.ntau);
+                            const int k2 = hr * VHALF + j;
+                            const float s = vote_s(v.x, v.y, B.nx[k2], B.ny[k2], B.pu[k2], B.pw[k2], vc.ntau);
                             if (fabsf(s) < v.z) {
                                 const int fast = (int)(__float_as_uint(s) >> 31);
                                 const float2 hp = hyp_i[hidx];
-                                const int exact = vote_exact<ARITH>(rec.x[gsrc + k], rec.y[gsrc + k], rec.nx[gsrc + k], rec.ny[gsrc + k], hp.x, hp.y, thresh) ? 1 : 0;
+                                const int exact = vote_exact<ARITH>(rec.x[gsrc + k2], rec.y[gsrc + k2], rec.nx[gsrc + k2], rec.ny[gsrc + k2], hp.x, hp.y, thresh) ? 1 : 0;
                                 if (exact != fast) atomicAdd(&votes_i[hidx], exact - fast);
                             }
                         }
@@ -1198,20 +1204,21 @@ int vote_tail_div() {
     static int v = 0;
     if (v == 0) {
         const char *e = getenv("FPC_VOTE_TAIL_DIV");
-        v = e ? std::max(1, std::min(8, atoi(e))) : 4;
+        v = e ? std::max(1, std::min(8, atoi(e))) : 1;
     }
     return v;
 }
 
 // Pixels per vote work item: P/2048 rounded down to a power of two, clamped to [128, FPC_VOTE_ITEM_PX].  The upper clamp
-// (default 512, FPC_VOTE_ITEM_PX in the environment, at most VOTE_CHUNK = the shared-memory buffer) trades per-item overhead
+// (default 1024 = the buffer size, FPC_VOTE_ITEM_PX in the environment, at most VOTE_CHUNK = the shared-memory buffer) trades per-item overhead
 // against the tail of the ticket queue: with ~5 items per resident block a block that draws one item more than its
-// neighbours finishes 20 % later.  640x480: b = 1 -> 128, b = 2 -> 256, b >= 4 -> 512.
+// neighbours finishes 20 % later; but every item costs ~350 instructions per warp of set-up, and with several batches in
+// flight the idle tail of one batch is filled by the kernels of the next, so fewer, larger items win (measured).
 int vote_chunk_for(long long P, int hn) {
     static int cap = 0;
     if (cap == 0) {
         const char *e = getenv("FPC_VOTE_ITEM_PX");
-        int v = e ? atoi(e) : 512;
+        int v = e ? atoi(e) : 1024;
         int c = 128;
         while (c * 2 <= v && c * 2 <= VOTE_CHUNK) c *= 2;
         cap = c;
