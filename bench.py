@@ -66,6 +66,36 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pins this process (and therefore the pages of the pinned buffers it allocates afterwards: first touch) to the CPUs of
+    the NUMA node its GPU hangs off, read from sysfs.  Returns a description for the bench line (no numactl in this image)."""
+    info = {"gpu": local_rank, "numa_node": None, "cpus": None, "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank]) if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank)
+        busid = pynvml.nvmlDeviceGetPciInfo(h).busId
+        busid = busid.decode() if isinstance(busid, bytes) else busid
+        busid = busid.lower()[-12:]                       # 0000:3b:00.0
+        with open(f"/sys/bus/pci/devices/{busid}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpulist = f.read().strip()
+            cpus = set()
+            for part in cpulist.split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info.update({"cpus": cpulist, "bound": True})
+    except Exception as e:                                  # not fatal: the numbers are then simply not NUMA-local
+        info["error"] = str(e)[:120]
+    return info
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -188,6 +218,7 @@ def run_b200(args):
         raise RuntimeError("bench.py --impl b200 needs a CUDA device: the path has no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = syn.WORKLOADS[args.workload]
@@ -212,7 +243,7 @@ def run_b200(args):
     idxs[:n_expected] = syn.presampled_idxs(tn_disc * bpg, hn, seed=1234).reshape(n_expected, hn, 2)
     idxs = idxs.to(dev)
     # the one collective of the path: all-gather of the pose tables, on its own stream (overlaps the next batch)
-    gatherer = OverlappedGather(pipe.engines, world, dev) if world > 1 else None
+    gatherer = OverlappedGather(pipe.engines, world, dev) if (world > 1 and not args.no_gather) else None
 
     nk = eng.num_launches
     kernel_names = [_lib.lib().fpc_pose_recover_kernel_name(k).decode() for k in range(nk)]
@@ -314,10 +345,14 @@ def run_b200(args):
     torch.cuda.synchronize()
     instrumented_ms_per_step = i_start.elapsed_time(i_end) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+        # every rank's own device time: the reported step is the MAX (contract); the spread tells rank skew from a real
+        # scaling cost (median close to the 1-GPU step = the extra is the slowest GPU of the box, not the collective)
+        allt = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, torch.tensor([elapsed_ms], dtype=torch.float64, device=dev))
+        per_rank_ms = [v / args.steps for v in allt.tolist()]
+        elapsed_ms = max(allt.tolist())
     ms_per_step = elapsed_ms / args.steps
     value = world * bpg / (ms_per_step * 1e-3)
 
@@ -383,7 +418,7 @@ def run_b200(args):
         e2e_depth = max(1, args.e2e_depth) if args.e2e_mode == "zerocopy" else 1     # staged copies share one input buffer
         pipe_e = PoseRecoveryPipeline(e2e_depth, bpg, wl.h, wl.w, wl.num_classes, hn, dev, max_instances=max(1024, 2 * n_expected),
                                       multi_stream=e2e_depth > 1)
-        e2e_gather = OverlappedGather(pipe_e.engines, world, dev) if world > 1 else None
+        e2e_gather = OverlappedGather(pipe_e.engines, world, dev) if (world > 1 and not args.no_gather) else None
 
         def e2e_after(e):
             if e2e_gather is not None:
@@ -434,7 +469,27 @@ def run_b200(args):
             t = torch.tensor([ems], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
+        # ceiling of the host side: plain pinned -> device copies of the mask logits on ALL ranks at once
+        link_dst = torch.empty_like(logits["mask"])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(3):
+            link_dst.copy_(host["mask"], non_blocking=True)
+        l1.record()
+        torch.cuda.synchronize()
+        link_ms = l0.elapsed_time(l1) / 3
+        if world > 1:
+            t = torch.tensor([link_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            link_ms = float(t.item())
+        link_gbs = world * host["mask"].numel() * 4 / (link_ms * 1e-3) / 1e9
+        del link_dst
         e2e = {"value": world * bpg / (ems / ksteps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "host_to_device_copy_gbs_all_ranks": link_gbs,
+               "achieved_host_read_gbs_all_ranks": world * h2d / (ems / ksteps * 1e-3) / 1e9,
                "ms_per_step": ems / ksteps, "steps": ksteps,
                "mode": args.e2e_mode, "batches_in_flight": e2e_depth,
                "note": ("pinned host head maps read in place by the kernels (zero-copy over PCIe: h2d bytes = algorithmic "
@@ -492,6 +547,9 @@ def run_b200(args):
             "gpu_launches": nk * args.steps,
             "clocks": clocks,
             "instances": n,
+            "numa": numa,
+            "all_gather": (world > 1 and not args.no_gather),
+            "ms_per_step_per_rank": {"min": min(per_rank_ms), "median": statistics.median(per_rank_ms), "max": max(per_rank_ms)},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -905,6 +963,8 @@ def main():
     ap.add_argument("--e2e-mode", default="zerocopy", choices=["zerocopy", "copy"])
     ap.add_argument("--e2e-depth", type=int, default=1, help="batches in flight in the end-to-end loop (measured: no gain, the loop is PCIe-bound)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the all-gather of the pose tables (attribution experiment only)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-head-epilogue", action="store_true", help="skip the low-resolution-input (SURVEY 8f rank 2) measurements")
     ap.add_argument("--no-matching", action="store_true", help="skip the matching (SURVEY 8f rank 1) measurements")
     args = ap.parse_args()

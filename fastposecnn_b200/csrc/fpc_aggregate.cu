@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
                     // direction: feeds the votes -> keep the reference's value / norm with IEEE sqrt and divide
                     const float qq = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
                     if (qq != 0.f) { const float rq = rsqrtf(qq); q0 *= rq; q1 *= rq; q2 *= rq; q3 *= rq; }
-                    const float vn = __fsqrt_rn(vx * vx + vy * vy);
+                    const float vn = torch_norm2(vx, vy);
                     if (vn != 0.f) { vx = __fdiv_rn(vx, vn); vy = __fdiv_rn(vy, vn); }
                 } else {
                     // already class-compressed CategoricalData (lib/type_hinting.py:12-17): [b,4|3|2,h,w], z [b,h,w]

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) k_normalize(const float *__restrict__ in,
         float ss = 0.f;
         for (int k = 0; k < c; ++k) {
             const float v = src[k * inner];
-            ss = fmaf(v, v, ss);
+            ss = __fadd_rn(ss, __fmul_rn(v, v));
         }
         const float nrm = __fsqrt_rn(ss);
         const float d = nrm != 0.f ? nrm : 1.f;
@@ -138,9 +138,9 @@ __global__ void __launch_bounds__(256) k_class_compress(const float *__restrict_
         s0 = __ldcs(s); s1 = __ldcs(s + HW); s2 = __ldcs(s + 2 * HW);
         vx = __ldcs(v); vy = __ldcs(v + HW);
         zz = __ldcs(z + ((size_t)bi * K + k) * HW + pix);
-        const float qn = __fsqrt_rn(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        const float qn = torch_norm4(q0, q1, q2, q3);
         if (qn != 0.f) { q0 = __fdiv_rn(q0, qn); q1 = __fdiv_rn(q1, qn); q2 = __fdiv_rn(q2, qn); q3 = __fdiv_rn(q3, qn); }
-        const float vn = __fsqrt_rn(vx * vx + vy * vy);
+        const float vn = torch_norm2(vx, vy);
         if (vn != 0.f) { vx = __fdiv_rn(vx, vn); vy = __fdiv_rn(vy, vn); }
     }
     float *qo = q_out + (size_t)bi * 4 * HW + pix;

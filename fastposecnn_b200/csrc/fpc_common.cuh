@@ -123,6 +123,15 @@ __device__ __forceinline__ bool hypothesis_exact(float d0x, float d0y, float c0x
     return true;
 }
 
+// ---- gtf.normalize (lib/gpu_tensor_funcs.py:37-50) as a GPU torch build computes it -------------------------------
+// torch.norm(dim) on CUDA accumulates  acc + a*a  with every product and every sum rounded separately (no FMA contraction),
+// in index order, then takes an IEEE square root; the division is IEEE as well (measured on the B200:
+// tests/test_dropin_gpu.py::test_direction_normalisation_equals_torch_cuda_bit_for_bit).  These two helpers ARE that formula.
+__device__ __forceinline__ float torch_norm2(float x, float y) { return __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))); }
+__device__ __forceinline__ float torch_norm4(float a, float b, float c, float d) {
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)), __fmul_rn(d, d)));
+}
+
 // ---- small device utilities --------------------------------------------------------------
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser
     x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;

@@ -984,7 +984,7 @@ __global__ void __launch_bounds__(256) k_vote_refine_backward_labels(const int *
         off = (size_t)2 * ((int)cl[p] - 1) * hw + p;
         rx = head[off];
         ry = head[off + hw];
-        nrm = __fsqrt_rn(rx * rx + ry * ry);
+        nrm = torch_norm2(rx, ry);
         dx = rx; dy = ry;
         if (nrm != 0.f) { dx = __fdiv_rn(rx, nrm); dy = __fdiv_rn(ry, nrm); }
     };

@@ -125,13 +125,15 @@ def samplewise_get_RT(agg_data: Dict[str, torch.Tensor], inv_intrinsics: torch.T
 
 
 def quats_2_rotation_matrix(q: torch.Tensor) -> torch.Tensor:
-    """lib/gpu_tensor_funcs.py:306-326 for already normalised quaternions [n,4] -> [n,3,3]."""
+    """lib/gpu_tensor_funcs.py:306-326, quaternions [n,4] -> [n,3,3].  The reference's formula is quadratic in q and does
+    not normalise: R_ref(q) = |q|^2 R(q / |q|).  The kernel behind ``batchwise_get_RT`` normalises (as :215-218 does before
+    calling this), so the factor is applied here -- identical for unit quaternions, faithful for the others."""
     n = q.shape[0]
     zeros2 = torch.zeros((n, 2), dtype=torch.float32, device=q.device)
     ones = torch.ones((n, 1), dtype=torch.float32, device=q.device)
     eye = torch.eye(3, dtype=torch.float32, device=q.device)
     R, _, _ = batchwise_get_RT(q, zeros2, ones, eye)
-    return R
+    return R * (q.detach().float() ** 2).sum(dim=-1).reshape(n, 1, 1) if n else R
 
 
 def batchwise_get_2d_iou(batch_masks1: torch.Tensor, batch_masks2: torch.Tensor) -> torch.Tensor:

@@ -273,3 +273,86 @@ def test_voting_multi_keypoint_vn2():
     out = ransac_voting_layer_v3(agg["instance_masks"].to(DEV), vertex.to(DEV), hn, idxs=idxs.to(DEV))
     assert out.shape == ref.shape == (n, 2, 2)
     assert helpers.rel_err(out.reshape(n, -1), ref.reshape(n, -1)) <= helpers.REL_TOL
+
+
+def test_native_module_mirrors_validate_shapes():
+    """mismatched buffers must raise on the host instead of becoming out-of-bounds device accesses."""
+    from fastposecnn_b200.ransac_voting_gpu_layer import ransac_voting as rv
+    tn, vn, hn = 50, 2, 8
+    direct = torch.randn(tn, vn, 2, device=DEV)
+    coords = torch.rand(tn, 2, device=DEV)
+    idxs = torch.randint(0, tn, (hn, vn, 2), dtype=torch.int32, device=DEV)
+    hyp = rv.generate_hypothesis(direct, coords, idxs)
+    with pytest.raises(RuntimeError, match="idxs must be"):
+        rv.generate_hypothesis(direct, coords, idxs[:, :1].contiguous())
+    with pytest.raises(RuntimeError, match="coords must be"):
+        rv.generate_hypothesis(direct, coords[:-1].contiguous(), idxs)
+    with pytest.raises(RuntimeError, match="inliers must be"):
+        rv.voting_for_hypothesis(direct, coords, hyp, torch.zeros((hn, vn, tn - 1), dtype=torch.uint8, device=DEV), 0.999)
+    with pytest.raises(RuntimeError, match="hypo_pts must be"):
+        rv.voting_for_hypothesis_vanishing_point(direct, coords, hyp, torch.zeros((hn, vn, tn), dtype=torch.uint8, device=DEV), 0.999)
+
+
+def test_quats_2_rotation_matrix_matches_the_reference_for_non_unit_quaternions():
+    import fastposecnn_b200 as fp
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(64, 4, generator=g) * 1.7
+    q[3] = 0
+    ref = port.quats_2_rotation_matrix(q)
+    got = fp.quats_2_rotation_matrix(q.to(DEV)).cpu()
+    assert helpers.rel_err(got, ref) <= helpers.REL_TOL
+
+
+def test_arg_max_of_raw_logits_versus_log_softmax_on_unquantised_logits():
+    """cat_mask = argmax(LogSoftmax(x)) in the reference (pose_regressor.py:449); the kernels take argmax(x).  Log-softmax is
+    monotone, so the two agree unless its rounding collapses two DISTINCT logits onto one value and first-index tie-breaking
+    then prefers the earlier class.  On unquantised logits every disagreement must be such a near-tie (top-2 gap of a few ulp of
+    the log-sum-exp), and there are hardly any (documented deviation)."""
+    import fastposecnn_b200 as fp
+    g = torch.Generator().manual_seed(3)
+    b, h, w = 4, 120, 160
+    logits = syn.render_heads([[(40, 40, 20, 2)], [], [(80, 60, 30, 5)], []], h, w, seed=7, quantize_mask=False)
+    logits["mask"] += torch.randn(b, 7, h, w, generator=g) * 2.0
+    # plant exact near-ties: class 4 a hair below class 1 on a few thousand pixels
+    sel = torch.rand(b, h, w, generator=g) < 0.05
+    top = logits["mask"].max(dim=1).values + 1.0
+    logits["mask"][:, 4][sel] = top[sel]
+    logits["mask"][:, 1][sel] = torch.nextafter(top[sel], torch.tensor(-1e30))
+    ref = port.class_compression(logits, 7)["mask"]
+    got = fp.class_compression(_gpu(logits), 7)["mask"].cpu()
+    diff = got != ref
+    x = logits["mask"].permute(0, 2, 3, 1)[diff]
+    if x.numel():
+        top2 = x.topk(2, dim=1).values
+        gap = (top2[:, 0] - top2[:, 1]).abs()
+        scale = torch.logsumexp(x, dim=1).abs().clamp_min(1.0)
+        assert float((gap / scale).max()) <= 4 * 2.0 ** -23, "a disagreement that is not a rounding collapse"
+    assert int(diff.sum()) <= int(sel.sum())          # only planted near-ties can flip
+    assert int((got != logits["mask"].argmax(dim=1)).sum()) == 0
+
+
+def test_direction_normalisation_equals_torch_cuda_bit_for_bit():
+    """which formula does a GPU torch build of the reference use?  gtf.normalize (gpu_tensor_funcs.py:37-50) =
+    torch.norm + division ON THE DEVICE.  Measured here (tools/diag_norm.py): torch-CUDA's norm is sqrt(x*x + y*y) with the two
+    products and the sum rounded separately (no FMA contraction), and the division is IEEE.  The kernels use exactly that
+    (torch_norm2 / torch_norm4 in fpc_common.cuh): class_compression's xy and quaternion fields, normalize() and the directions
+    the fused path votes with equal torch-CUDA's bit for bit (torch-CPU's vectorised norm differs in the last ulp on ~0.7 % of the
+    pixels, which is why the CPU oracle is compared at 1e-4)."""
+    import fastposecnn_b200 as fp
+    frames, h, w = helpers.scenes()["wide"]
+    logits = syn.render_heads(frames, h, w, seed=5)
+    g_logits = _gpu(logits)
+    out = fp.class_compression(g_logits, 7)
+    cat_mask = out["mask"]
+    # the reference's ops on CUDA tensors: select the predicted class's xy channels, then gtf.normalize
+    onehot = torch.zeros((len(frames), 7, h, w), device=DEV).scatter_(1, cat_mask.unsqueeze(1), 1.0)[:, 1:]
+    xy = g_logits["xy"].reshape(len(frames), 6, 2, h, w)
+    sel = torch.where(onehot.unsqueeze(2).bool(), xy.double(), torch.zeros((), dtype=torch.float64, device=DEV)).float().sum(dim=1)
+    ref = port.normalize(sel, 1)                       # torch ops, run on the GPU
+    assert ref.is_cuda
+    assert torch.equal(out["xy"], ref)
+    x = torch.randn(3, 4, 64, 65, device=DEV)
+    assert torch.equal(fp.normalize(x, 1), port.normalize(x, 1))
+    q = g_logits["quaternion"].reshape(len(frames), 6, 4, h, w)
+    qsel = torch.where(onehot.unsqueeze(2).bool(), q.double(), torch.zeros((), dtype=torch.float64, device=DEV)).float().sum(dim=1)
+    assert torch.equal(out["quaternion"], port.normalize(qsel, 1))
