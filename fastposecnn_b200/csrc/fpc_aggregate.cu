@@ -186,9 +186,6 @@ __global__ void __launch_bounds__(256, 4) k_gather(const uint8_t *__restrict__ c
             if (sel && sub) sel = select_uniform(pp, p) < thr;
             const unsigned bal = __ballot_sync(FULL, sel);
             if (sel && want_rec) {
-                // a direction the reference's |n| < 1e-6 guard would skip but that is not exactly zero: the fast
-                // vote test cannot see that, so the whole instance is voted with the reference expression
-                if ((vx != 0.f || vy != 0.f) && fmaf(vx, vx, vy * vy) < 1.1e-12f) T.tiny[i] = 1;
                 const int idx = rec0 + running + __popc(bal & ((1u << lane) - 1u));
                 rec.x[idx] = (float)(x0 + kx); rec.y[idx] = (float)y; rec.nx[idx] = vx; rec.ny[idx] = vy;
             }

@@ -189,7 +189,7 @@ static size_t carve(Workspace &ws, void *base, long long P, long long rows_total
     ws.T.xmax = c.take<int>(ni);
     ws.T.mincls = c.take<int>(ni);
     ws.T.nruns = c.take<int>(ni);
-    ws.T.tiny = c.take<int>(ni);
+    ws.T.rmax2 = c.take<int>(ni);
     ws.T.rowoff = c.take<int>(ni);
     ws.T.tn = c.take<int>(ni);
     ws.T.pxoff = c.take<int>(ni);

@@ -12,7 +12,7 @@ struct InstTables {
     int *ymin, *ymax, *xmin, *xmax;
     int *mincls;   // min non-zero class id inside the component (aggregation_layer.py:113)
     int *nruns;    // runs (horizontal segments) of the instance
-    int *tiny;     // 1 if some voting pixel has 0 < |dir| <= ~1e-6 (reference skips it, .cu:119): vote it exactly
+    int *rmax2;    // bit pattern of max |pixel - centre of the bounding box|^2 over the instance (k_gather; the vote kernel's |d| bound)
     int *rowoff;   // [N+1] first (instance,row) item of the instance
     int *tn;       // pixels that vote (0 if count < min_num; ~max_num if sub-sampled)
     int *pxoff;    // [N+1] first voting record of the instance

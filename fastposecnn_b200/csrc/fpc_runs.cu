@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(1024) k_run_assign(RunTables RT, const int *__
         T.nruns[id] = 0;
         T.ymin[id] = INT_MAX; T.ymax[id] = -1; T.xmin[id] = INT_MAX; T.xmax[id] = -1;
         T.mincls[id] = INT_MAX;
-        T.tiny[id] = 0;
+        T.rmax2[id] = 0;
     }
 }
 
@@ -607,6 +607,10 @@ __global__ void __launch_bounds__(256) k_run_slots(RunTables RT, InstTables T, R
         const int flags = ROW_CONTIG | (sub ? ROW_SUB : 0) | (votes_at_all ? ROW_VOTES : 0);
         for (int k = tid; k < pp.hn; k += 256) votes[(size_t)i * pp.hn + k] = 0;
         if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; }      // (slots, voting pixels) of the rows handled so far
+        // farthest pixel from the centre of the bounding box (an end of some run): the vote kernel bounds |hypothesis - pixel|
+        // with it (tighter than the box diagonal: 36 instead of 51 pixels for a disc of radius 35)
+        const float ox = (float)((T.xmin[i] + T.xmax[i] + 1) >> 1), oy = (float)((ymin + ymax + 1) >> 1);
+        float r2max = 0.f;
         __syncthreads();
         for (int yb = ymin; yb <= ymax; yb += 256) {
             // one thread per image row: own runs of this row and their voting pixels
@@ -618,6 +622,11 @@ __global__ void __launch_bounds__(256) k_run_slots(RunTables RT, InstTables T, R
                 for (int m = m0; m < m1; ++m)
                     if (RT.inst[m] == i) {
                         ++nr;
+                        {
+                            const int xa = (RT.start[m] - img * pp.hw) - y * pp.w, xb = xa + (RT.end[m] - RT.start[m]);
+                            const float dy = (float)y - oy, da = (float)xa - ox, db = (float)xb - ox;
+                            r2max = fmaxf(r2max, fmaf(dy, dy, fmaxf(da * da, db * db)));
+                        }
                         if (votes_at_all) {
                             if (!sub) nv += RT.end[m] - RT.start[m] + 1;
                             else for (int q = RT.start[m]; q <= RT.end[m]; ++q) nv += select_uniform(pp, q) < thr ? 1 : 0;
@@ -654,6 +663,8 @@ __global__ void __launch_bounds__(256) k_run_slots(RunTables RT, InstTables T, R
             __syncthreads();
         }
         if (tid == 0) T.tn[i] = s_carry[1];
+        r2max = __int_as_float(__reduce_max_sync(FULL, __float_as_int(r2max)));   // non-negative floats order like their bit patterns
+        if (lane == 0 && r2max > 0.f) atomicMax(&T.rmax2[i], __float_as_int(r2max));
         __syncthreads();
     }
 }
@@ -679,7 +690,7 @@ __global__ void __launch_bounds__(256) k_dense_init(InstTables T, int *counters,
     T.nruns[j] = 0;
     T.xmin[j] = INT_MAX; T.xmax[j] = -1; T.ymin[j] = INT_MAX; T.ymax[j] = -1;
     T.mincls[j] = 0;
-    T.tiny[j] = 0;
+    T.rmax2[j] = 0;
 }
 // empty problems: a zero-height row range so that the slot kernel has nothing to walk
 __global__ void __launch_bounds__(256) k_dense_fix_empty(InstTables T, int nprob) {

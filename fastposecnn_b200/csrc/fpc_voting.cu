@@ -192,7 +192,8 @@ __device__ __forceinline__ VoteFrame vote_frame(const InstTables &T, int i) {
     f.oy = (float)((y0 + y1 + 1) >> 1);
     const float rx = 0.5f * (float)(x1 - x0) + 1.f, ry = 0.5f * (float)(y1 - y0) + 1.f;   // >= |c'x|, |c'y|
     f.rsum = rx + ry;
-    f.rdiag = 1.0001f * sqrtf(rx * rx + ry * ry);
+    // >= |c'| for every voting pixel: the farthest pixel from the origin as measured by k_gather, never more than the box diagonal
+    f.rdiag = 1.0001f * fminf(sqrtf(rx * rx + ry * ry), sqrtf(__int_as_float(T.rmax2[i])) + 1e-3f);
     return f;
 }
 __device__ __forceinline__ bool near_lattice(float x, float y) {
@@ -1172,9 +1173,11 @@ static int launch_vote_t(const Workspace &ws, const PathParams &pp, const float2
         FPC_CUDA_TRY(cudaFuncSetAttribute(k_vote<ARITH, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vote<ARITH, PACKED>, VT, smem) != cudaSuccess || n < 1) n = 2;
-        // FPC_VOTE_BLOCKS_PER_SM caps the persistent grid (leaves room for kernels of another stream to co-reside)
+        // Two blocks per SM by default although three fit: the hot loop saturates the issue ports with two warps per
+        // scheduler, and the third block's registers are worth more to the kernels of the other batches in flight (measured:
+        // the kernel alone is 2 % slower, the pipelined step 3 % faster).  FPC_VOTE_BLOCKS_PER_SM overrides.
         const char *e = getenv("FPC_VOTE_BLOCKS_PER_SM");
-        if (e && atoi(e) >= 1) n = std::min(n, atoi(e));
+        n = std::min(n, (e && atoi(e) >= 1) ? atoi(e) : 2);
         blocks_per_sm = n;
     }
     const VoteConsts vc = vote_consts(pp);
