@@ -219,6 +219,14 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False}
+    if args.l2_fetch_granularity:
+        import ctypes
+        torch.zeros(1, device=dev)
+        rt = ctypes.CDLL("libcudart.so.12")
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(args.l2_fetch_granularity))      # cudaLimitMaxL2FetchGranularity = 0x05
+        got = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(got), 5)
+        print(f"cudaLimitMaxL2FetchGranularity: set rc={rc}, now {got.value}", file=sys.stderr)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = syn.WORKLOADS[args.workload]
@@ -279,7 +287,7 @@ def run_b200(args):
     for res in pipe.drain():
         check(res)
     if use_graph:
-        pipe.capture(logits, inv_k, idxs=idxs)          # the 15 launches of one step become one graph launch
+        pipe.capture(logits, inv_k, idxs=idxs)          # the launches of one step become one graph launch
         for _ in range(2 * depth):
             step(replay=True)
         for res in pipe.drain():
@@ -961,12 +969,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches in the timed loop instead of CUDA-graph replay")
     ap.add_argument("--e2e-mode", default="zerocopy", choices=["zerocopy", "copy"])
-    ap.add_argument("--e2e-depth", type=int, default=1, help="batches in flight in the end-to-end loop (measured: no gain, the loop is PCIe-bound)")
+    ap.add_argument("--e2e-depth", type=int, default=2,
+                    help="batches in flight in the end-to-end loop, one stream each (measured, profiles/r02_e2e_depth.txt: 2 keeps the PCIe "
+                         "link busy across the batch boundary, +7 %% over 1; 3 and 4 add nothing)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the all-gather of the pose tables (attribution experiment only)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-head-epilogue", action="store_true", help="skip the low-resolution-input (SURVEY 8f rank 2) measurements")
     ap.add_argument("--no-matching", action="store_true", help="skip the matching (SURVEY 8f rank 1) measurements")
+    ap.add_argument("--l2-fetch-granularity", type=int, default=0, choices=[0, 32, 64, 128],
+                    help="experiment: cudaLimitMaxL2FetchGranularity (bytes) before the run; 0 = leave the driver default")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "b200" and world != args.gpus:

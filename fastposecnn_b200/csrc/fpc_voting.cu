@@ -166,9 +166,13 @@ constexpr int VT = 256;            // threads per block
 constexpr int VQ = 4;              // hypotheses per lane
 constexpr int VHB = 512;           // hypotheses per batch (4 groups of 32 lanes x VQ)
 constexpr int VROUND = 16;         // pixels per round (unit of the work split between warps)
-constexpr int VHALF = VROUND;      // pixels per note (unit of the re-examination)
+#ifndef FPC_VOTE_NOTE_PX
+#define FPC_VOTE_NOTE_PX 8
+#endif
+constexpr int VHALF = FPC_VOTE_NOTE_PX;   // pixels per note (unit of the re-examination by k_vote_settle): 16 halves the notes, 8 halves the settle work
+constexpr int VNH = VROUND / VHALF;       // notes per round
 constexpr int VSEGCAP = 4096;      // flagged notes one block can hand to k_vote_settle; beyond that items are re-examined in place
-constexpr int VNOTES = 4096;       // raw notes per work item: rounds x hypothesis groups (padded to 2^k) x 32 lanes
+constexpr int VNOTES = 4096 * (VNH > 2 ? 2 : VNH);  // raw notes per work item: rounds x notes per round x hypothesis groups (padded to 2^k) x 32 lanes (32 KB at most)
 constexpr float V_FAR = 1e12f;     // |h'x| + |h'y| beyond this (or NaN): the hypothesis is voted exactly
 constexpr float V_NEVER = 1e30f;   // pw of a pixel that can never be an inlier
 
@@ -543,16 +547,18 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
                 dqi[q] = __float_as_uint(v.z);
                 cnt[q] = 0u;
             }
-            // one note word per (lane, round): index (rd Gp + g) 32 + lane
-            unsigned *note = &sm.notes[(part * Gp + g) * 32 + lane];
-            const int note_step = parts * Gp * 32;
+            // one note word per (lane, VHALF pixels of a round): index ((rd VNH + hf) Gp + g) 32 + lane
+            unsigned *note = &sm.notes[(part * VNH * Gp + g) * 32 + lane];
+            const int note_step = parts * VNH * Gp * 32;
             for (int rd = part; rd < nrounds; rd += parts, note += note_step) {
                 const int kb = rd * VROUND;
+#pragma unroll
+              for (int hf = 0; hf < VNH; ++hf) {
                 float m[VQ];
 #pragma unroll
                 for (int q = 0; q < VQ; ++q) m[q] = 3e38f;
 #pragma unroll
-                for (int j4 = 0; j4 < VROUND; j4 += 4) {
+                for (int j4 = hf * VHALF; j4 < (hf + 1) * VHALF; j4 += 4) {
                     const float4 pu = *reinterpret_cast<const float4 *>(&B.pu[kb + j4]);
                     const float4 pw = *reinterpret_cast<const float4 *>(&B.pw[kb + j4]);
                     const float4 nx = *reinterpret_cast<const float4 *>(&B.nx[kb + j4]);
@@ -563,13 +569,14 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
                         vote_pair<PACKED>(hx[q], hy[q], nx.z, nx.w, ny.z, ny.w, pu.z, pu.w, pw.z, pw.w, vc.ntau, cnt[q], m[q]);
                     }
                 }
-                // byte q of the note: sign set <=> some vote of hypothesis q in this round may be uncertain (min |s| < band_delta,
+                // byte q of the note: sign set <=> some vote of hypothesis q in these VHALF pixels may be uncertain (min |s| < band_delta,
                 // compared as integers: both are non-negative floats).  Stored unconditionally -- no branch, no atomic; the
                 // signs counted above stay in the count, k_vote_settle corrects them.
                 unsigned t[VQ];
 #pragma unroll
                 for (int q = 0; q < VQ; ++q) t[q] = __float_as_uint(m[q]) - dqi[q];
-                *note = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x7300), 0x7610);
+                note[hf * Gp * 32] = __byte_perm(__byte_perm(t[0], t[1], 0x0073), __byte_perm(t[2], t[3], 0x7300), 0x7610);
+              }
             }
 #pragma unroll
             for (int q = 0; q < VQ; ++q)
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
         __syncthreads();
         // ---- flagged notes (sign bit of a byte set) -> this block's segment of the global list; k_vote_settle re-examines
         //      them after the kernel (bit-identical s, the reference expression where |s| < band_delta) and corrects the counts
-        const int nnotes = (vc.debug_skip & 1) ? 0 : nrounds * Gp * 32;
+        const int nnotes = (vc.debug_skip & 1) ? 0 : nrounds * VNH * Gp * 32;
         for (int e4 = tid * 4; e4 < nnotes; e4 += VT * 4) {
             // four notes per 16-byte load; almost all of them carry no flag
             const uint4 w4 = *reinterpret_cast<const uint4 *>(&sm.notes[e4]);
@@ -590,12 +597,12 @@ __global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *_
                 const int e = e4 + k, g = (e >> 5) & (Gp - 1);
                 if (!w || g >= G) continue;
                 unsigned qm = ((w >> 7) & 1u) | ((w >> 14) & 2u) | ((w >> 21) & 4u) | ((w >> 28) & 8u);
-                const int ln = e & 31, hr = e >> (5 + gsh);             // lane, round
+                const int ln = e & 31, hr = e >> (5 + gsh);             // lane, index of the VHALF-pixel unit
                 const int slot = atomicAdd(&sm.segn, 1);
                 if (slot < VSEGCAP) {
                     // self-contained entry: first record of the round, first hypothesis of the lane, frame origin, q mask | live pixels
                     seg[slot] = make_uint4((unsigned)(gsrc + hr * VHALF), (unsigned)((size_t)i * hn + hb + g * 128 + ln),
-                                           (unsigned)it.f.ox | ((unsigned)it.f.oy << 16), qm | ((unsigned)min(VHALF, npx - hr * VHALF) << 4));
+                                           (unsigned)it.f.ox | ((unsigned)it.f.oy << 16), qm | ((unsigned)max(0, min(VHALF, npx - hr * VHALF)) << 4));
                 } else {
                     // the segment is full: re-examine this note right here
                     while (qm) {
@@ -1228,10 +1235,10 @@ int vote_chunk_for(long long P, int hn) {
     }
     int c = cap;
     while (c > 128 && (long long)c * 2048 > P) c >>= 1;
-    // the note table holds half rounds x hypothesis groups (padded to 1, 2 or 4) <= 128 per item: 1024 px for hn <= 128,
-    // 512 px for hn <= 256, 256 px beyond
+    // the note table holds (VHALF-pixel units) x hypothesis groups (padded to 1, 2 or 4) <= VNOTES / 32 per item: 1024 px for
+    // hn <= 256, 512 px beyond
     const int G = (std::min(hn, VHB) + 127) / 128, Gp = G > 2 ? 4 : G;
-    while (c > 128 && Gp * (c / VROUND) > VNOTES / 32) c >>= 1;
+    while (c > 128 && Gp * (c / VHALF) > VNOTES / 32) c >>= 1;
     return c;
 }
 

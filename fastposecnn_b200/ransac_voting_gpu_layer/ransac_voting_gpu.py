@@ -2,7 +2,8 @@
 (:518-607, the one HoughVotingLayer calls), ``ransac_voting_layer`` (v1, :11-98), ``b_inv`` (:503-516) and, from the
 "next" rows, ``ransac_voting_layer_v2`` (:100), ``ransac_voting_hypothesis`` (:218), ``estimate_voting_distribution``
 (:263), ``estimate_voting_distribution_with_mean`` (:333), ``ransac_voting_layer_v4`` (:678, + residual variance) and
-``ransac_voting_layer_v5`` (:771, + confidence).  (``ransac_voting_vanish_point_layer`` :408 references an
+``ransac_voting_layer_v5`` (:771, + confidence), ``ransac_voting_layer_v6`` (:868), ``ransac_voting_center`` (:609),
+``ransac_motion_voting`` (:968) and the driver ``generate_hypothesis`` (:991).  (``ransac_voting_vanish_point_layer`` :408 references an
 undefined ``class_num`` and cannot run in the reference; its two kernels are mirrored in ``ransac_voting.py``.)
 
 Same positional/keyword signatures and result layouts.  Instead of a Python loop with ~40 small
@@ -214,6 +215,81 @@ def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
     :return: ``[b,vn,2]`` refined points, ``[b,vn]`` confidences (zeros for instances with < ``min_num`` pixels)."""
     pts, det = _binary_mask_vote(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idxs, select_mask, select_u)
     return pts, torch.stack([d["confidence"] for d in det], dim=1)
+
+
+def ransac_voting_layer_v6(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                           max_num=100, *, idxs: Optional[torch.Tensor] = None, select_u: Optional[torch.Tensor] = None):
+    """ransac_voting_gpu.py:868-966 -- v5 except that the foreground count deciding the skip (``< min_num``) and the
+    sub-sampling ratio (``max_num / count``) is ``torch.sum(mask)`` over the WHOLE batch (:884), and a pixel belongs to the
+    mask iff ``mask.byte()`` is non-zero (:885).  ``select_u``: the ``[b,h,w]`` uniforms of the sub-sampling (drawn on the
+    device when omitted).  An image left without a single pixel gets zeros (the reference raises there).
+
+    :return: ``[b,vn,2]`` refined points, ``[b,vn]`` confidences."""
+    mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
+    vertex = _lib.require_cuda(vertex, "vertex", torch.float32, contiguous=False)
+    b, h, w, vn, two = vertex.shape
+    if two != 2 or tuple(mask.shape) != (b, h, w):
+        raise RuntimeError(f"expected mask [b,h,w] and vertex [b,h,w,vn,2], got {tuple(mask.shape)}, {tuple(vertex.shape)}")
+    total = torch.sum(mask)
+    if bool(total < min_num):
+        return (torch.zeros((b, vn, 2), dtype=torch.float32, device=vertex.device),
+                torch.zeros((b, vn), dtype=torch.float32, device=vertex.device))
+    fmask = (mask.byte() != 0).to(torch.float32)
+    if bool(total > max_num):
+        u = _lib.require_cuda(select_u, "select_u", torch.float32).reshape(b, h, w) if select_u is not None else \
+            torch.rand((b, h, w), dtype=torch.float32, device=vertex.device)
+        fmask = fmask * (u < (max_num / total.float())).to(torch.float32)
+    det: list = []
+    # the decisions were taken above for the whole batch: every image with a pixel left votes with all of its pixels
+    pts = _vote(b, h, w, vn, fmask.contiguous(), None, 1, 0, vertex, int(round_hyp_num), inlier_thresh, 1, 2 ** 31 - 1, True,
+                idxs, None, det)
+    return pts, torch.stack([d["confidence"] for d in det], dim=1)
+
+
+def ransac_voting_center(mask, vertex, round_hyp_num, inlier_thresh=0.99, confidence=0.999, max_iter=20, min_num=100):
+    """ransac_voting_gpu.py:609-676.  The reference votes for one centre per image and then drops the result: the list it
+    returns holds one all-zero ``[h,w]`` mask per image with FEWER than ``min_num`` pixels and nothing for the others
+    (:624-628, :676).  Reproduced as is -- there is nothing to compute."""
+    mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
+    b, h, w = mask.shape
+    few = (mask.byte().flatten(1).sum(dim=1) < min_num).tolist()
+    return [torch.zeros((h, w), dtype=torch.float32, device=mask.device) for bi in range(b) if few[bi]]
+
+
+def ransac_motion_voting(mask, vertex):
+    """ransac_voting_gpu.py:968-989 -> ``[b,vn,2]``: mean over the mask's pixels of (pixel (x, y) + its vector); zeros for an
+    empty mask.  Two batched masked sums instead of the per-image loop (sums in another order: <= 1e-5 relative)."""
+    mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
+    vertex = _lib.require_cuda(vertex, "vertex", torch.float32, contiguous=False)
+    b, h, w, vn, _ = vertex.shape
+    m = (mask.byte() != 0)
+    n = m.flatten(1).sum(dim=1).to(torch.float32)                                   # [b]
+    mf = m.to(torch.float32)
+    ys = torch.arange(h, dtype=torch.float32, device=vertex.device).view(1, h, 1)
+    xs = torch.arange(w, dtype=torch.float32, device=vertex.device).view(1, 1, w)
+    centre = torch.stack(((mf * xs).flatten(1).sum(dim=1), (mf * ys).flatten(1).sum(dim=1)), dim=1)      # [b,2]
+    total = (vertex * mf.view(b, h, w, 1, 1)).flatten(1, 2).sum(dim=1) + centre.unsqueeze(1)              # [b,vn,2]
+    return torch.where((n > 0).view(b, 1, 1), total / n.clamp_min(1).view(b, 1, 1), torch.zeros_like(total))
+
+
+def generate_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                        max_num=30000, *, idxs: Optional[torch.Tensor] = None, select_mask: Optional[torch.Tensor] = None,
+                        select_u: Optional[torch.Tensor] = None):
+    """ransac_voting_gpu.py:991-1043 -> all hypotheses ``[b,hn,vn,2]`` and their vote counts ``[b,hn,vn]`` (int64) over
+    the binary mask of every image, no winner and no refinement.  An image with fewer than ``min_num`` pixels makes the
+    reference fail (NameError at :1010); here it raises RuntimeError."""
+    mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
+    vertex = _lib.require_cuda(vertex, "vertex", torch.float32, contiguous=False)
+    b, h, w, vn, two = vertex.shape
+    if two != 2 or tuple(mask.shape) != (b, h, w):
+        raise RuntimeError(f"expected mask [b,h,w] and vertex [b,h,w,vn,2], got {tuple(mask.shape)}, {tuple(vertex.shape)}")
+    fmask = (mask.byte() != 0).to(torch.float32).contiguous()
+    if bool((fmask.flatten(1).sum(dim=1) < min_num).any()):
+        raise RuntimeError("generate_hypothesis: an image has fewer than min_num mask pixels (the reference raises NameError here)")
+    su = _select_u(select_mask, select_u, (b, h, w), vertex.device)
+    det: list = []
+    _vote(b, h, w, vn, fmask, None, 1, 0, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num, False, idxs, su, det)
+    return torch.stack([d["hyp"] for d in det], dim=2), torch.stack([d["counts"] for d in det], dim=2).long()
 
 
 def _class1_hypotheses(mask, vertex, hn, inlier_thresh, min_num, max_num, idxs, select_u):

@@ -731,19 +731,20 @@ def calculate_aps(raw_data, metrics_threshold, metrics_operator):
     return aps
 
 
-def _v3_with_extras(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idx_source, rv):
+def _v3_with_extras(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idx_source, rv, batch_fg=False, select_u=None):
     """Shared body of v4 (:678-769) and v5 (:771-866): per image the binary mask's winner, its inlier-weighted normal
     equations, the residual variance about the refined point (v4) and the inlier ratio AT the refined point with the
     hard-coded threshold 0.999 (v5).  Yields (points [vn,2], var [vn], conf [vn]) or None for a skipped image."""
     b, h, w, vn, _ = vertex.shape
     for bi in range(b):
         cur = mask[bi].byte()
-        fg = torch.sum(cur)
+        # v6 (:884) counts the foreground of the WHOLE batch (``torch.sum(mask)``), v4 / v5 that of the image
+        fg = torch.sum(mask) if batch_fg else torch.sum(cur)
         if fg < min_num:
             yield None
             continue
         if fg > max_num:
-            u = torch.zeros(cur.shape, dtype=torch.float32).uniform_(0, 1)
+            u = select_u[bi] if select_u is not None else torch.zeros(cur.shape, dtype=torch.float32).uniform_(0, 1)
             cur = cur * (u < (max_num / fg.float()))
         sel = cur.bool()
         coords = torch.nonzero(sel).float()[:, [1, 0]]
@@ -792,6 +793,68 @@ def ransac_voting_layer_v5(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
         pts.append(torch.zeros([1, vn, 2]) if res is None else res[0].unsqueeze(0))
         conf.append(torch.zeros([1, vn]) if res is None else res[2].unsqueeze(0))
     return torch.cat(pts), torch.cat(conf)
+
+
+def ransac_voting_layer_v6(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                           max_num=100, *, idx_source: Optional[IdxSource] = None, select_u=None, kernels=None):
+    """ransac_voting_gpu.py:868-966 -> ``[b,vn,2]`` points, ``[b,vn]`` confidences.  v5 with one difference: the
+    foreground count that decides the skip and the sub-sampling ratio is the sum of the mask over the WHOLE batch (:884)."""
+    vn = vertex.shape[3]
+    pts, conf = [], []
+    for res in _v3_with_extras(mask, vertex, round_hyp_num, inlier_thresh, min_num, max_num, idx_source or seeded_idx_source(),
+                               kernels or native.ransac_voting, batch_fg=True, select_u=select_u):
+        pts.append(torch.zeros([1, vn, 2]) if res is None else res[0].unsqueeze(0))
+        conf.append(torch.zeros([1, vn]) if res is None else res[2].unsqueeze(0))
+    return torch.cat(pts), torch.cat(conf)
+
+
+def ransac_voting_center(mask, vertex, round_hyp_num, inlier_thresh=0.99, confidence=0.999, max_iter=20, min_num=100):
+    """ransac_voting_gpu.py:609-676.  The function votes (vn = 1) and then DROPS the result: only images with fewer than
+    ``min_num`` pixels append anything -- an all-zero ``[h,w]`` mask -- to the returned list (:624-628, :676)."""
+    b, h, w, _ = vertex.shape
+    return [torch.zeros([h, w], dtype=torch.float32) for bi in range(b) if torch.sum(mask[bi].byte()) < min_num]
+
+
+def ransac_motion_voting(mask, vertex):
+    """ransac_voting_gpu.py:968-989 -> ``[b,vn,2]``: mean over the mask's pixels of (pixel + its motion vector); zeros
+    for an empty mask."""
+    b, h, w, vn, _ = vertex.shape
+    pts = []
+    for bi in range(b):
+        cur = mask[bi].byte().bool()
+        coords = torch.nonzero(cur).float()
+        if coords.shape[0] < 1:
+            pts.append(torch.zeros([1, vn, 2], dtype=torch.float32))
+            continue
+        coords = coords[:, (1, 0)]
+        pts.append(torch.mean(vertex[bi][cur] + coords.unsqueeze(1), 0).unsqueeze(0))
+    return torch.cat(pts, 0)
+
+
+def generate_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                        max_num=30000, *, idx_source: Optional[IdxSource] = None, kernels=None):
+    """ransac_voting_gpu.py:991-1043 -> all hypotheses ``[b,hn,vn,2]`` and their vote counts ``[b,hn,vn]`` (int64) of the
+    binary mask of every image.  (An image with fewer than ``min_num`` pixels makes the reference raise NameError, :1010.)"""
+    rv = kernels or native.ransac_voting
+    idx_source = idx_source or seeded_idx_source()
+    b, h, w, vn, _ = vertex.shape
+    hyps, counts = [], []
+    for bi in range(b):
+        cur = mask[bi].byte()
+        fg = torch.sum(cur)
+        if fg < min_num:
+            raise NameError("name 'batch_win_pts' is not defined")
+        if fg > max_num:
+            u = torch.zeros(cur.shape, dtype=torch.float32).uniform_(0, 1)
+            cur = cur * (u < (max_num / fg.float()))
+        sel = cur.bool()
+        coords = torch.nonzero(sel).float()[:, [1, 0]]
+        direct = vertex[bi].masked_select(sel.unsqueeze(2).unsqueeze(3)).view([coords.shape[0], vn, 2])
+        idxs = idx_source(bi, round_hyp_num, vn, coords.shape[0]).contiguous()
+        hyp, inl = _vote_round(rv, direct, coords, idxs, inlier_thresh)
+        hyps.append(hyp)
+        counts.append(torch.sum(inl, 2))
+    return torch.stack(hyps), torch.stack(counts)
 
 
 def from_RTs_get_T_offset_errors(gt_rts, pred_rts) -> torch.Tensor:

@@ -131,3 +131,57 @@ def test_v4_v5(vn):
     assert helpers.rel_err(got_pts.reshape(-1, 2), want_pts.reshape(-1, 2)) <= helpers.REL_TOL
     # the confidence counts votes at the refined point: a last-ulp difference of that point can flip a borderline pixel
     assert float((got_conf.cpu() - want_conf).abs().max()) <= 2.0 / 600
+
+
+@pytest.mark.parametrize("vn", [1, 2])
+def test_v6(vn):
+    from fastposecnn_b200.ransac_voting_gpu_layer.ransac_voting_gpu import ransac_voting_layer_v6
+    from test_pvnet_variants_oracle import dense_scene
+    mask, vertex = dense_scene(vn)
+    hn = 40
+    draw, log = recorded(8)
+    want_pts, want_conf = port.ransac_voting_layer_v6(mask, vertex, hn, max_num=30000, idx_source=draw)
+    idxs = torch.zeros((mask.shape[0], hn, vn, 2), dtype=torch.int32)
+    for i, t in log:
+        idxs[i] = t
+    got_pts, got_conf = ransac_voting_layer_v6(mask.to(DEV), vertex.to(DEV), hn, max_num=30000, idxs=idxs.to(DEV))
+    assert got_pts.shape == want_pts.shape and got_conf.shape == want_conf.shape
+    assert helpers.rel_err(got_pts.reshape(-1, 2), want_pts.reshape(-1, 2)) <= helpers.REL_TOL
+    assert float((got_conf.cpu() - want_conf).abs().max()) <= 2.0 / 600
+    # the whole batch's foreground count decides the sub-sampling: every image thinned by max_num / sum(mask), same uniforms
+    u = torch.rand(mask.shape, generator=torch.Generator().manual_seed(5))
+    draw, log = recorded(9)
+    want_pts, want_conf = port.ransac_voting_layer_v6(mask, vertex, hn, max_num=900, idx_source=draw, select_u=u)
+    for i, t in log:
+        idxs[i] = t
+    got_pts, got_conf = ransac_voting_layer_v6(mask.to(DEV), vertex.to(DEV), hn, max_num=900, idxs=idxs.to(DEV), select_u=u.to(DEV))
+    assert helpers.rel_err(got_pts.reshape(-1, 2), want_pts.reshape(-1, 2)) <= helpers.REL_TOL
+    assert float((got_conf.cpu() - want_conf).abs().max()) <= 2.0 / 200
+    # ... and the skip: below min_num as a batch, zeros everywhere
+    got_pts, got_conf = ransac_voting_layer_v6(mask.to(DEV), vertex.to(DEV), hn, min_num=10 ** 6)
+    assert got_pts.shape == (3, vn, 2) and int(got_pts.abs().sum()) == 0 and int(got_conf.abs().sum()) == 0
+
+
+def test_center_motion_and_hypothesis_driver():
+    from fastposecnn_b200.ransac_voting_gpu_layer.ransac_voting_gpu import (generate_hypothesis, ransac_motion_voting,
+                                                                           ransac_voting_center)
+    from test_pvnet_variants_oracle import dense_scene, instance_scene
+    mask, vertex = instance_scene(2)
+    want = port.ransac_voting_center(mask, vertex[:, :, :, 0], 16, min_num=100)
+    got = ransac_voting_center(mask.to(DEV), vertex[:, :, :, 0].to(DEV), 16, min_num=100)
+    assert len(got) == len(want) == 2 and all(g.shape == w_.shape and int(g.abs().sum()) == 0 and g.is_cuda for g, w_ in zip(got, want))
+    want = port.ransac_motion_voting(mask, vertex)
+    got = ransac_motion_voting(mask.to(DEV), vertex.to(DEV))
+    assert got.shape == want.shape == (4, 2, 2) and int(got[3].abs().sum()) == 0
+    assert helpers.rel_err(got.reshape(-1, 2), want.reshape(-1, 2)) <= helpers.REL_TOL
+    mask, vertex = dense_scene(2)
+    hn = 24
+    draw, log = recorded(12)
+    want_h, want_c = port.generate_hypothesis(mask, vertex, hn, idx_source=draw)
+    idxs = torch.zeros((mask.shape[0], hn, 2, 2), dtype=torch.int32)
+    for i, t in log:
+        idxs[i] = t
+    got_h, got_c = generate_hypothesis(mask.to(DEV), vertex.to(DEV), hn, idxs=idxs.to(DEV))
+    assert got_c.dtype == want_c.dtype and torch.equal(got_h.cpu(), want_h) and torch.equal(got_c.cpu(), want_c)
+    with pytest.raises(RuntimeError, match="fewer than min_num"):
+        generate_hypothesis(*[t.to(DEV) for t in instance_scene(2)], hn)

@@ -83,3 +83,70 @@ def test_v4_v5_equal_reference(vn):
         b_pts, b_conf = ref.rvg.ransac_voting_layer_v5(mask, vertex, hn, max_num=30000)
     assert torch.equal(a_pts, b_pts) and torch.equal(a_conf, b_conf)
     assert torch.equal(a_conf[3], torch.zeros(vn)) and float(a_conf[:2, 0].min()) > 0.3
+
+
+def dense_scene(vn=1):
+    """every image has at least a handful of mask pixels (generate_hypothesis / v6 have no working skip branch per image)"""
+    frames = [[(30, 30, 14, 1)], [(64, 48, 22, 3)], [(100, 60, 6, 2), (40, 40, 9, 1)]]
+    logits = syn.render_heads(frames, 96, 128, seed=11)
+    cat = port.class_compression(logits, 7)
+    vertex = cat["xy"].permute(0, 2, 3, 1).unsqueeze(3)
+    if vn > 1:
+        vertex = torch.cat([vertex, vertex.flip(-1) * torch.tensor([1.0, -1.0])], dim=3)
+    return (cat["mask"] != 0).float(), vertex.contiguous()
+
+
+@pytest.mark.parametrize("vn", [1, 2])
+def test_v6_equals_reference(vn, capsys):
+    ref = ref_import.load()
+    mask, vertex = dense_scene(vn)
+    hn = 40
+    # (a) no sub-sampling (max_num above the batch's foreground count)
+    a_pts, a_conf = port.ransac_voting_layer_v6(mask, vertex, hn, max_num=30000, idx_source=port.seeded_idx_source(8))
+    with ref_import.fixed_idxs(port.seeded_idx_source(8), hn, vn), ref_import.legacy_uint8_masks():
+        b_pts, b_conf = ref.rvg.ransac_voting_layer_v6(mask, vertex, hn, max_num=30000)
+    assert a_pts.shape == b_pts.shape == (3, vn, 2) and torch.equal(a_pts, b_pts) and torch.equal(a_conf, b_conf)
+    assert float(a_conf[:2, 0].min()) > 0.3
+    # (b) the whole batch's count decides: sub-sampled by max_num / sum(mask) in every image (same RNG stream on both sides)
+    torch.manual_seed(77)
+    a_pts, a_conf = port.ransac_voting_layer_v6(mask, vertex, hn, max_num=900, idx_source=port.seeded_idx_source(8))
+    torch.manual_seed(77)
+    with ref_import.fixed_idxs(port.seeded_idx_source(8), hn, vn), ref_import.legacy_uint8_masks():
+        b_pts, b_conf = ref.rvg.ransac_voting_layer_v6(mask, vertex, hn, max_num=900)
+    assert torch.equal(a_pts, b_pts) and torch.equal(a_conf, b_conf)
+    # (c) whole batch below min_num: zeros for every image
+    a_pts, a_conf = port.ransac_voting_layer_v6(mask, vertex, hn, min_num=10 ** 6, idx_source=port.seeded_idx_source(8))
+    with ref_import.legacy_uint8_masks():
+        b_pts, b_conf = ref.rvg.ransac_voting_layer_v6(mask, vertex, hn, min_num=10 ** 6)
+    assert torch.equal(a_pts, b_pts) and torch.equal(a_conf, b_conf) and int(a_pts.abs().sum()) == 0
+    capsys.readouterr()            # the reference prints the mask's device (:880)
+
+
+def test_center_motion_and_hypothesis_driver_equal_reference():
+    ref = ref_import.load()
+    mask, vertex = instance_scene()
+    # ransac_voting_center: only the images below min_num contribute (a zero mask each); an image at or above min_num makes
+    # the reference raise (its masked_select at :636 broadcasts a [h,w,1,1] mask against the [h,w,2] field)
+    a = port.ransac_voting_center(mask[2:], vertex[2:, :, :, 0], 16, min_num=100)
+    with ref_import.legacy_uint8_masks():
+        b = ref.rvg.ransac_voting_center(mask[2:], vertex[2:, :, :, 0], 16, min_num=100)
+        with pytest.raises(RuntimeError):
+            ref.rvg.ransac_voting_center(mask, vertex[:, :, :, 0], 16, min_num=100)
+    assert len(a) == len(b) == 2 and all(torch.equal(x, y) and x.shape == (96, 128) for x, y in zip(a, b))
+    # ransac_motion_voting
+    mask2, vertex2 = instance_scene(2)
+    with ref_import.legacy_uint8_masks():
+        want = ref.rvg.ransac_motion_voting(mask2, vertex2)
+    got = port.ransac_motion_voting(mask2, vertex2)
+    assert got.shape == want.shape == (4, 2, 2) and torch.equal(got, want) and int(got[3].abs().sum()) == 0
+    # generate_hypothesis (the driver at :991, not the native kernel)
+    mask3, vertex3 = dense_scene(2)
+    hn = 24
+    a_h, a_c = port.generate_hypothesis(mask3, vertex3, hn, idx_source=port.seeded_idx_source(12))
+    with ref_import.fixed_idxs(port.seeded_idx_source(12), hn, 2), ref_import.legacy_uint8_masks():
+        b_h, b_c = ref.rvg.generate_hypothesis(mask3, vertex3, hn)
+    assert a_h.shape == (3, hn, 2, 2) and torch.equal(a_h, b_h) and a_c.dtype == b_c.dtype and torch.equal(a_c, b_c)
+    with pytest.raises(NameError), ref_import.legacy_uint8_masks():
+        ref.rvg.generate_hypothesis(mask, vertex, hn)                 # image 3 of instance_scene is empty
+    with pytest.raises(NameError):
+        port.generate_hypothesis(mask, vertex, hn)
