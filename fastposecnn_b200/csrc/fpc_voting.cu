@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k_voting_for_hypothesis_vp(const float *_
 // ransac_voting_gpu.py:562-566).
 //
 // Exactness.  The reference decides   cos = dot(d,n) / (|n| |d|) > t,  d = fl(h - c),  in rounded binary32 ops; its
-// rounded cosine is within (8 + 1/t) u of the cosine of the exact d = h - c (u = 2^-24; one u of that is fl(h - c)).
+// rounded cosine is within (7 + 1/t + T(t)) u of the cosine of the exact d = h - c (u = 2^-24; the T(t) u is fl(h - c)).
 // The fast test works in tangent form, far better conditioned next to cos = 1:  with U = d.n and W = d x n,
 //   cos > c  <=>  U > 0 and |W| < T(c) U,   T(c) = sqrt(1 - c^2) / c.
 // FIVE fused multiply-adds per vote.  Every block first re-expresses the chunk it staged in instance-local
@@ -153,12 +153,12 @@ __global__ void __launch_bounds__(256) k_voting_for_hypothesis_vp(const float *_
 // with one LEA.HI per vote.  The absolute error of U and W is <= 8u (|h'x| + |h'y| + Rx + Ry) =: E (Rx, Ry = half
 // extents of the bounding box), so the answer is certain as soon as
 //   |s| >= delta(h) = 1.01 [ max(T_lo - tau, tau - T_hi) (|d|max + E) + (1 + T_lo) E ],   |d|max = |h'| + |(Rx, Ry)|,
-// T_hi = T(t (1 + eps)), T_lo = T(t (1 - eps)), eps = 1.25 (9 + 1/t) u  (derivation in DESIGN.md).  The hot loop only
-// tracks  m = min |s|  per hypothesis over a 16-pixel round (one 3-input FMNMX per two votes) and leaves a one-word
-// note per (lane, round); rounds with m < delta (about one vote in 10^3 lands there) are re-examined after the
-// loop -- bit-identical s, one thread per note -- and their uncertain votes are settled by all lanes in parallel with
-// the reference expression itself (explicitly rounded intrinsics, original operands re-read from the record planes),
-// which corrects the fast count.  Hypotheses within 1e-3 of a pixel-lattice point (where |d| may fall under the
+// T_hi = T(t (1 + eps)), T_lo = T(t (1 - eps)), eps = 1.02 (7 + 1/t + T(t)) u  (vote_consts; derivation in DESIGN.md).  The hot loop only
+// tracks  m = min |s|  per hypothesis over VHALF = 8 pixels (one 3-input FMNMX per two votes) and leaves a one-word
+// note per (lane, 8 pixels); notes with m < delta (about one vote in 10^3 lands there) are handed to k_vote_settle,
+// which recomputes the bit-identical s of their 8 pixels -- one thread per (note, pixel) -- and settles the uncertain
+// ones with the reference expression itself (explicitly rounded intrinsics, original operands re-read from the record
+// planes), correcting the fast count.  Hypotheses within 1e-3 of a pixel-lattice point (where |d| may fall under the
 // reference's 1e-6 guard), non-finite or absurdly far hypotheses have ALL their votes settled that way; pixels whose
 // direction the reference's |n| < 1e-6 guard skips are given pw = 1e30 (never an inlier), pixels with an absurd |n|
 // get n = 0, pw = 0 (s = 0: always uncertain).

@@ -41,6 +41,7 @@ def main():
     agg = {}
     for r in rows[2:]:
         name = re.sub(r"^(void )?(fpc::)?", "", r[ik]).split("<")[0].split("(")[0]
+        name = re.sub(r"^(k_argmax_runs|k_emit_runs)(_[a-z]+\d+|\d+)$", r"\1", name)     # variants report under bench.py's kernel name
         a = agg.setdefault(name, {"n": 0, **{k: 0.0 for k in idx}})
         a["n"] += 1
         for k, i in idx.items():
