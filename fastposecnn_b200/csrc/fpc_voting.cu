@@ -410,12 +410,17 @@ __device__ __forceinline__ void prepare_pixel_rare(float ocx, float ocy, float &
     pu = X; pw = Y; nx = NX; ny = NY;
 }
 
-#ifndef FPC_VOTE_MINB
-#define FPC_VOTE_MINB 3
+// Register cap: 64 per thread, so that the kernel's two blocks per SM hold exactly half of the register file and two blocks of
+// the bandwidth-bound kernels of the other batches in flight (arg-max: 2 x 14k registers, gather: 2 x 16k) fit beside them.  At 80
+// registers (what the compiler takes without a cap) only one of those blocks fits and the kernels of different batches take turns
+// instead of sharing the SMs: the hot loop is the same 294 instructions either way, the kernel alone is 2 % slower at 64, the
+// pipelined step 4 % (cfg2) to 7 % (cfg4) faster (profiles/r02_ab_vote_registers.txt).
+#ifndef FPC_VOTE_MAXREG
+#define FPC_VOTE_MAXREG 64
 #endif
 
 template <int ARITH, bool PACKED>
-__global__ void __launch_bounds__(VT, FPC_VOTE_MINB) k_vote(InstTables T, int *__restrict__ counters, PathParams pp, RecPlanes rec,
+__global__ void __maxnreg__(FPC_VOTE_MAXREG) k_vote(InstTables T, int *__restrict__ counters, PathParams pp, RecPlanes rec,
                                                             const float2 *__restrict__ hyp_g, const float4 *__restrict__ hloc_g,
                                                             int *__restrict__ votes, const int4 *__restrict__ work,
                                                             const float4 *__restrict__ workf, uint4 *__restrict__ segs,
@@ -1180,9 +1185,9 @@ static int launch_vote_t(const Workspace &ws, const PathParams &pp, const float2
         FPC_CUDA_TRY(cudaFuncSetAttribute(k_vote<ARITH, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_vote<ARITH, PACKED>, VT, smem) != cudaSuccess || n < 1) n = 2;
-        // Two blocks per SM by default although three fit: the hot loop saturates the issue ports with two warps per
-        // scheduler, and the third block's registers are worth more to the kernels of the other batches in flight (measured:
-        // the kernel alone is 2 % slower, the pipelined step 3 % faster).  FPC_VOTE_BLOCKS_PER_SM overrides.
+        // Two blocks per SM (that is also what the shared-memory buffers allow): the hot loop saturates the issue ports with two
+        // warps per scheduler, and the rest of the SM is worth more to the kernels of the other batches in flight.
+        // FPC_VOTE_BLOCKS_PER_SM=1 overrides (experiments).
         const char *e = getenv("FPC_VOTE_BLOCKS_PER_SM");
         n = std::min(n, (e && atoi(e) >= 1) ? atoi(e) : 2);
         blocks_per_sm = n;
