@@ -587,9 +587,13 @@ def run_cfg5(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that cannot complete fails after two minutes instead of holding the GPUs until the job is killed
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     b, h, w, C, hn = args.batch_per_gpu or 64, 480, 640, 7, 128
-    torch.manual_seed(1234 + rank)
+    # the SAME random network and images on every rank: the instance count, hence the grown table capacity, hence the size of the
+    # all-gather buffers must agree across ranks (with per-rank seeds the 8-GPU run hung in the collective)
+    torch.manual_seed(1234)
     net = TorchFeeder(C).to(dev).eval()
     host_imgs = torch.randn(b, 3, h, w).pin_memory()
     imgs = torch.empty((b, 3, h, w), device=dev)
@@ -653,6 +657,11 @@ def run_cfg5(args):
             torch.cuda.current_stream(dev).wait_stream(side)
             table_host = torch.empty((eng.max_instances, _lib.POSE_ROW), dtype=torch.float32).pin_memory()
             gathered = torch.empty((world,) + tuple(eng.table_full.shape), dtype=torch.float32, device=dev) if world > 1 else None
+            if world > 1:
+                cap = torch.tensor([eng.max_instances, -eng.max_instances], dtype=torch.int64, device=dev)
+                dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+                if int(cap[0]) != -int(cap[1]):
+                    raise RuntimeError(f"cfg5: table capacities differ across ranks ({-int(cap[1])}..{int(cap[0])}); the all-gather needs equal sizes")
 
             def step(g, read_table):
                 g.replay()
