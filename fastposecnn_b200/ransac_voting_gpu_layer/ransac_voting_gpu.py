@@ -256,20 +256,26 @@ def ransac_voting_center(mask, vertex, round_hyp_num, inlier_thresh=0.99, confid
     return [torch.zeros((h, w), dtype=torch.float32, device=mask.device) for bi in range(b) if few[bi]]
 
 
+def _motion_mean(mask, vertex):
+    """[b,vn,2] mean over the mask's pixels of (pixel (x, y) + its vector); zeros for an empty mask.  Device-agnostic torch."""
+    b, h, w, vn, _ = vertex.shape
+    m = (mask.byte() != 0)
+    n = m.flatten(1).sum(dim=1).to(torch.float32)                                   # [b]
+    ys = torch.arange(h, dtype=torch.float32, device=vertex.device).view(1, h, 1)
+    xs = torch.arange(w, dtype=torch.float32, device=vertex.device).view(1, 1, w)
+    zero = torch.zeros((), dtype=torch.float32, device=vertex.device)
+    centre = torch.stack((torch.where(m, xs, zero).flatten(1).sum(dim=1), torch.where(m, ys, zero).flatten(1).sum(dim=1)), dim=1)
+    # select, do not multiply: values outside the mask (possibly NaN / inf) must not reach the sums -- the reference indexes
+    total = torch.where(m.view(b, h, w, 1, 1), vertex, zero).flatten(1, 2).sum(dim=1) + centre.unsqueeze(1)    # [b,vn,2]
+    return torch.where((n > 0).view(b, 1, 1), total / n.clamp_min(1).view(b, 1, 1), torch.zeros_like(total))
+
+
 def ransac_motion_voting(mask, vertex):
     """ransac_voting_gpu.py:968-989 -> ``[b,vn,2]``: mean over the mask's pixels of (pixel (x, y) + its vector); zeros for an
     empty mask.  Two batched masked sums instead of the per-image loop (sums in another order: <= 1e-5 relative)."""
     mask = _lib.require_cuda(mask, "mask", None, contiguous=False)
     vertex = _lib.require_cuda(vertex, "vertex", torch.float32, contiguous=False)
-    b, h, w, vn, _ = vertex.shape
-    m = (mask.byte() != 0)
-    n = m.flatten(1).sum(dim=1).to(torch.float32)                                   # [b]
-    mf = m.to(torch.float32)
-    ys = torch.arange(h, dtype=torch.float32, device=vertex.device).view(1, h, 1)
-    xs = torch.arange(w, dtype=torch.float32, device=vertex.device).view(1, 1, w)
-    centre = torch.stack(((mf * xs).flatten(1).sum(dim=1), (mf * ys).flatten(1).sum(dim=1)), dim=1)      # [b,2]
-    total = (vertex * mf.view(b, h, w, 1, 1)).flatten(1, 2).sum(dim=1) + centre.unsqueeze(1)              # [b,vn,2]
-    return torch.where((n > 0).view(b, 1, 1), total / n.clamp_min(1).view(b, 1, 1), torch.zeros_like(total))
+    return _motion_mean(mask, vertex)
 
 
 def generate_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,

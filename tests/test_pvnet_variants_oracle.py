@@ -150,3 +150,19 @@ def test_center_motion_and_hypothesis_driver_equal_reference():
         ref.rvg.generate_hypothesis(mask, vertex, hn)                 # image 3 of instance_scene is empty
     with pytest.raises(NameError):
         port.generate_hypothesis(mask, vertex, hn)
+
+
+def test_motion_mean_host_logic_ignores_values_outside_the_mask():
+    """The drop-in's batched masked sums (device-agnostic torch) against the oracle's per-image loop, with NaN / inf planted
+    outside the mask: the reference indexes the masked pixels, so they must not matter."""
+    from fastposecnn_b200.ransac_voting_gpu_layer.ransac_voting_gpu import _motion_mean
+    mask, vertex = instance_scene(2)
+    vertex = vertex.clone()
+    outside = mask == 0
+    vertex[outside] = float("nan")
+    vertex[0, 0, 0] = float("inf")
+    want = port.ransac_motion_voting(mask, vertex)
+    got = _motion_mean(mask, vertex)
+    assert torch.isfinite(got).all() and got.shape == want.shape
+    assert float(((got - want).norm(dim=-1) / want.norm(dim=-1).clamp_min(1e-6)).max()) <= 1e-5
+    assert int(got[3].abs().sum()) == 0
