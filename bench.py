@@ -592,7 +592,7 @@ def run_cfg5(args):
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     b, h, w, C, hn = args.batch_per_gpu or 64, 480, 640, 7, 128
     # the SAME random network and images on every rank: the instance count, hence the grown table capacity, hence the size of the
-    # all-gather buffers must agree across ranks (with per-rank seeds the 8-GPU run hung in the collective)
+    # all-gather buffers must agree across ranks (with per-rank seeds the 8-GPU run hung; unequal buffers are the likely cause)
     torch.manual_seed(1234)
     net = TorchFeeder(C).to(dev).eval()
     host_imgs = torch.randn(b, 3, h, w).pin_memory()
