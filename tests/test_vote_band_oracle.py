@@ -73,14 +73,19 @@ def test_fma32_is_a_single_rounding():
 
 
 # ---- the two sides ---------------------------------------------------------------------------------------------------
-def reference_inlier(cx, cy, nx, ny, hx, hy, t):
-    """ransac_voting_kernel.cu:112-125, FPC_ARITH_IEEE: every operation rounded to binary32 separately."""
+def reference_inlier(cx, cy, nx, ny, hx, hy, t, nvcc_fma=False):
+    """ransac_voting_kernel.cu:112-125.  FPC_ARITH_IEEE: every operation rounded to binary32 separately (a CPU build);
+    nvcc_fma: the contraction nvcc makes of the same source, a*b + c*d -> fma(a, b, c*d) (FPC_ARITH_NVCC_FMA)."""
+    def sum_prod(a, b, c, d):
+        cd = (c * d).astype(f32)
+        a, b, cd = np.broadcast_arrays(a, b, cd)
+        return fma32(a, b, cd).reshape(cd.shape) if nvcc_fma else ((a * b).astype(f32) + cd).astype(f32)
     dx, dy = (hx - cx).astype(f32), (hy - cy).astype(f32)
-    norm1 = np.sqrt((nx * nx).astype(f32) + (ny * ny).astype(f32), dtype=f32)
-    norm2 = np.sqrt((dx * dx).astype(f32) + (dy * dy).astype(f32), dtype=f32)
+    norm1 = np.sqrt(sum_prod(nx, nx, ny, ny), dtype=f32)
+    norm2 = np.sqrt(sum_prod(dx, dx, dy, dy), dtype=f32)
     skip = (norm1 <= f32(1e-6)) | (norm2 <= f32(1e-6))
     with np.errstate(divide="ignore", invalid="ignore"):
-        ang = (((dx * nx).astype(f32) + (dy * ny).astype(f32)).astype(f32) / (norm1 * norm2).astype(f32)).astype(f32)
+        ang = (sum_prod(dx, nx, dy, ny) / (norm1 * norm2).astype(f32)).astype(f32)
     return ~skip & (ang > f32(t))
 
 
@@ -144,7 +149,7 @@ def on_fast_path(hx, hy, lx, ly):
     return ~near_lattice & ((np.abs(lx) + np.abs(ly)) < f32(1e12))
 
 
-def check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag):
+def check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag, nvcc_fma=False):
     """all hypotheses x all pixels; returns (votes checked outside the band, votes inside the band)"""
     ntau, half_w, opt = vote_consts(t)
     lx, ly = (hx - ox).astype(f32), (hy - oy).astype(f32)                          # k_hypotheses: hloc
@@ -154,7 +159,7 @@ def check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag):
     delta = band_delta(lx, ly, rsum, rdiag, half_w, opt) * f32(1 - 1e-5)
     H, P = hx[:, None], px[None, :]
     s = fast_s(P, py[None, :], nx[None, :], ny[None, :], lx[:, None], ly[:, None], ox, oy, ntau)
-    ref = reference_inlier(P, py[None, :], nx[None, :], ny[None, :], H, hy[:, None], t)
+    ref = reference_inlier(P, py[None, :], nx[None, :], ny[None, :], H, hy[:, None], t, nvcc_fma)
     certain = np.abs(s) >= delta[:, None]
     wrong = certain & ((s < 0) != ref)
     assert not wrong.any(), (f"t={t}: {int(wrong.sum())} votes outside the band disagree with the reference, e.g. "
@@ -162,8 +167,9 @@ def check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag):
     return int(certain.sum()), int((~certain).sum())
 
 
+@pytest.mark.parametrize("nvcc_fma", [False, True], ids=["ieee", "nvcc_fma"])
 @pytest.mark.parametrize("t", [0.999, 0.99, 0.9])
-def test_sign_of_s_is_the_reference_answer_outside_the_band(t):
+def test_sign_of_s_is_the_reference_answer_outside_the_band(t, nvcc_fma):
     rng = np.random.default_rng(int(t * 1000))
     total_certain = total_band = 0
     for radius, cx0, cy0, noise in ((35, 320, 240, 0.6), (12, 53, 460, 0.2), (60, 600, 70, 2.0)):
@@ -172,15 +178,16 @@ def test_sign_of_s_is_the_reference_answer_outside_the_band(t):
         # random hypotheses: around the centre (where RANSAC puts them), across the box, and far outside
         hx = np.concatenate([cx0 + rng.standard_normal(24) * 1.5, cx0 + rng.uniform(-radius, radius, 12), cx0 + rng.uniform(-3000, 3000, 6)]).astype(f32)
         hy = np.concatenate([cy0 + rng.standard_normal(24) * 1.5, cy0 + rng.uniform(-radius, radius, 12), cy0 + rng.uniform(-3000, 3000, 6)]).astype(f32)
-        c, b = check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag)
+        c, b = check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag, nvcc_fma)
         total_certain += c
         total_band += b
     # the band is what k_vote_settle pays for: it must stay a small share of random votes
     assert total_band < 0.02 * (total_certain + total_band)
 
 
+@pytest.mark.parametrize("nvcc_fma", [False, True], ids=["ieee", "nvcc_fma"])
 @pytest.mark.parametrize("t", [0.999, 0.99])
-def test_hypotheses_on_the_threshold_cone(t):
+def test_hypotheses_on_the_threshold_cone(t, nvcc_fma):
     """Adversarial: every hypothesis is built from a pixel c and its direction n so that the angle between n and h - c is the
     threshold angle scaled by 1 +- k ulp-sized steps: those votes sit in or right next to the band.  Outside the band the
     sign must still be the reference's answer; and the construction must really exercise the band (many votes inside it)."""
@@ -204,7 +211,7 @@ def test_hypotheses_on_the_threshold_cone(t):
     delta = band_delta(lx, ly, rsum, rdiag, half_w, opt)
     s_own = fast_s(px[pick], py[pick], nx[pick], ny[pick], lx, ly, ox, oy, ntau)   # each hypothesis against ITS pixel
     assert (np.abs(s_own) < delta).mean() > 0.5                                    # the construction does land in the band
-    check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag)
+    check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag, nvcc_fma)
 
 
 def test_lattice_and_far_hypotheses_stay_off_the_fast_path():
