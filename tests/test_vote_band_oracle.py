@@ -113,8 +113,21 @@ def band_delta(lx, ly, rsum, rdiag, half_w, one_plus_tlo):
     return (f32(1.01) * (inner + (one_plus_tlo * E).astype(f32)).astype(f32)).astype(f32)
 
 
+def scale_direction(nx, ny):
+    """prepare_pixel_rare: a direction whose squared norm lies outside [0.25, 1.0002] is scaled by a power of two (exact) so
+    that it lands in [0.25, 1); directions the fast prepare accepts stay as they are."""
+    nn = ((nx * nx).astype(f32) + (ny * ny).astype(f32)).astype(f32)
+    fast = (nn <= f32(1.0002)) & (nn >= f32(0.25))
+    e2 = ((nn.view(np.uint32) >> 23) & 0xFF).astype(np.int64) - 127
+    sh = (e2 + 2) >> 1
+    sc = ((127 - sh).astype(np.uint32) << 23).view(f32)
+    sc = np.where(fast, f32(1), sc)
+    return (nx * sc).astype(f32), (ny * sc).astype(f32)
+
+
 def fast_s(cx, cy, nx, ny, lx, ly, ox, oy, ntau):
-    """prepare_pixel_fast + vote_s (FPC_ARITH_IEEE): the same five roundings in the same order."""
+    """prepare_pixel_fast / prepare_pixel_rare + vote_s (FPC_ARITH_IEEE): the same roundings in the same order."""
+    nx, ny = scale_direction(nx, ny)
     ccx, ccy = (cx - ox).astype(f32), (cy - oy).astype(f32)                       # exact: integers
     pu = -fma32(ccx, nx, (ccy * ny).astype(f32))
     pw = -fma32(ccx, ny, -(ccy * nx).astype(f32))
@@ -212,6 +225,24 @@ def test_hypotheses_on_the_threshold_cone(t, nvcc_fma):
     s_own = fast_s(px[pick], py[pick], nx[pick], ny[pick], lx, ly, ox, oy, ntau)   # each hypothesis against ITS pixel
     assert (np.abs(s_own) < delta).mean() > 0.5                                    # the construction does land in the band
     check(t, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag, nvcc_fma)
+
+
+@pytest.mark.parametrize("scale", [3e-4, 0.3, 7.0, 4e4])
+def test_unnormalised_directions_of_the_voting_drop_in(scale):
+    """ransac_voting_layer* accept any direction field: the kernel scales a direction by a power of two into [1/2, 1) before the
+    fast test (the reference's cosine does not depend on |n|).  Same claim, directions of norm `scale` (x 1..2)."""
+    rng = np.random.default_rng(11)
+    px, py, ox, oy, rsum, rdiag = disc_instance(rng, 20, 100, 90)
+    nx, ny = unit_directions(rng, px, py, 100.3, 89.6, 0.4)
+    k = (scale * rng.uniform(1.0, 2.0, px.shape)).astype(f32)
+    nx, ny = (nx * k).astype(f32), (ny * k).astype(f32)
+    sx, sy = scale_direction(nx, ny)
+    snn = sx.astype(np.float64) ** 2 + sy.astype(np.float64) ** 2
+    assert snn.min() >= 0.2499 and snn.max() <= 1.0003
+    hx = (100 + rng.standard_normal(40) * 2.0).astype(f32)
+    hy = (90 + rng.standard_normal(40) * 2.0).astype(f32)
+    certain, band = check(0.999, px, py, nx, ny, hx, hy, ox, oy, rsum, rdiag)
+    assert band < 0.02 * (certain + band)
 
 
 def test_lattice_and_far_hypotheses_stay_off_the_fast_path():
